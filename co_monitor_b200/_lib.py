@@ -1,0 +1,198 @@
+"""ctypes binding of ``libcomonitor_sm100.so`` (the C ABI in ``include/comonitor_sm100.h``).
+
+The library is the product: there is no Python/NumPy fallback.  If it has not been built
+(``python -m co_monitor_b200.csrc.build`` / ``__graft_entry__.build()``) loading raises
+``ComonitorLibraryError``; compute entry points raise ``ComonitorError`` on any non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcomonitor_sm100.so")
+
+COM_OK, COM_E_BADARG, COM_E_CUDA, COM_E_NOMEM, COM_E_OVERFLOW, COM_E_GEOMETRY, COM_E_EMPTY = 0, -1, -2, -3, -4, -5, -6
+COM_MAX_EDGES = 32
+
+
+class ComonitorLibraryError(ImportError):
+    pass
+
+
+class ComonitorError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str):
+        self.code = code
+        super().__init__(f"{where}: {detail} (status {code})")
+
+
+c_double3 = C.c_double * 3
+
+
+class ComAperture(C.Structure):
+    _fields_ = [
+        ("p1", c_double3),
+        ("normal", c_double3),
+        ("e1", c_double3),
+        ("e2", c_double3),
+        ("n_edges", C.c_int32),
+        ("reserved", C.c_int32),
+        ("edge", (C.c_double * 3) * COM_MAX_EDGES),
+        ("vertex", (C.c_double * 2) * COM_MAX_EDGES),
+    ]
+
+    def edges(self) -> np.ndarray:
+        return np.array([list(self.edge[k]) for k in range(self.n_edges)])
+
+    def vertices(self) -> np.ndarray:
+        return np.array([list(self.vertex[k]) for k in range(self.n_edges)])
+
+
+class ComSceneDesc(C.Structure):
+    _fields_ = [
+        ("n_crystal", C.c_int32),
+        ("n_slits", C.c_int32),
+        ("crystal_xyz", C.POINTER(C.c_double)),
+        ("crystal_normal", C.POINTER(C.c_double)),
+        ("slit_crys_side", C.POINTER(C.c_double)),
+        ("slit_plasma_side", C.POINTER(C.c_double)),
+        ("slit_depth", c_double3),
+        ("n_port_vertices", C.c_int32),
+        ("n_detector_vertices", C.c_int32),
+        ("port_vertices", C.POINTER(C.c_double)),
+        ("port_depth", c_double3),
+        ("detector_vertices", C.POINTER(C.c_double)),
+        ("detector_depth", c_double3),
+        ("origin", c_double3),
+        ("area_pt", C.c_double),
+        ("refl_max", C.c_double),
+        ("aoi0", C.c_double),
+        ("refl_sigma", C.c_double),
+        ("filter_eps_mm", C.c_double),
+        ("apertures_override", C.POINTER(ComAperture)),
+        ("near_edge_mm", C.c_double),
+        ("n_voxel_corners", C.c_int32),
+        ("reserved", C.c_int32),
+        ("voxel_corners", (C.c_double * 3) * 8),
+    ]
+
+
+class ComLattice(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int64),
+        ("ny", C.c_int64),
+        ("nz", C.c_int64),
+        ("start", c_double3),
+        ("step", c_double3),
+        ("stop", c_double3),
+        ("centre", c_double3),
+        ("rotation", C.c_double * 9),
+        ("shift", c_double3),
+    ]
+
+
+class ComStats(C.Structure):
+    _fields_ = [
+        ("tests", C.c_uint64),
+        ("candidates", C.c_uint64),
+        ("passing_rays", C.c_uint64),
+        ("near_edge_rays", C.c_uint64),
+        ("visible_voxels", C.c_uint64),
+        ("candidate_capacity", C.c_uint64),
+        ("overflow", C.c_uint64),
+        ("reserved", C.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
+
+
+RAY_RECORD_DTYPE = np.dtype(
+    [("ray_index", np.int64), ("distance", np.float64), ("aoi", np.float64), ("weight", np.float64)]
+)
+STATS_DTYPE = np.dtype([(name, np.uint64) for name, _ in ComStats._fields_])
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, u64p, dp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+    lib.com_abi_version.restype = C.c_int
+    lib.com_last_error.restype = C.c_char_p
+    lib.com_error_string.restype = C.c_char_p
+    lib.com_error_string.argtypes = [C.c_int]
+    lib.com_aperture_from_slab.argtypes = [dp, i32, dp, C.POINTER(ComAperture)]
+    lib.com_aperture_contains.argtypes = [C.POINTER(ComAperture), dp]
+    lib.com_scene_create.argtypes = [C.POINTER(ComSceneDesc), C.POINTER(vp)]
+    lib.com_scene_destroy.argtypes = [vp]
+    lib.com_scene_aperture_count.argtypes = [vp]
+    lib.com_scene_get_aperture.argtypes = [vp, i32, C.POINTER(ComAperture)]
+    lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), dp]
+    lib.com_visibility_workspace_bytes.restype = C.c_size_t
+    lib.com_visibility_workspace_bytes.argtypes = [vp, i64, C.c_double]
+    lib.com_visibility_weights.argtypes = [
+        vp, C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, C.c_size_t, vp,
+    ]
+    lib.com_visibility_weights_host.argtypes = [
+        C.POINTER(ComSceneDesc), C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, u64p, C.POINTER(ComStats),
+    ]
+    lib.com_compact_workspace_bytes.restype = C.c_size_t
+    lib.com_compact_workspace_bytes.argtypes = [i64]
+    lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
+    return lib
+
+
+#: every symbol include/comonitor_sm100.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED_SYMBOLS = [
+    "com_abi_version", "com_last_error", "com_error_string",
+    "com_aperture_from_slab", "com_aperture_contains",
+    "com_scene_create", "com_scene_destroy", "com_scene_aperture_count", "com_scene_get_aperture",
+    "com_scene_filter_info",
+    "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
+    "com_compact_workspace_bytes", "com_compact_visible",
+]
+
+
+def load():
+    """Load the shared library (once).  Raises ComonitorLibraryError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ComonitorLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -m co_monitor_b200.csrc.build` "
+                "(there is no CPU fallback for the accelerated path)"
+            )
+        try:
+            _lib = _declare(C.CDLL(LIB_PATH))
+        except OSError as exc:  # pragma: no cover
+            raise ComonitorLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+    return _lib
+
+
+def check(code: int, where: str) -> None:
+    if code != COM_OK:
+        lib = load()
+        detail = lib.com_last_error().decode() or lib.com_error_string(code).decode()
+        raise ComonitorError(code, where, detail)
+
+
+def as_double_ptr(arr: np.ndarray):
+    assert arr.dtype == np.float64 and arr.flags.c_contiguous
+    return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def aperture_from_slab(vertices: np.ndarray, offset: np.ndarray) -> ComAperture:
+    """Host-only: plane + polygon of one aperture (no GPU needed)."""
+    lib = load()
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    o = np.ascontiguousarray(np.asarray(offset, dtype=np.float64).reshape(3))
+    ap = ComAperture()
+    check(lib.com_aperture_from_slab(as_double_ptr(v), len(v), as_double_ptr(o), C.byref(ap)), "com_aperture_from_slab")
+    return ap
+
+
+def aperture_contains(ap: ComAperture, point) -> bool:
+    p = np.ascontiguousarray(point, dtype=np.float64)
+    return bool(load().com_aperture_contains(C.byref(ap), as_double_ptr(p)))

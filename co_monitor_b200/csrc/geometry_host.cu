@@ -1,0 +1,413 @@
+// Host-side geometry analysis (pure CPU, fp64): apertures -> plane + convex polygon, and the FP32
+// filter tables derived from them.  No CUDA calls in this file.
+//
+// Reference semantics reduced here:
+//   simulation.py:198-200   plane normal N = (p2-p1) x (p3-p2), plane point p1
+//   simulation.py:226-231   slab = vertices +/- orientation_vector
+//   simulation.py:260-261   Delaunay(slab).find_simplex(X) >= 0   with X on the plane
+// => X passes iff it lies in the cross-section polygon of conv(slab) with the plane.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "scene.h"
+
+namespace com {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_error; }
+
+namespace {
+
+struct V3 {
+  double x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double norm(V3 a) { return std::sqrt(dot(a, a)); }
+inline V3 load(const double* p) { return {p[0], p[1], p[2]}; }
+inline void store(double* p, V3 a) { p[0] = a.x, p[1] = a.y, p[2] = a.z; }
+
+struct P2 {
+  double x, y;
+};
+inline double cross2(P2 o, P2 a, P2 b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); }
+
+// Andrew monotone chain, counter-clockwise, strictly convex (collinear points dropped).
+std::vector<P2> convex_hull(std::vector<P2> pts, double merge_tol, double flat_tol) {
+  std::sort(pts.begin(), pts.end(), [](P2 a, P2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+  std::vector<P2> uniq;
+  for (auto p : pts) {
+    bool dup = false;
+    for (auto q : uniq)
+      if (std::hypot(p.x - q.x, p.y - q.y) <= merge_tol) {
+        dup = true;
+        break;
+      }
+    if (!dup) uniq.push_back(p);
+  }
+  pts.swap(uniq);
+  std::sort(pts.begin(), pts.end(), [](P2 a, P2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+  size_t n = pts.size();
+  if (n < 3) return pts;
+  std::vector<P2> h(2 * n);
+  size_t k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    while (k >= 2 && cross2(h[k - 2], h[k - 1], pts[i]) <= 0) --k;
+    h[k++] = pts[i];
+  }
+  for (size_t i = n - 1, t = k + 1; i > 0; --i) {
+    while (k >= t && cross2(h[k - 2], h[k - 1], pts[i - 1]) <= 0) --k;
+    h[k++] = pts[i - 1];
+  }
+  h.resize(k - 1);
+  // drop vertices that stick out of the line through their neighbours by less than flat_tol:
+  // such an edge pair has no numerical meaning at the reference's own round-off level.
+  bool changed = true;
+  while (changed && h.size() > 3) {
+    changed = false;
+    for (size_t i = 0; i < h.size(); ++i) {
+      P2 a = h[(i + h.size() - 1) % h.size()], b = h[i], c = h[(i + 1) % h.size()];
+      double len = std::hypot(c.x - a.x, c.y - a.y);
+      if (len == 0 || std::fabs(cross2(a, c, b)) / len < flat_tol) {
+        h.erase(h.begin() + i);
+        changed = true;
+        break;
+      }
+    }
+  }
+  return h;
+}
+
+void edges_from_vertices(const std::vector<P2>& v, double (*edge)[3]) {
+  size_t n = v.size();
+  for (size_t k = 0; k < n; ++k) {
+    P2 a = v[k], b = v[(k + 1) % n];
+    double dx = b.x - a.x, dy = b.y - a.y, len = std::hypot(dx, dy);
+    double ea = -dy / len, eb = dx / len;  // inward normal of a CCW polygon
+    edge[k][0] = ea;
+    edge[k][1] = eb;
+    edge[k][2] = -(ea * a.x + eb * a.y);
+  }
+}
+
+}  // namespace
+
+int aperture_from_slab(const double* verts, int n, const double* offset, ComAperture* out) {
+  if (!verts || !offset || !out || n < 3 || n > 16) {
+    set_error("com_aperture_from_slab: need 3..16 vertices (got %d)", n);
+    return COM_E_BADARG;
+  }
+  std::memset(out, 0, sizeof(*out));
+  V3 p1 = load(verts), p2 = load(verts + 3), p3 = load(verts + 6), off = load(offset);
+  V3 N = cross(p2 - p1, p3 - p2);
+  double nn = norm(N), l12 = norm(p2 - p1);
+  if (!(nn > 0) || !(l12 > 0)) {
+    set_error("aperture plane is degenerate (first three vertices collinear)");
+    return COM_E_GEOMETRY;
+  }
+  V3 nh = (1.0 / nn) * N, e1 = (1.0 / l12) * (p2 - p1), e2 = cross(nh, e1);
+  store(out->p1, p1), store(out->normal, N), store(out->e1, e1), store(out->e2, e2);
+
+  std::vector<V3> slab;
+  for (int i = 0; i < n; ++i) slab.push_back(load(verts + 3 * i) + off);
+  for (int i = 0; i < n; ++i) slab.push_back(load(verts + 3 * i) - off);
+  std::vector<double> dist(slab.size());
+  double scale = 0;
+  for (size_t i = 0; i < slab.size(); ++i) {
+    dist[i] = dot(nh, slab[i] - p1);
+    scale = std::max(scale, norm(slab[i] - p1));
+  }
+  const double on_plane = 1e-12 * std::max(1.0, scale);
+  std::vector<P2> pts;
+  auto push = [&](V3 X) { pts.push_back({dot(X - p1, e1), dot(X - p1, e2)}); };
+  for (size_t i = 0; i < slab.size(); ++i) {
+    if (std::fabs(dist[i]) <= on_plane) push(slab[i]);
+    for (size_t j = i + 1; j < slab.size(); ++j)
+      if ((dist[i] < -on_plane && dist[j] > on_plane) || (dist[i] > on_plane && dist[j] < -on_plane)) {
+        double t = dist[i] / (dist[i] - dist[j]);
+        push(slab[i] + t * (slab[j] - slab[i]));
+      }
+  }
+  std::vector<P2> hull = convex_hull(pts, 1e-10, 1e-10);
+  if (hull.size() < 3) {
+    set_error("aperture slab does not cut its own plane in a polygon (%zu section points)", hull.size());
+    return COM_E_GEOMETRY;
+  }
+  if (hull.size() > COM_MAX_EDGES) {
+    set_error("aperture section has %zu edges (max %d)", hull.size(), COM_MAX_EDGES);
+    return COM_E_GEOMETRY;
+  }
+  out->n_edges = (int)hull.size();
+  for (size_t k = 0; k < hull.size(); ++k) out->vertex[k][0] = hull[k].x, out->vertex[k][1] = hull[k].y;
+  edges_from_vertices(hull, out->edge);
+  return COM_OK;
+}
+
+int aperture_contains(const ComAperture* ap, const double* point) {
+  V3 r = load(point) - load(ap->p1);
+  double x = dot(r, load(ap->e1)), y = dot(r, load(ap->e2));
+  for (int k = 0; k < ap->n_edges; ++k)
+    if (!(ap->edge[k][0] * x + ap->edge[k][1] * y + ap->edge[k][2] >= 0)) return 0;
+  return 1;
+}
+
+namespace {
+
+// Superset of a convex polygon with fewer half-planes: drop an edge when the corner created by its
+// neighbours sticks out by at most delta.  (Conservative: the FP32 filter may only over-accept.)
+std::vector<std::array<double, 3>> simplify_halfplanes(const ComAperture& ap, double delta) {
+  std::vector<std::array<double, 3>> e;
+  for (int k = 0; k < ap.n_edges; ++k) e.push_back({ap.edge[k][0], ap.edge[k][1], ap.edge[k][2]});
+  bool changed = true;
+  while (changed && e.size() > 3) {
+    changed = false;
+    for (size_t k = 0; k < e.size(); ++k) {
+      auto& a = e[(k + e.size() - 1) % e.size()];
+      auto& b = e[(k + 1) % e.size()];
+      double det = a[0] * b[1] - a[1] * b[0];
+      if (std::fabs(det) < 1e-9) continue;  // neighbours parallel: dropping would unbound the polygon
+      double x = (-a[2] * b[1] + b[2] * a[1]) / det, y = (-a[0] * b[2] + b[0] * a[2]) / det;
+      double out = -(e[k][0] * x + e[k][1] * y + e[k][2]);  // how far the new corner is outside edge k
+      if (det > 0 && out >= 0 && out <= delta) {
+        e.erase(e.begin() + k);
+        changed = true;
+        break;
+      }
+    }
+  }
+  return e;
+}
+
+std::vector<P2> vertices_of(const std::vector<std::array<double, 3>>& e) {
+  std::vector<P2> v;
+  for (size_t k = 0; k < e.size(); ++k) {  // vertex k = edge k-1 /\ edge k  (start of edge k)
+    auto& a = e[(k + e.size() - 1) % e.size()];
+    auto& b = e[k];
+    double det = a[0] * b[1] - a[1] * b[0];
+    v.push_back({(-a[2] * b[1] + b[2] * a[1]) / det, (-a[0] * b[2] + b[0] * a[2]) / det});
+  }
+  return v;
+}
+
+void fill_filter_plane(FilterPlane& fp, const ComAperture& ap, const std::vector<std::array<double, 3>>& e,
+                       const double origin[3], float eps) {
+  V3 N = load(ap.normal);
+  V3 nh = (1.0 / norm(N)) * N;
+  V3 q0 = load(ap.p1) - load(origin);
+  for (int i = 0; i < 3; ++i) {
+    fp.n[i] = (float)(&nh.x)[i];
+    fp.q0[i] = (float)(&q0.x)[i];
+    fp.e1[i] = (float)ap.e1[i];
+    fp.e2[i] = (float)ap.e2[i];
+  }
+  fp.n_edges = (int)e.size();
+  fp.eps = eps;
+  for (size_t k = 0; k < e.size(); ++k)
+    for (int i = 0; i < 3; ++i) fp.edge[k][i] = (float)e[k][i];
+}
+
+}  // namespace
+
+int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
+  if (d.n_crystal <= 0 || d.n_slits <= 0 || !d.crystal_xyz || !d.crystal_normal || !d.slit_crys_side ||
+      !d.slit_plasma_side || !d.port_vertices || !d.detector_vertices || d.n_port_vertices < 3 ||
+      d.n_port_vertices > 16 || d.n_detector_vertices < 3 || d.n_detector_vertices > 16 ||
+      d.n_voxel_corners < 0 || d.n_voxel_corners > 8) {
+    set_error("com_scene_create: incomplete or inconsistent scene description");
+    return COM_E_BADARG;
+  }
+  const int C = d.n_crystal, S = d.n_slits;
+  DeviceScene& dv = hs.dev;
+  dv.n_crystal = C;
+  dv.n_crystal_padded = (C + 31) / 32 * 32;
+  dv.n_slits = S;
+  dv.n_apertures = 2 * S + 2;
+  for (int i = 0; i < 3; ++i) dv.origin[i] = d.origin[i];
+  dv.area_pt = d.area_pt, dv.refl_max = d.refl_max, dv.aoi0 = d.aoi0, dv.refl_sigma = d.refl_sigma;
+  hs.crystal_xyz.assign(d.crystal_xyz, d.crystal_xyz + 3 * (size_t)C);
+  hs.crystal_normal.assign(d.crystal_normal, d.crystal_normal + 3 * (size_t)C);
+
+  // ---- apertures: crys_0, plasma_0, crys_1, ..., port, detector -------------------------------------
+  dv.near_edge_mm = d.near_edge_mm > 0 ? d.near_edge_mm : 1e-9;
+  hs.apertures.assign(dv.n_apertures, ComAperture{});
+  if (d.apertures_override) {
+    for (int a = 0; a < dv.n_apertures; ++a) {
+      hs.apertures[a] = d.apertures_override[a];
+      ComAperture& ap = hs.apertures[a];
+      if (ap.n_edges < 3 || ap.n_edges > COM_MAX_EDGES) {
+        set_error("apertures_override[%d] has %d edges", a, ap.n_edges);
+        return COM_E_GEOMETRY;
+      }
+      std::vector<std::array<double, 3>> e;
+      for (int k = 0; k < ap.n_edges; ++k) e.push_back({ap.edge[k][0], ap.edge[k][1], ap.edge[k][2]});
+      std::vector<P2> v = vertices_of(e);  // keep the vertex list consistent with the (possibly shifted) edges
+      for (int k = 0; k < ap.n_edges; ++k) ap.vertex[k][0] = v[k].x, ap.vertex[k][1] = v[k].y;
+    }
+  } else
+  for (int k = 0; k < S; ++k) {
+    int rc = aperture_from_slab(d.slit_crys_side + 12 * k, 4, d.slit_depth, &hs.apertures[2 * k]);
+    if (rc) return rc;
+    rc = aperture_from_slab(d.slit_plasma_side + 12 * k, 4, d.slit_depth, &hs.apertures[2 * k + 1]);
+    if (rc) return rc;
+  }
+  if (!d.apertures_override) {
+    int rc = aperture_from_slab(d.port_vertices, d.n_port_vertices, d.port_depth, &hs.apertures[2 * S]);
+    if (rc) return rc;
+    rc = aperture_from_slab(d.detector_vertices, d.n_detector_vertices, d.detector_depth, &hs.apertures[2 * S + 1]);
+    if (rc) return rc;
+  }
+
+  // ---- FP32 filter ----------------------------------------------------------------------------------
+  double eps = d.filter_eps_mm > 0 ? d.filter_eps_mm : 5e-3;
+  dv.filter_disabled = eps >= 1e30 ? 1 : 0;
+  if (dv.filter_disabled) eps = 5e-3;
+  const double delta = 0.2 * eps;  // polygon simplification allowance, covered by the band
+
+  // slits: one polygon per side, repeated with period T along e1.  Verify the periodicity the collimator
+  // builder guarantees (collimator.py:103-119); otherwise the slit stage of the filter is switched off.
+  const ComAperture& c0 = hs.apertures[0];
+  const ComAperture& p0 = hs.apertures[1];
+  double period = 0;
+  bool periodic = true;
+  if (S > 1) {
+    period = dot(load(hs.apertures[2].p1) - load(c0.p1), load(c0.e1));
+    for (int k = 1; k < S && periodic; ++k)
+      for (int side = 0; side < 2 && periodic; ++side) {
+        const ComAperture& a0 = hs.apertures[side];
+        const ComAperture& ak = hs.apertures[2 * k + side];
+        V3 sh = load(ak.p1) - load(a0.p1);
+        if (std::fabs(dot(sh, load(a0.e1)) - k * period) > 1e-6 || std::fabs(dot(sh, load(a0.e2))) > 1e-6 ||
+            std::fabs(dot(sh, load(a0.normal))) / norm(load(a0.normal)) > 1e-6 || ak.n_edges != a0.n_edges)
+          periodic = false;
+        for (int e = 0; e < a0.n_edges && periodic; ++e)
+          if (std::hypot(ak.vertex[e][0] - a0.vertex[e][0], ak.vertex[e][1] - a0.vertex[e][1]) > 1e-6)
+            periodic = false;
+      }
+    if (!(period > 1e-3)) periodic = false;
+  } else {
+    period = 1e9;
+  }
+  auto ec = simplify_halfplanes(c0, delta), ep = simplify_halfplanes(p0, delta);
+  auto eport = simplify_halfplanes(hs.apertures[2 * S], delta);
+  auto edet = simplify_halfplanes(hs.apertures[2 * S + 1], delta);
+  if ((int)ec.size() > kMaxFilterEdges || (int)ep.size() > kMaxFilterEdges || (int)eport.size() > kMaxFilterEdges) {
+    set_error("filter polygon too large");
+    return COM_E_GEOMETRY;
+  }
+  fill_filter_plane(dv.slit_crys, c0, ec, d.origin, (float)eps);
+  fill_filter_plane(dv.slit_plasma, p0, ep, d.origin, (float)eps);
+  fill_filter_plane(dv.port, hs.apertures[2 * S], eport, d.origin, (float)eps);
+  if (!periodic) dv.slit_crys.n_edges = dv.slit_plasma.n_edges = 0;  // 0 edges = stage skipped (always passes)
+  dv.slit_period = (float)period;
+  dv.slit_inv_period = (float)(1.0 / period);
+
+  // detector cone: mirror the (simplified) detector polygon in the crystal's tangent plane at every
+  // crystal point; the ray p -> c reflects onto the detector iff the line p-c meets the mirrored polygon,
+  // i.e. iff p lies inside the cone  { g_j . (p - c) >= 0 }  (forward nappe) or its opposite.
+  const ComAperture& det = hs.apertures[2 * S + 1];
+  std::vector<P2> dverts = vertices_of(edet);
+  int NE = (int)dverts.size();
+  if (NE > kMaxConeEdges) {  // fall back to the unsimplified bounding: keep the 8 longest? -> disable stage A
+    set_error("detector section has %d edges after simplification (max %d)", NE, kMaxConeEdges);
+    return COM_E_GEOMETRY;
+  }
+  const int NEpad = NE <= 4 ? 4 : NE <= 6 ? 6 : 8;  // widths the filter kernel is instantiated for
+  dv.cone_edges = NEpad;
+  dv.cone_eps = (float)(4.0 * eps);
+  const int Cp = dv.n_crystal_padded;
+  hs.cone_forms.assign((size_t)4 * NEpad * Cp, 0.f);
+  hs.crystal_f.assign((size_t)4 * Cp, 0.f);
+  std::vector<V3> Q(NE);
+  V3 centroid{0, 0, 0};
+  for (int j = 0; j < NE; ++j) {
+    Q[j] = load(det.p1) + dverts[j].x * load(det.e1) + dverts[j].y * load(det.e2);
+    centroid = centroid + (1.0 / NE) * Q[j];
+  }
+  V3 O = load(d.origin);
+  bool single = d.n_voxel_corners > 0;
+  for (int c = 0; c < Cp; ++c) {
+    if (c >= C) continue;  // padding lanes stay zero; the kernel masks them by index
+    V3 cp = load(&hs.crystal_xyz[3 * (size_t)c]), n = load(&hs.crystal_normal[3 * (size_t)c]);
+    V3 cl = cp - O;
+    hs.crystal_f[4 * (size_t)c + 0] = (float)cl.x;
+    hs.crystal_f[4 * (size_t)c + 1] = (float)cl.y;
+    hs.crystal_f[4 * (size_t)c + 2] = (float)cl.z;
+    auto mirror = [&](V3 q) {
+      V3 r = q - cp;
+      return r - (2.0 * dot(r, n)) * n;  // relative to the crystal point
+    };
+    V3 mc = mirror(centroid);
+    V3 pstar = -1.0 * mc;  // a point (relative to c) whose ray certainly reflects onto the detector
+    bool back_unreachable = false;
+    for (int j = 0; j < NE; ++j) {
+      V3 a = mirror(Q[j]), b = mirror(Q[(j + 1) % NE]);
+      V3 g = cross(a, b);
+      double gl = norm(g);
+      if (!(gl > 0)) {
+        set_error("detector cone degenerate at crystal point %d", c);
+        return COM_E_GEOMETRY;
+      }
+      g = (1.0 / gl) * g;
+      if (dot(g, pstar) < 0) g = -1.0 * g;
+      double h = -dot(g, cl);
+      float* f = &hs.cone_forms[((size_t)j * Cp + c) * 4];
+      f[0] = (float)g.x, f[1] = (float)g.y, f[2] = (float)g.z, f[3] = (float)h;
+      if (single) {  // is the backward nappe (all E_j <= 0) excluded over the voxel hull by this face?
+        double mn = 1e300;
+        for (int q = 0; q < d.n_voxel_corners; ++q) mn = std::min(mn, dot(g, load(d.voxel_corners[q]) - O) + h);
+        if (mn > 8.0 * eps + 1.0) back_unreachable = true;
+      }
+    }
+    if (!back_unreachable) single = false;
+    for (int j = NE; j < NEpad; ++j)  // padding faces repeat face 0: neutral for both min and max
+      for (int i = 0; i < 4; ++i) hs.cone_forms[((size_t)j * Cp + c) * 4 + i] = hs.cone_forms[(size_t)c * 4 + i];
+  }
+  dv.single_nappe = single ? 1 : 0;
+  return COM_OK;
+}
+
+}  // namespace com
+
+extern "C" {
+
+int com_aperture_from_slab(const double* verts_h, int32_t n, const double* offset_h, ComAperture* out_h) {
+  return com::aperture_from_slab(verts_h, n, offset_h, out_h);
+}
+
+int com_aperture_contains(const ComAperture* ap_h, const double* point_h) {
+  if (!ap_h || !point_h) return 0;
+  return com::aperture_contains(ap_h, point_h);
+}
+
+const char* com_last_error(void) { return com::last_error(); }
+
+const char* com_error_string(int code) {
+  switch (code) {
+    case COM_OK: return "ok";
+    case COM_E_BADARG: return "bad argument";
+    case COM_E_CUDA: return "CUDA error";
+    case COM_E_NOMEM: return "out of memory / workspace too small";
+    case COM_E_OVERFLOW: return "candidate list overflow";
+    case COM_E_GEOMETRY: return "degenerate geometry";
+    case COM_E_EMPTY: return "Not enough points to perform calculations!";
+    default: return "unknown error";
+  }
+}
+
+int com_abi_version(void) { return COM_ABI_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+"""Stage-1 engine: Python host side of the sm_100a visibility kernels.
+
+Packs the reference-level geometry of one spectroscopic channel into a ``ComSceneDesc``,
+owns the device-resident ``ComScene`` handle and drives ``com_visibility_weights`` on
+torch-allocated device buffers (torch is used for memory, streams and NCCL only).
+There is no CPU fallback: without the CUDA library or a CUDA device this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .. import _lib
+from .apertures import build_apertures
+from .mesh_calculation import Lattice
+
+DEFAULT_FILTER_EPS_MM = 5e-3
+
+
+def crystal_normals(points: np.ndarray, radius_central_point, B, C_vertex) -> np.ndarray:
+    """Unit normals of the crystal cylinder at *points* (simulation.py:286-312).
+
+    The cylinder axis runs through ``radius_central_point`` along ``B - C``; the normal is the
+    unit vector from the foot of the perpendicular on that axis to the crystal point.
+    """
+    a = np.asarray(radius_central_point, dtype=float)
+    ab = np.asarray(B, dtype=float) - np.asarray(C_vertex, dtype=float)
+    b = a + ab
+    ab = b - a
+    foot = np.array([a + np.dot(p - a, ab) / np.dot(ab, ab) * ab for p in points])
+    n = points - foot
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    return n
+
+
+def lattice_struct(lat: Lattice) -> _lib.ComLattice:
+    out = _lib.ComLattice()
+    out.nx, out.ny, out.nz = lat.nx, lat.ny, lat.nz
+    for i in range(3):
+        out.start[i], out.step[i], out.stop[i] = lat.start[i], lat.step[i], lat.stop[i]
+        out.centre[i], out.shift[i] = lat.centre[i], lat.shift[i]
+    for i, v in enumerate(np.asarray(lat.rotation, dtype=float).reshape(9)):
+        out.rotation[i] = v
+    return out
+
+
+@dataclass
+class VisibilityResult:
+    """Device-resident output of one Stage-1 launch over the voxels [begin, end)."""
+
+    begin: int
+    end: int
+    weight: "object"  # torch.float64 (n,)
+    nrays: "object"  # torch.int32 (n,) (uint32 payload)
+    stats: dict
+    rays: np.ndarray | None = None  # structured host array of passing rays (optional)
+
+
+class ChannelScene:
+    """Device-resident beam line of one channel (crystal, collimator, port, detector)."""
+
+    def __init__(self, crystal_points, normals, slit_crys, slit_plasma, vector_front_back, port_vertices,
+                 port_ov, det_vertices, det_ov, origin, area_pt, refl_max, aoi0, refl_sigma=2.2,
+                 voxel_corners=None, filter_eps_mm=DEFAULT_FILTER_EPS_MM, calibrate_apertures=True,
+                 near_edge_mm=0.0):
+        self._lib = _lib.load()
+        self._keep = {}
+
+        def hold(name, arr):
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            self._keep[name] = arr
+            return _lib.as_double_ptr(arr)
+
+        d = _lib.ComSceneDesc()
+        d.n_crystal = len(crystal_points)
+        d.n_slits = len(slit_crys)
+        d.crystal_xyz = hold("xyz", crystal_points)
+        d.crystal_normal = hold("nrm", normals)
+        d.slit_crys_side = hold("sc", slit_crys)
+        d.slit_plasma_side = hold("sp", slit_plasma)
+        d.n_port_vertices = len(port_vertices)
+        d.n_detector_vertices = len(det_vertices)
+        d.port_vertices = hold("pv", port_vertices)
+        d.detector_vertices = hold("dv", det_vertices)
+        pov = np.asarray(port_ov, dtype=float).reshape(3)
+        dov = np.asarray(det_ov, dtype=float).reshape(3)
+        vfb = np.asarray(vector_front_back, dtype=float).reshape(3)
+        for i in range(3):
+            d.slit_depth[i], d.port_depth[i], d.detector_depth[i] = vfb[i], pov[i], dov[i]
+            d.origin[i] = float(origin[i])
+        d.area_pt, d.refl_max, d.aoi0, d.refl_sigma = float(area_pt), float(refl_max), float(aoi0), float(refl_sigma)
+        d.filter_eps_mm = float(filter_eps_mm)
+        d.near_edge_mm = float(near_edge_mm)
+        self.aperture_shifts = None
+        if calibrate_apertures:
+            arr, self.aperture_shifts = build_apertures(
+                self._keep["sc"].reshape(-1, 4, 3), self._keep["sp"].reshape(-1, 4, 3), vfb,
+                self._keep["pv"], pov, self._keep["dv"], dov, calibrate=True)
+            self._keep["apertures"] = arr
+            d.apertures_override = C.cast(arr, C.POINTER(_lib.ComAperture))
+        if voxel_corners is not None:
+            vc = np.asarray(voxel_corners, dtype=float).reshape(-1, 3)
+            d.n_voxel_corners = len(vc)
+            for q in range(len(vc)):
+                for i in range(3):
+                    d.voxel_corners[q][i] = vc[q, i]
+        self.desc = d
+        self.n_crystal = d.n_crystal
+        self.n_slits = d.n_slits
+        self.handle = C.c_void_p()
+        _lib.check(self._lib.com_scene_create(C.byref(d), C.byref(self.handle)), "com_scene_create")
+
+    # -- lifetime ----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self._lib.com_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- introspection -------------------------------------------------------------------
+    def filter_info(self) -> dict:
+        ce, sn, se, pe = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        eps = C.c_double()
+        _lib.check(self._lib.com_scene_filter_info(self.handle, C.byref(ce), C.byref(sn), C.byref(se), C.byref(pe),
+                                                   C.byref(eps)), "com_scene_filter_info")
+        return dict(cone_edges=ce.value, single_nappe=bool(sn.value), slit_edges=se.value, port_edges=pe.value,
+                    eps_mm=eps.value)
+
+    def aperture(self, index: int) -> _lib.ComAperture:
+        ap = _lib.ComAperture()
+        _lib.check(self._lib.com_scene_get_aperture(self.handle, index, C.byref(ap)), "com_scene_get_aperture")
+        return ap
+
+    # -- Stage 1 -------------------------------------------------------------------------
+    def visibility(self, lattice: Lattice | None = None, voxels=None, begin: int = 0, end: int | None = None,
+                   want_rays: bool = False, candidate_fraction: float = 0.0, reff_bin=None, hist=None,
+                   device=None, max_retries: int = 3) -> VisibilityResult:
+        """Run K1a/K1b over the voxels [begin, end).
+
+        *lattice* selects the implicit CuboidMesh lattice; *voxels* is a torch.float64 CUDA tensor ``(P, 3)``
+        of explicit coordinates (global mm).  Returns device tensors; nothing is copied to the host except
+        the 64-byte statistics block (and the ray list when *want_rays*).
+        """
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.ComonitorError(_lib.COM_E_CUDA, "ChannelScene.visibility",
+                                      "no CUDA device: the accelerated path has no CPU fallback")
+        if (lattice is None) == (voxels is None):
+            raise ValueError("give exactly one of lattice= or voxels=")
+        device = torch.device(device if device is not None else "cuda")
+        lat_struct = None
+        vox_ptr = None
+        if lattice is not None:
+            total = lattice.n_points
+            lat_struct = lattice_struct(lattice)
+        else:
+            if voxels.dtype != torch.float64 or not voxels.is_cuda or voxels.dim() != 2 or voxels.shape[1] != 3:
+                raise ValueError("voxels must be a CUDA float64 tensor of shape (P, 3)")
+            voxels = voxels.contiguous()
+            total = voxels.shape[0]
+            vox_ptr = C.c_void_p(voxels.data_ptr())
+            device = voxels.device
+        end = total if end is None else end
+        if not (0 <= begin <= end <= total):
+            raise ValueError(f"voxel range [{begin},{end}) outside [0,{total})")
+        n = end - begin
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            w = torch.empty(n, dtype=torch.float64, device=device)
+            nr = torch.empty(n, dtype=torch.int32, device=device)
+            stats_t = torch.empty(8, dtype=torch.int64, device=device)
+            frac = candidate_fraction
+            rays_cap = 0
+            for attempt in range(max_retries + 1):
+                ws_bytes = self._lib.com_visibility_workspace_bytes(self.handle, n, frac)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                rays_t = rays_cnt = None
+                if want_rays:
+                    rays_cap = rays_cap or max(1 << 16, (ws_bytes - 256) // 8)
+                    rays_t = torch.empty(rays_cap * 4, dtype=torch.float64, device=device)
+                    rays_cnt = torch.zeros(1, dtype=torch.int64, device=device)
+                rc = self._lib.com_visibility_weights(
+                    self.handle, C.byref(lat_struct) if lat_struct is not None else None, vox_ptr, begin, end,
+                    C.c_void_p(w.data_ptr()), C.c_void_p(nr.data_ptr()),
+                    C.c_void_p(rays_t.data_ptr()) if want_rays else None, rays_cap,
+                    C.c_void_p(rays_cnt.data_ptr()) if want_rays else None,
+                    C.c_void_p(reff_bin.data_ptr()) if reff_bin is not None else None,
+                    C.c_void_p(hist.data_ptr()) if hist is not None else None,
+                    int(hist.numel()) if hist is not None else 0,
+                    C.c_void_p(stats_t.data_ptr()), C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream))
+                _lib.check(rc, "com_visibility_weights")
+                stats = dict(zip([f[0] for f in _lib.ComStats._fields_], stats_t.cpu().tolist()))
+                stats.pop("reserved", None)
+                if not stats["overflow"]:
+                    break
+                if hist is not None:
+                    raise _lib.ComonitorError(_lib.COM_E_OVERFLOW, "com_visibility_weights",
+                                              "candidate overflow while accumulating into a caller histogram")
+                # the filter let more rays through than the list holds: size it from the count and redo
+                frac = 1.05 * stats["candidates"] / max(1, stats["tests"]) + 1e-6
+            else:
+                raise _lib.ComonitorError(_lib.COM_E_OVERFLOW, "com_visibility_weights", "candidate list overflow")
+            rays = None
+            if want_rays:
+                cnt = int(rays_cnt.item())
+                if cnt > rays_cap:
+                    raise _lib.ComonitorError(_lib.COM_E_OVERFLOW, "com_visibility_weights",
+                                              f"{cnt} passing rays > ray-list capacity {rays_cap}")
+                rays = rays_t[: cnt * 4].cpu().numpy().view(_lib.RAY_RECORD_DTYPE).copy()
+        return VisibilityResult(begin=begin, end=end, weight=w, nrays=nr, stats=stats, rays=rays)
+
+    def compact(self, result: VisibilityResult):
+        """Visible voxels of *result*: (flat indices int64, weights float64), device tensors, ascending."""
+        import torch
+
+        n = result.end - result.begin
+        dev = result.weight.device
+        with torch.cuda.device(dev):
+            idx = torch.empty(n, dtype=torch.int64, device=dev)
+            wc = torch.empty(n, dtype=torch.float64, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+            ws_bytes = self._lib.com_compact_workspace_bytes(n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rc = self._lib.com_compact_visible(
+                C.c_void_p(result.nrays.data_ptr()), C.c_void_p(result.weight.data_ptr()), n, result.begin,
+                C.c_void_p(idx.data_ptr()), C.c_void_p(wc.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc, "com_compact_visible")
+            m = int(cnt.item())
+        return idx[:m], wc[:m]

@@ -1,0 +1,200 @@
+/*
+ * comonitor_sm100.h - C ABI of libcomonitor_sm100.so
+ *
+ * B200 (sm_100a) implementation of the two data-parallel stages of tfornal/co_monitor.
+ * The reference is pure Python and has no FFI layer; the entry points below are what a
+ * binding of its two hot classes would call (ctypes stub in INTEGRATION.md):
+ *
+ *   Stage 1  co_monitor/geometry/simulation.py:30-75   Simulation.__init__
+ *            (calculate_radiation_reflection :273-325, check_ray_transmission :327-432,
+ *             calculate_distances :483-504, calculate_angles :506-536,
+ *             calculate_radiation_fraction :538-594)                  -> com_visibility_weights*
+ *   Stage 2  co_monitor/emissivity/reader.py:22-81     Emissivity.__init__
+ *            (read_ne_te :199-243, find_closest_temp_idx :282-299, read_pec :316-341,
+ *             calculate_intensity :343-378, calculate_total_emissivity :380-401)
+ *                                                                      -> com_emissivity_integrate*
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only.  "_h" / "host" = host memory; everything else that is a
+ *     buffer is DEVICE memory owned by the caller.  The library owns only what a ComScene /
+ *     ComTables handle holds.
+ *   - every function returns COM_OK (0) or a negative COM_E_* code; nothing throws.  A short text
+ *     for the last failure on the calling thread is available from com_last_error().
+ *   - work is enqueued on the caller's CUDA stream (com_stream_t == cudaStream_t); the *_host
+ *     variants copy, run and synchronise by themselves.
+ *   - lengths are in elements, coordinates in millimetres, fp64 unless stated.
+ *   - there is no CPU fallback: without a CUDA device the compute entry points return COM_E_CUDA.
+ */
+#ifndef COMONITOR_SM100_H
+#define COMONITOR_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COM_ABI_VERSION 1
+
+#define COM_OK 0
+#define COM_E_BADARG (-1)   /* null pointer, bad size, inconsistent description            */
+#define COM_E_CUDA (-2)     /* CUDA runtime error (no device, launch failure, ...)         */
+#define COM_E_NOMEM (-3)    /* host or device allocation failed / workspace too small      */
+#define COM_E_OVERFLOW (-4) /* candidate / ray list capacity exceeded (see ComStats)       */
+#define COM_E_GEOMETRY (-5) /* degenerate aperture (collinear plane points, empty section) */
+#define COM_E_EMPTY (-6)    /* no ray passed: the reference's "Not enough points to perform
+                               calculations!" (simulation.py:451-456)                      */
+
+typedef void* com_stream_t; /* cudaStream_t */
+
+#define COM_MAX_EDGES 32
+
+/* One aperture of the beam line reduced to "plane + convex polygon in that plane".
+ * The reference tests  Delaunay(vertices +/- orientation_vector).find_simplex(X) >= 0  for the point X
+ * where the ray meets the plane through the aperture's first three vertices
+ * (simulation.py:175-207, 209-271).  X lies in that plane, so the test equals "X inside the
+ * cross-section of the slab's convex hull with the plane" - a convex polygon. */
+typedef struct ComAperture {
+  double p1[3];     /* first vertex: the plane point used by the reference                    */
+  double normal[3]; /* (p2-p1) x (p3-p2), NOT normalised: the |N.u| < 1e-6 rule needs it      */
+  double e1[3];     /* in-plane orthonormal basis, e1 = (p2-p1)/|p2-p1|, e2 = n^ x e1         */
+  double e2[3];
+  int32_t n_edges;
+  int32_t reserved;
+  double edge[COM_MAX_EDGES][3];   /* a*x + b*y + c >= 0 inside, (a,b) unit, (x,y) = ((X-p1).e1,(X-p1).e2) */
+  double vertex[COM_MAX_EDGES][2]; /* polygon vertices, counter-clockwise, same frame          */
+} ComAperture;
+
+/* Host-only helper (no CUDA): cross-section of conv(verts + offset, verts - offset) with the plane through
+ * verts[0..2].  verts is (n,3) row-major, 3 <= n <= 16. */
+int com_aperture_from_slab(const double* verts_h, int32_t n, const double* offset_h, ComAperture* out_h);
+
+/* Host-only helper (no CUDA): 1 if the point (global mm) passes the aperture test in fp64, else 0. */
+int com_aperture_contains(const ComAperture* ap_h, const double* point_h);
+
+/* The beam line of one spectroscopic channel, at the level of the reference's own arrays. */
+typedef struct ComSceneDesc {
+  int32_t n_crystal;             /* C = crystal_height_step * crystal_length_step                     */
+  int32_t n_slits;               /* S                                                                 */
+  const double* crystal_xyz;     /* (C,3) DispersiveElement.crystal_points                            */
+  const double* crystal_normal;  /* (C,3) unit cylinder normals (simulation.py:286-312)               */
+  const double* slit_crys_side;  /* (S,4,3) Collimator.read_colim_coord()[1]                          */
+  const double* slit_plasma_side;/* (S,4,3) Collimator.read_colim_coord()[2]                          */
+  double slit_depth[3];          /* collimator "vector front-back" (slab half-depth of every slit)    */
+  int32_t n_port_vertices;       /* 14                                                                */
+  int32_t n_detector_vertices;   /* 4                                                                 */
+  const double* port_vertices;   /* (n_port_vertices,3)                                               */
+  double port_depth[3];          /* Port.orientation_vector                                           */
+  const double* detector_vertices; /* (n_detector_vertices,3)                                         */
+  double detector_depth[3];      /* Detector.orientation_vector                                       */
+  double origin[3];              /* recentring offset of the FP32 filter (crystal central point)      */
+  double area_pt;                /* round(1600/(h*l), 2) mm^2, simulation.py:137-139                  */
+  double refl_max;               /* max reflectivity                                                  */
+  double aoi0;                   /* nominal angle of incidence, degrees                               */
+  double refl_sigma;             /* 2.2                                                               */
+  double filter_eps_mm;          /* FP32 filter band; <=0 selects the default (2e-3 mm);
+                                    >= 1e30 disables the filter: every ray is evaluated in fp64       */
+  const ComAperture* apertures_override; /* NULL, or 2S+2 apertures (crys_0, plasma_0, ..., port, detector)
+                                    to use instead of the exact hull sections computed from the vertex lists.
+                                    Lets the host reproduce scipy/Qhull's in-simplex leeway: find_simplex accepts
+                                    points up to sqrt(100*eps) = 1.5e-7 (barycentric) outside hull faces that
+                                    Qhull covered with a flat simplex, i.e. up to ~1e-4 mm beyond an edge.     */
+  double near_edge_mm;           /* |margin| below which a decided ray is counted in ComStats.near_edge_rays;
+                                    <= 0 selects 1e-9 mm                                               */
+  int32_t n_voxel_corners;       /* 0 = unknown (general two-nappe detector filter), else <= 8        */
+  int32_t reserved;
+  double voxel_corners[8][3];    /* points whose convex hull contains every voxel that will be tested
+                                    (the 8 corners of the lattice); lets the filter drop the backward
+                                    nappe of the detector cone when it cannot be reached               */
+} ComSceneDesc;
+
+typedef struct ComScene ComScene; /* opaque: device-resident tables of one channel */
+
+int com_scene_create(const ComSceneDesc* desc_h, ComScene** out);
+int com_scene_destroy(ComScene* scene);
+/* number of apertures (2S+2, order: crys_0, plasma_0, crys_1, ..., port, detector) and a host copy of one */
+int com_scene_aperture_count(const ComScene* scene);
+int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* out_h);
+/* what the FP32 filter was built with (any output pointer may be NULL) */
+int com_scene_filter_info(const ComScene* scene, int32_t* cone_edges, int32_t* single_nappe, int32_t* slit_edges,
+                          int32_t* port_edges, double* eps_mm);
+
+/* Implicit voxel lattice == CuboidMesh (mesh_calculation.py:119-159):
+ *   flat = (iy*nx + ix)*nz + iz ;  p = ((x[ix],y[iy],z[iz]) - centre) . R + centre + shift
+ *   x[i] = start[0] + i*step[0]  (last sample = stop[0], as numpy.linspace does) */
+typedef struct ComLattice {
+  int64_t nx, ny, nz;
+  double start[3];
+  double step[3];
+  double stop[3];
+  double centre[3];
+  double rotation[9]; /* row-major R, row-vector convention (p_row . R) */
+  double shift[3];
+} ComLattice;
+
+typedef struct ComStats {
+  uint64_t tests;           /* voxel x crystal-point rays examined                                   */
+  uint64_t candidates;      /* rays the FP32 filter sent to the fp64 stage                           */
+  uint64_t passing_rays;    /* rays that pass every aperture in fp64                                 */
+  uint64_t near_edge_rays;  /* fp64-decided rays within near_edge_mm of an aperture edge they were tested on */
+  uint64_t visible_voxels;  /* voxels with >= 1 passing ray                                          */
+  uint64_t candidate_capacity; /* capacity the launch ran with                                       */
+  uint64_t overflow;        /* != 0: candidates > capacity, results incomplete (COM_E_OVERFLOW)      */
+  uint64_t reserved;
+} ComStats;
+
+/* One passing ray (optional output): what the reference keeps per selected ray
+ * (calculate_indices :434-461, calculate_distances :483-504, calculate_angles :506-536). */
+typedef struct ComRayRecord {
+  int64_t ray_index; /* voxel_flat_index * C + crystal_index */
+  double distance;   /* |plasma - crystal|, mm              */
+  double aoi;        /* (180 - round(deg, 2)) / 2           */
+  double weight;     /* contribution to total_intensity_fraction */
+} ComRayRecord;
+
+/* Bytes of scratch needed by com_visibility_weights for n voxels against this scene.
+ * candidate_fraction <= 0 selects the default (2 % of the rays, at least 1 Mi entries). */
+size_t com_visibility_workspace_bytes(const ComScene* scene, int64_t n_voxels, double candidate_fraction);
+
+/* Stage 1 on the voxels [vox_begin, vox_end).
+ *   lattice_h != NULL : voxel coordinates come from the implicit lattice (flat indices are lattice indices);
+ *   vox_xyz   != NULL : (n_total,3) fp64 DEVICE array in global mm, indexed by the same flat index.
+ * Outputs are indexed by (flat - vox_begin):
+ *   w_out     (n) fp64   sum of the passing rays' weights (0 for invisible voxels) - overwritten
+ *   nrays_out (n) u32    number of passing rays per voxel (visibility mask = nrays > 0) - overwritten, nullable
+ *   rays_out  optional list of passing rays, unordered; *rays_count_out (device u64) receives how many
+ *             were produced (may exceed rays_capacity: then only the first rays_capacity are valid)
+ *   reff_bin / hist_out optional fused Reff-bin histogram: hist_out[reff_bin[flat]] += weight
+ *             (reff_bin indexed by absolute flat index; bins >= n_bins are skipped) - accumulated, not cleared
+ *   stats_out device ComStats - overwritten
+ * Stream-ordered; returns after enqueueing. */
+int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz,
+                           int64_t vox_begin, int64_t vox_end, double* w_out, uint32_t* nrays_out,
+                           ComRayRecord* rays_out, int64_t rays_capacity, uint64_t* rays_count_out,
+                           const uint16_t* reff_bin, double* hist_out, int32_t n_bins, ComStats* stats_out,
+                           void* workspace, size_t workspace_bytes, com_stream_t stream);
+
+/* Host-buffer variant (the reference-facing call): host in, host out, device work inside; synchronous.
+ * vox_xyz_h may be NULL when lattice_h is given.  rays_out_h may be NULL.  Returns COM_E_EMPTY when no
+ * ray passes (outputs are still valid: all zero). */
+int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                int64_t vox_begin, int64_t vox_end, double* w_out_h, uint32_t* nrays_out_h,
+                                ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
+                                ComStats* stats_out_h);
+
+/* Compaction of the visible voxels (nrays > 0), ascending flat index: idx_out[i] = vox_begin + position,
+ * w_compact[i] = w[position].  *count_out (device u64).  idx_out / w_compact need room for n entries. */
+int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
+                        double* w_compact, uint64_t* count_out, void* workspace, size_t workspace_bytes,
+                        com_stream_t stream);
+size_t com_compact_workspace_bytes(int64_t n);
+
+const char* com_last_error(void);
+const char* com_error_string(int code);
+int com_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMONITOR_SM100_H */

@@ -1,0 +1,134 @@
+"""Stage-1 parity on the GPU: CUDA path (through the C ABI) vs the golden files shipped with the
+reference and vs the CPU oracle on the same voxels."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "co_monitor_b200",
+                         "input_files", "geometry", "observed_plasma_volume")
+PASSING_RAYS = {"B": 652069, "C": 613537, "N": 1049965, "O": 901918}  # full-grid oracle runs (oracle/stage1.py --full)
+
+
+def golden(el):
+    df = pd.read_csv(os.path.join(GOLD_ROOT, el, f"{el}_plasma_coordinates-10_mm_spacing-height_30-length_20-slit_100.dat"), sep=";")
+    return df.sort_values("idx_sel_plas_points").reset_index(drop=True)
+
+
+@pytest.fixture(scope="module")
+def sims():
+    from co_monitor_b200.geometry.simulation import Simulation
+
+    cache = {}
+
+    def get(el):
+        if el not in cache:
+            cache[el] = Simulation(el, slits_number=10, distance_between_points=10, crystal_height_step=30,
+                                   crystal_length_step=20, plot=False, verbose=False)
+        return cache[el]
+
+    return get
+
+
+@pytest.mark.parametrize("el", list("CBNO"))
+def test_golden_file_parity(sims, el):
+    """Full 270 000-voxel grid: identical visible set and coordinates, weights <= 1e-12 relative."""
+    sim = sims(el)
+    gold = golden(el)
+    ddf = sim.ddf.compute()
+    assert sim.stats["tests"] == 270000 * 600
+    assert not sim.stats["overflow"]
+    mine, ref = ddf.idx_sel_plas_points.to_numpy(), gold.idx_sel_plas_points.to_numpy()
+    extra, missing = np.setdiff1d(mine, ref), np.setdiff1d(ref, mine)
+    print(f"{el}: stats {sim.stats} extra {extra} missing {missing}")
+    assert len(extra) == 0 and len(missing) == 0, (extra, missing)
+    assert sim.stats["passing_rays"] == PASSING_RAYS[el]
+    assert sim.stats["visible_voxels"] == len(gold)
+    for col in ("plasma_x", "plasma_y", "plasma_z"):
+        assert np.array_equal(ddf[col].to_numpy(), gold[col].to_numpy())
+    rel = np.abs(ddf.total_intensity_fraction.to_numpy() / gold.total_intensity_fraction.to_numpy() - 1)
+    print(f"{el}: max rel weight err {rel.max():.3e}, near-edge rays {sim.stats['near_edge_rays']}")
+    assert rel.max() <= 1e-12
+
+
+def test_filter_is_conservative(sims):
+    """FP32 filter on vs off (every ray in fp64): identical ray counts and weights on a visible slab."""
+    import torch
+
+    sim = sims("C")
+    from co_monitor_b200.geometry.engine import ChannelScene
+
+    lo, hi = 120000, 150000
+    a = sim.scene.visibility(lattice=sim.mesh.lattice, begin=lo, end=hi)
+    brute = ChannelScene(
+        sim.disp_elem_coord, sim.crystal_normals, sim.slit_coord_crys_side, sim.slit_coord_plasma_side,
+        sim.collim_vector_front_back, sim.port_vertices_coordinates, sim.port_orientation_vector,
+        sim.detector_vertices_coordinates, sim.detector_orientation_vector, origin=sim._crystal_central_point,
+        area_pt=sim.crystal_point_area, refl_max=sim.max_reflectivity, aoi0=float(sim.AOI), filter_eps_mm=1e30)
+    b = brute.visibility(lattice=sim.mesh.lattice, begin=lo, end=hi)
+    assert b.stats["candidates"] == (hi - lo) * 600
+    assert a.stats["candidates"] < 0.02 * b.stats["candidates"]
+    assert a.stats["passing_rays"] == b.stats["passing_rays"] > 0
+    assert torch.equal(a.nrays, b.nrays)
+    assert torch.allclose(a.weight, b.weight, rtol=1e-13, atol=0)
+    brute.close()
+
+
+def test_ray_level_parity_with_oracle(sims):
+    """Per-ray mask, distance and AOI against the NumPy/Qhull oracle on 1500 voxels of a visible region."""
+    from oracle import geometry_setup as gs
+    from oracle import stage1 as oracle
+
+    sim = sims("C")
+    lo, hi = 131000, 132500
+    scene = oracle.build_scene("C", 10, 30, 20)
+    vox = gs.voxel_mesh(gs.load_db(), 10, flat_indices=np.arange(lo, hi))
+    ref = oracle.run_chunk(scene, vox, want_rays=True)
+    res = sim.scene.visibility(lattice=sim.mesh.lattice, begin=lo, end=hi, want_rays=True)
+    assert ref.mask.sum() > 1000
+    mask = np.zeros((hi - lo) * 600, bool)
+    mask[res.rays["ray_index"] - lo * 600] = True
+    assert np.array_equal(mask.reshape(hi - lo, 600), ref.mask)
+    order = np.argsort(res.rays["ray_index"])
+    rays = res.rays[order]
+    assert np.allclose(rays["distance"], ref.dist[ref.mask], rtol=1e-14, atol=0)
+    assert np.array_equal(rays["aoi"], ref.aoi[ref.mask])
+    assert np.allclose(rays["weight"], ref.w_ray[ref.mask], rtol=1e-13, atol=0)
+    assert np.allclose(res.weight.cpu().numpy(), ref.weight, rtol=1e-13, atol=1e-300)
+    assert np.array_equal(res.nrays.cpu().numpy(), ref.nrays)
+
+
+def test_explicit_voxels_match_lattice(sims):
+    import torch
+
+    sim = sims("C")
+    lo, hi = 100000, 140000
+    a = sim.scene.visibility(lattice=sim.mesh.lattice, begin=lo, end=hi)
+    pts = torch.from_numpy(sim.mesh.points_at(np.arange(0, hi))).cuda()
+    b = sim.scene.visibility(voxels=pts, begin=lo, end=hi)
+    assert torch.equal(a.nrays, b.nrays)
+    assert torch.allclose(a.weight, b.weight, rtol=1e-12, atol=0)
+
+
+def test_reference_attributes(sims):
+    sim = sims("C")
+    assert sim.crystal_point_area == 2.67
+    assert list(sim.ddf.columns) == ["idx_sel_plas_points", "plasma_x", "plasma_y", "plasma_z", "total_intensity_fraction"]
+    sel = sim.selected_intersections
+    assert sel.shape == (270000, 600) and sel.sum() == PASSING_RAYS["C"]
+    assert len(sim.distances) == len(sim.angles_of_incident) == PASSING_RAYS["C"]
+    per_voxel = sel.sum(axis=1)
+    assert np.array_equal(np.flatnonzero(per_voxel), sim.ddf.idx_sel_plas_points.to_numpy())
+
+
+def test_no_visible_voxel_exits_like_the_reference():
+    from co_monitor_b200.geometry.simulation import Simulation
+
+    with pytest.raises(SystemExit) as exc:
+        # a single 1x1 crystal grid point at the crystal corner sees nothing through the collimator at 100 mm spacing
+        Simulation("C", slits_number=1, distance_between_points=120, crystal_height_step=1, crystal_length_step=1,
+                   plot=False, verbose=False)
+    assert "Not enough points" in str(exc.value)
