@@ -129,7 +129,7 @@ def _declare(lib):
     lib.com_scene_destroy.argtypes = [vp]
     lib.com_scene_aperture_count.argtypes = [vp]
     lib.com_scene_get_aperture.argtypes = [vp, i32, C.POINTER(ComAperture)]
-    lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), dp]
+    lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), dp, dp]
     lib.com_visibility_workspace_bytes.restype = C.c_size_t
     lib.com_visibility_workspace_bytes.argtypes = [vp, i64, C.c_double]
     lib.com_visibility_weights.argtypes = [
@@ -141,6 +141,9 @@ def _declare(lib):
     lib.com_compact_workspace_bytes.restype = C.c_size_t
     lib.com_compact_workspace_bytes.argtypes = [i64]
     lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.com_measure_fp32_tflops.restype = C.c_double
+    lib.com_kernel_timing_enable.argtypes = [C.c_int]
+    lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
     return lib
 
 
@@ -152,6 +155,7 @@ EXPORTED_SYMBOLS = [
     "com_scene_filter_info",
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
     "com_compact_workspace_bytes", "com_compact_visible",
+    "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
 ]
 
 

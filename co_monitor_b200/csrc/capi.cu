@@ -1,6 +1,7 @@
 // C ABI glue: scene lifetime, stream-ordered entry points, host-buffer variants, visible-voxel compaction.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -13,6 +14,8 @@ int visibility_launch(const ComScene*, const ComLattice*, const double*, long lo
                       ComRayRecord*, long long, unsigned long long*, const uint16_t*, double*, int, ComStats*, void*,
                       size_t, cudaStream_t);
 size_t visibility_workspace_bytes(const DeviceScene&, long long, double);
+void kernel_timing_enable(int on);
+void kernel_timing_read(double*, double*, long long*);
 }  // namespace com
 
 #define COM_CUDA(x)                                                            \
@@ -89,9 +92,48 @@ __global__ void compact_scatter(const unsigned int* nrays, const double* w, long
   }
 }
 
+// FP32 FMA issue-rate probe: 8 independent chains per thread, register operands only.
+__global__ void __launch_bounds__(256) fma_probe(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fmaf(x0, a, b), x1 = fmaf(x1, a, b), x2 = fmaf(x2, a, b), x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b), x5 = fmaf(x5, a, b), x6 = fmaf(x6, a, b), x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 }  // namespace
 
 extern "C" {
+
+/* Measured FP32 FMA throughput of the current device in TFLOP/s (FMA = 2 FLOP); < 0 on error. */
+double com_measure_fp32_tflops(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return -1.0;
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  float* d = nullptr;
+  if (cudaMalloc(&d, sizeof(float) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a), cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    fma_probe<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a), cudaEventDestroy(b);
+  cudaFree(d);
+  return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
 
 int com_scene_create(const ComSceneDesc* desc_h, ComScene** out) {
   if (!desc_h || !out) {
@@ -106,28 +148,28 @@ int com_scene_create(const ComSceneDesc* desc_h, ComScene** out) {
   if (!sc) return COM_E_NOMEM;
   sc->dev = hs.dev;
   sc->apertures_h = hs.apertures;
+  sc->filter_eps_mm = desc_h->filter_eps_mm > 0 ? desc_h->filter_eps_mm : 5e-3;
 
-  const size_t b_xyz = align_up(hs.crystal_xyz.size() * sizeof(double), 256);
-  const size_t b_nrm = align_up(hs.crystal_normal.size() * sizeof(double), 256);
-  const size_t b_ap = align_up(hs.apertures.size() * sizeof(ComAperture), 256);
-  const size_t b_cone = align_up(hs.cone_forms.size() * sizeof(float), 256);
-  const size_t b_cf = align_up(hs.crystal_f.size() * sizeof(float), 256);
-  std::vector<char> blob(b_xyz + b_nrm + b_ap + b_cone + b_cf, 0);
-  size_t o = 0;
-  std::memcpy(blob.data() + o, hs.crystal_xyz.data(), hs.crystal_xyz.size() * sizeof(double));
-  const size_t o_xyz = o;
-  o += b_xyz;
-  std::memcpy(blob.data() + o, hs.crystal_normal.data(), hs.crystal_normal.size() * sizeof(double));
-  const size_t o_nrm = o;
-  o += b_nrm;
-  std::memcpy(blob.data() + o, hs.apertures.data(), hs.apertures.size() * sizeof(ComAperture));
-  const size_t o_ap = o;
-  o += b_ap;
-  std::memcpy(blob.data() + o, hs.cone_forms.data(), hs.cone_forms.size() * sizeof(float));
-  const size_t o_cone = o;
-  o += b_cone;
-  std::memcpy(blob.data() + o, hs.crystal_f.data(), hs.crystal_f.size() * sizeof(float));
-  const size_t o_cf = o;
+  // one device allocation, sections 256-byte aligned
+  struct Section {
+    const void* src;
+    size_t bytes;
+    size_t offset;
+  } sec[] = {
+      {hs.crystal_xyz.data(), hs.crystal_xyz.size() * sizeof(double), 0},
+      {hs.crystal_normal.data(), hs.crystal_normal.size() * sizeof(double), 0},
+      {hs.dev_apertures.data(), hs.dev_apertures.size() * sizeof(com::DevAperture), 0},
+      {hs.edges.data(), hs.edges.size() * sizeof(double), 0},
+      {hs.det_forms.data(), hs.det_forms.size() * sizeof(float), 0},
+      {hs.slit_forms.data(), hs.slit_forms.size() * sizeof(float), 0},
+  };
+  size_t total = 0;
+  for (auto& x : sec) {
+    x.offset = total;
+    total += align_up(x.bytes, 256);
+  }
+  std::vector<char> blob(total, 0);
+  for (auto& x : sec) std::memcpy(blob.data() + x.offset, x.src, x.bytes);
 
   cudaError_t e = cudaGetDevice(&sc->device);
   if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.size());
@@ -139,11 +181,12 @@ int com_scene_create(const ComSceneDesc* desc_h, ComScene** out) {
     return COM_E_CUDA;
   }
   char* d = static_cast<char*>(sc->d_blob);
-  sc->dev.crystal_xyz = reinterpret_cast<const double*>(d + o_xyz);
-  sc->dev.crystal_normal = reinterpret_cast<const double*>(d + o_nrm);
-  sc->dev.apertures = reinterpret_cast<const ComAperture*>(d + o_ap);
-  sc->dev.cone_forms = reinterpret_cast<const float4*>(d + o_cone);
-  sc->dev.crystal_f = reinterpret_cast<const float4*>(d + o_cf);
+  sc->dev.crystal_xyz = reinterpret_cast<const double*>(d + sec[0].offset);
+  sc->dev.crystal_normal = reinterpret_cast<const double*>(d + sec[1].offset);
+  sc->dev.apertures = reinterpret_cast<const com::DevAperture*>(d + sec[2].offset);
+  sc->dev.edges = reinterpret_cast<const double*>(d + sec[3].offset);
+  sc->dev.det_forms = reinterpret_cast<const float4*>(d + sec[4].offset);
+  sc->dev.slit_forms = reinterpret_cast<const float4*>(d + sec[5].offset);
   *out = sc;
   return COM_OK;
 }
@@ -163,14 +206,13 @@ int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* ou
   return COM_OK;
 }
 
-int com_scene_filter_info(const ComScene* scene, int32_t* cone_edges, int32_t* single_nappe, int32_t* slit_edges,
-                          int32_t* port_edges, double* eps_mm) {
+int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
+                          double* eps_mm) {
   if (!scene) return COM_E_BADARG;
-  if (cone_edges) *cone_edges = scene->dev.cone_edges;
-  if (single_nappe) *single_nappe = scene->dev.single_nappe;
-  if (slit_edges) *slit_edges = scene->dev.slit_crys.n_edges;
-  if (port_edges) *port_edges = scene->dev.port.n_edges;
-  if (eps_mm) *eps_mm = scene->dev.filter_disabled ? 1e30 : (double)scene->dev.port.eps;
+  if (slit_filter) *slit_filter = scene->dev.slit_filter;
+  if (filter_disabled) *filter_disabled = scene->dev.filter_disabled;
+  if (slit_period_mm) *slit_period_mm = scene->dev.slit_period_d;
+  if (eps_mm) *eps_mm = scene->filter_eps_mm;
   return COM_OK;
 }
 
@@ -266,6 +308,18 @@ int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* la
     com::set_error("Not enough points to perform calculations!");
     return COM_E_EMPTY;
   }
+  return COM_OK;
+}
+
+int com_kernel_timing_enable(int on) {
+  com::kernel_timing_enable(on);
+  return COM_OK;
+}
+
+int com_kernel_timing_read(double* filter_ms, double* exact_ms, int64_t* launches) {
+  long long n = 0;
+  com::kernel_timing_read(filter_ms, exact_ms, &n);
+  if (launches) *launches = n;
   return COM_OK;
 }
 

@@ -167,31 +167,6 @@ int aperture_contains(const ComAperture* ap, const double* point) {
 
 namespace {
 
-// Superset of a convex polygon with fewer half-planes: drop an edge when the corner created by its
-// neighbours sticks out by at most delta.  (Conservative: the FP32 filter may only over-accept.)
-std::vector<std::array<double, 3>> simplify_halfplanes(const ComAperture& ap, double delta) {
-  std::vector<std::array<double, 3>> e;
-  for (int k = 0; k < ap.n_edges; ++k) e.push_back({ap.edge[k][0], ap.edge[k][1], ap.edge[k][2]});
-  bool changed = true;
-  while (changed && e.size() > 3) {
-    changed = false;
-    for (size_t k = 0; k < e.size(); ++k) {
-      auto& a = e[(k + e.size() - 1) % e.size()];
-      auto& b = e[(k + 1) % e.size()];
-      double det = a[0] * b[1] - a[1] * b[0];
-      if (std::fabs(det) < 1e-9) continue;  // neighbours parallel: dropping would unbound the polygon
-      double x = (-a[2] * b[1] + b[2] * a[1]) / det, y = (-a[0] * b[2] + b[0] * a[2]) / det;
-      double out = -(e[k][0] * x + e[k][1] * y + e[k][2]);  // how far the new corner is outside edge k
-      if (det > 0 && out >= 0 && out <= delta) {
-        e.erase(e.begin() + k);
-        changed = true;
-        break;
-      }
-    }
-  }
-  return e;
-}
-
 std::vector<P2> vertices_of(const std::vector<std::array<double, 3>>& e) {
   std::vector<P2> v;
   for (size_t k = 0; k < e.size(); ++k) {  // vertex k = edge k-1 /\ edge k  (start of edge k)
@@ -201,23 +176,6 @@ std::vector<P2> vertices_of(const std::vector<std::array<double, 3>>& e) {
     v.push_back({(-a[2] * b[1] + b[2] * a[1]) / det, (-a[0] * b[2] + b[0] * a[2]) / det});
   }
   return v;
-}
-
-void fill_filter_plane(FilterPlane& fp, const ComAperture& ap, const std::vector<std::array<double, 3>>& e,
-                       const double origin[3], float eps) {
-  V3 N = load(ap.normal);
-  V3 nh = (1.0 / norm(N)) * N;
-  V3 q0 = load(ap.p1) - load(origin);
-  for (int i = 0; i < 3; ++i) {
-    fp.n[i] = (float)(&nh.x)[i];
-    fp.q0[i] = (float)(&q0.x)[i];
-    fp.e1[i] = (float)ap.e1[i];
-    fp.e2[i] = (float)ap.e2[i];
-  }
-  fp.n_edges = (int)e.size();
-  fp.eps = eps;
-  for (size_t k = 0; k < e.size(); ++k)
-    for (int i = 0; i < 3; ++i) fp.edge[k][i] = (float)e[k][i];
 }
 
 }  // namespace
@@ -271,11 +229,26 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
     if (rc) return rc;
   }
 
+  // ---- compact fp64 apertures for the exact kernel ------------------------------------------------------
+  hs.dev_apertures.clear();
+  hs.edges.clear();
+  for (const ComAperture& ap : hs.apertures) {
+    DevAperture da{};
+    for (int i = 0; i < 3; ++i) da.p1[i] = ap.p1[i], da.normal[i] = ap.normal[i], da.e1[i] = ap.e1[i], da.e2[i] = ap.e2[i];
+    da.n_edges = ap.n_edges;
+    da.edge_offset = (int)(hs.edges.size() / 3);
+    for (int k = 0; k < ap.n_edges; ++k)
+      for (int i = 0; i < 3; ++i) hs.edges.push_back(ap.edge[k][i]);
+    hs.dev_apertures.push_back(da);
+  }
+  dv.n_edges_total = (int)(hs.edges.size() / 3);
+
   // ---- FP32 filter ----------------------------------------------------------------------------------
+  // Every aperture test of the filter is "bounding rectangle of the polygon, grown by eps": a superset of the
+  // polygon, so the filter can only over-accept; the exact kernel decides.
   double eps = d.filter_eps_mm > 0 ? d.filter_eps_mm : 5e-3;
   dv.filter_disabled = eps >= 1e30 ? 1 : 0;
   if (dv.filter_disabled) eps = 5e-3;
-  const double delta = 0.2 * eps;  // polygon simplification allowance, covered by the band
 
   // slits: one polygon per side, repeated with period T along e1.  Verify the periodicity the collimator
   // builder guarantees (collimator.py:103-119); otherwise the slit stage of the filter is switched off.
@@ -294,89 +267,74 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
             std::fabs(dot(sh, load(a0.normal))) / norm(load(a0.normal)) > 1e-6 || ak.n_edges != a0.n_edges)
           periodic = false;
         for (int e = 0; e < a0.n_edges && periodic; ++e)
-          if (std::hypot(ak.vertex[e][0] - a0.vertex[e][0], ak.vertex[e][1] - a0.vertex[e][1]) > 1e-6)
+          if (std::hypot(ak.vertex[e][0] - a0.vertex[e][0], ak.vertex[e][1] - a0.vertex[e][1]) > 1e-4)
             periodic = false;
       }
     if (!(period > 1e-3)) periodic = false;
   } else {
     period = 1e9;
   }
-  auto ec = simplify_halfplanes(c0, delta), ep = simplify_halfplanes(p0, delta);
-  auto eport = simplify_halfplanes(hs.apertures[2 * S], delta);
-  auto edet = simplify_halfplanes(hs.apertures[2 * S + 1], delta);
-  if ((int)ec.size() > kMaxFilterEdges || (int)ep.size() > kMaxFilterEdges || (int)eport.size() > kMaxFilterEdges) {
-    set_error("filter polygon too large");
-    return COM_E_GEOMETRY;
-  }
-  fill_filter_plane(dv.slit_crys, c0, ec, d.origin, (float)eps);
-  fill_filter_plane(dv.slit_plasma, p0, ep, d.origin, (float)eps);
-  fill_filter_plane(dv.port, hs.apertures[2 * S], eport, d.origin, (float)eps);
-  if (!periodic) dv.slit_crys.n_edges = dv.slit_plasma.n_edges = 0;  // 0 edges = stage skipped (always passes)
+  dv.slit_filter = periodic ? 1 : 0;
   dv.slit_period = (float)period;
   dv.slit_inv_period = (float)(1.0 / period);
-
-  // detector cone: mirror the (simplified) detector polygon in the crystal's tangent plane at every
-  // crystal point; the ray p -> c reflects onto the detector iff the line p-c meets the mirrored polygon,
-  // i.e. iff p lies inside the cone  { g_j . (p - c) >= 0 }  (forward nappe) or its opposite.
-  const ComAperture& det = hs.apertures[2 * S + 1];
-  std::vector<P2> dverts = vertices_of(edet);
-  int NE = (int)dverts.size();
-  if (NE > kMaxConeEdges) {  // fall back to the unsimplified bounding: keep the 8 longest? -> disable stage A
-    set_error("detector section has %d edges after simplification (max %d)", NE, kMaxConeEdges);
-    return COM_E_GEOMETRY;
-  }
-  const int NEpad = NE <= 4 ? 4 : NE <= 6 ? 6 : 8;  // widths the filter kernel is instantiated for
-  dv.cone_edges = NEpad;
-  dv.cone_eps = (float)(4.0 * eps);
-  const int Cp = dv.n_crystal_padded;
-  hs.cone_forms.assign((size_t)4 * NEpad * Cp, 0.f);
-  hs.crystal_f.assign((size_t)4 * Cp, 0.f);
-  std::vector<V3> Q(NE);
-  V3 centroid{0, 0, 0};
-  for (int j = 0; j < NE; ++j) {
-    Q[j] = load(det.p1) + dverts[j].x * load(det.e1) + dverts[j].y * load(det.e2);
-    centroid = centroid + (1.0 / NE) * Q[j];
-  }
-  V3 O = load(d.origin);
-  bool single = d.n_voxel_corners > 0;
-  for (int c = 0; c < Cp; ++c) {
-    if (c >= C) continue;  // padding lanes stay zero; the kernel masks them by index
-    V3 cp = load(&hs.crystal_xyz[3 * (size_t)c]), n = load(&hs.crystal_normal[3 * (size_t)c]);
-    V3 cl = cp - O;
-    hs.crystal_f[4 * (size_t)c + 0] = (float)cl.x;
-    hs.crystal_f[4 * (size_t)c + 1] = (float)cl.y;
-    hs.crystal_f[4 * (size_t)c + 2] = (float)cl.z;
-    auto mirror = [&](V3 q) {
-      V3 r = q - cp;
-      return r - (2.0 * dot(r, n)) * n;  // relative to the crystal point
-    };
-    V3 mc = mirror(centroid);
-    V3 pstar = -1.0 * mc;  // a point (relative to c) whose ray certainly reflects onto the detector
-    bool back_unreachable = false;
-    for (int j = 0; j < NE; ++j) {
-      V3 a = mirror(Q[j]), b = mirror(Q[(j + 1) % NE]);
-      V3 g = cross(a, b);
-      double gl = norm(g);
-      if (!(gl > 0)) {
-        set_error("detector cone degenerate at crystal point %d", c);
-        return COM_E_GEOMETRY;
-      }
-      g = (1.0 / gl) * g;
-      if (dot(g, pstar) < 0) g = -1.0 * g;
-      double h = -dot(g, cl);
-      float* f = &hs.cone_forms[((size_t)j * Cp + c) * 4];
-      f[0] = (float)g.x, f[1] = (float)g.y, f[2] = (float)g.z, f[3] = (float)h;
-      if (single) {  // is the backward nappe (all E_j <= 0) excluded over the voxel hull by this face?
-        double mn = 1e300;
-        for (int q = 0; q < d.n_voxel_corners; ++q) mn = std::min(mn, dot(g, load(d.voxel_corners[q]) - O) + h);
-        if (mn > 8.0 * eps + 1.0) back_unreachable = true;
-      }
+  dv.slit_period_d = periodic ? period : 0.0;
+  auto rect_of = [&](const ComAperture& ap, double grow, double& xlo, double& xhi, double& ylo, double& yhi) {
+    xlo = ylo = 1e300, xhi = yhi = -1e300;
+    for (int k = 0; k < ap.n_edges; ++k) {
+      xlo = std::min(xlo, ap.vertex[k][0]), xhi = std::max(xhi, ap.vertex[k][0]);
+      ylo = std::min(ylo, ap.vertex[k][1]), yhi = std::max(yhi, ap.vertex[k][1]);
     }
-    if (!back_unreachable) single = false;
-    for (int j = NE; j < NEpad; ++j)  // padding faces repeat face 0: neutral for both min and max
-      for (int i = 0; i < 4; ++i) hs.cone_forms[((size_t)j * Cp + c) * 4 + i] = hs.cone_forms[(size_t)c * 4 + i];
+    xlo -= grow, xhi += grow, ylo -= grow, yhi += grow;
+  };
+  double xlo, xhi, ylo, yhi;
+  rect_of(c0, eps, xlo, xhi, ylo, yhi);
+  dv.rect_crys = SlitRect{(float)xlo, (float)xhi, (float)ylo, (float)yhi};
+  rect_of(p0, eps, xlo, xhi, ylo, yhi);
+  dv.rect_plasma = SlitRect{(float)xlo, (float)xhi, (float)ylo, (float)yhi};
+
+  const int Cp = dv.n_crystal_padded;
+  hs.det_forms.assign((size_t)4 * 3 * Cp, 0.f);
+  hs.slit_forms.assign((size_t)4 * 6 * Cp, 0.f);
+  const ComAperture& det = hs.apertures[2 * S + 1];
+  double dxlo, dxhi, dylo, dyhi;
+  rect_of(det, eps, dxlo, dxhi, dylo, dyhi);
+  const double xc = 0.5 * (dxlo + dxhi), yc = 0.5 * (dylo + dyhi), hw = 0.5 * (dxhi - dxlo), hh = 0.5 * (dyhi - dylo);
+  const V3 O = load(d.origin);
+  auto unit_normal = [&](const ComAperture& ap) {
+    V3 N = load(ap.normal);
+    return (1.0 / norm(N)) * N;
+  };
+  // value(p') = F.(c' - p')  ->  g = -F, h = F.c'
+  auto put = [&](std::vector<float>& tab, int form, int c, V3 F, V3 cl) {
+    float* f = &tab[((size_t)form * Cp + c) * 4];
+    f[0] = (float)-F.x, f[1] = (float)-F.y, f[2] = (float)-F.z, f[3] = (float)dot(F, cl);
+  };
+  for (int c = 0; c < Cp; ++c) {
+    if (c >= C) {  // padding lanes: |Xs| = 1e30 can never be <= |W| = 0
+      hs.det_forms[((size_t)0 * Cp + c) * 4 + 3] = 1e30f;
+      continue;
+    }
+    const V3 cp = load(&hs.crystal_xyz[3 * (size_t)c]), n = load(&hs.crystal_normal[3 * (size_t)c]);
+    const V3 cl = cp - O;
+    auto mirror = [&](V3 v) { return v - (2.0 * dot(v, n)) * n; };
+    {  // detector seen in the crystal mirror: the line voxel -> crystal point, continued, meets the mirrored
+       // detector plane at in-plane coordinates x = X'/W, y = Y'/W (homogeneous, linear in the voxel position)
+      const V3 nd = unit_normal(det), q = load(det.p1) - cp;
+      const double a = dot(nd, q), cx0 = dot(load(det.e1), q), cy0 = dot(load(det.e2), q);
+      const V3 Nm = mirror(nd), e1m = mirror(load(det.e1)), e2m = mirror(load(det.e2));
+      put(hs.det_forms, 0, c, (1.0 / hw) * (a * e1m - (cx0 + xc) * Nm), cl);
+      put(hs.det_forms, 1, c, (1.0 / hh) * (a * e2m - (cy0 + yc) * Nm), cl);
+      put(hs.det_forms, 2, c, Nm, cl);
+    }
+    for (int side = 0; side < 2; ++side) {
+      const ComAperture& ap = hs.apertures[side];
+      const V3 nh = unit_normal(ap), q = load(ap.p1) - cp;
+      const double a = dot(nh, q), cx0 = dot(load(ap.e1), q), cy0 = dot(load(ap.e2), q);
+      put(hs.slit_forms, 3 * side + 0, c, a * load(ap.e1) - cx0 * nh, cl);
+      put(hs.slit_forms, 3 * side + 1, c, a * load(ap.e2) - cy0 * nh, cl);
+      put(hs.slit_forms, 3 * side + 2, c, nh, cl);
+    }
   }
-  dv.single_nappe = single ? 1 : 0;
   return COM_OK;
 }
 

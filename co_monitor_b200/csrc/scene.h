@@ -7,18 +7,19 @@
 
 namespace com {
 
-constexpr int kMaxFilterEdges = 32;   // FP32 polygon of one filter plane (port is the largest: 14)
-constexpr int kMaxConeEdges = 8;      // stage-A detector cone faces per crystal point
+// Bounding rectangle of a slit polygon in its aperture frame, band included.
+struct SlitRect {
+  float xlo, xhi, ylo, yhi;
+};
 
-// One aperture plane for the FP32 filter, in the recentred frame (global - origin).
-struct FilterPlane {
-  float n[3];   // unit normal
-  float q0[3];  // plane point (aperture p1)
-  float e1[3];
-  float e2[3];
+// Compact fp64 aperture for the exact kernel: plane, in-plane basis, and a slice of the edge pool.
+struct DevAperture {
+  double p1[3];
+  double normal[3];  // raw (p2-p1) x (p3-p2)
+  double e1[3];
+  double e2[3];
   int n_edges;
-  float eps;    // band in mm at this plane
-  float edge[kMaxFilterEdges][3];  // a*x + b*y + c >= -eps passes; (a,b) unit
+  int edge_offset;  // first (a,b,c) triple in DeviceScene::edges
 };
 
 // Everything the kernels need, passed by value as a __grid_constant__ parameter.
@@ -26,30 +27,34 @@ struct DeviceScene {
   int n_crystal;
   int n_crystal_padded;  // multiple of 32
   int n_slits;
-  int n_apertures;       // 2S + 2
-  int cone_edges;        // faces per crystal point in cone_forms (<= kMaxConeEdges)
-  int single_nappe;      // 1: only the forward nappe of the detector cone can be hit inside voxel_bounds
+  int n_apertures;       // 2S + 2: crys_0, plasma_0, crys_1, ..., port, detector
+  int n_edges_total;
   int filter_disabled;   // 1: every ray goes to the fp64 stage
-  float cone_eps;        // stage-A band, mm of distance from the cone face at the voxel
-  float slit_period;     // 2 |vector_top_bottom| along e1
+  int slit_filter;       // 1: the collimator is periodic and stage B of the filter tests it
+  float slit_period;     // slit pitch along e1 (2 |vector_top_bottom|)
   float slit_inv_period;
+  SlitRect rect_crys, rect_plasma;
+  double slit_period_d;  // 0 when the collimator is not periodic (exact kernel then tries every slit)
   double origin[3];
   double area_pt, refl_max, aoi0, refl_sigma;
   double near_edge_mm;
   const double* crystal_xyz;     // (C,3) global
   const double* crystal_normal;  // (C,3)
-  const ComAperture* apertures;  // (2S+2)
-  const float4* cone_forms;      // [cone_edges][n_crystal_padded]: (gx,gy,gz,h), E = g.p' + h
-  const float4* crystal_f;       // [n_crystal_padded] recentred crystal points, w unused
-  FilterPlane slit_crys, slit_plasma, port;
+  const DevAperture* apertures;  // (2S+2)
+  const double* edges;           // (n_edges_total,3)
+  // FP32 filter tables: linear forms in the recentred voxel position p' = p - origin, value = g.p' + h
+  const float4* det_forms;       // [3][Cp]: Xs, Ys, W of the mirrored detector; passes iff max(|Xs|,|Ys|) <= |W|
+  const float4* slit_forms;      // [6][Cp]: X', Y', W on the crystal-side slit plane, then on the plasma side
 };
 
 // Host-side result of analysing a ComSceneDesc (pure CPU, no CUDA).
 struct HostScene {
   DeviceScene dev{};                  // pointers unset
   std::vector<ComAperture> apertures; // 2S + 2
-  std::vector<float> cone_forms;      // 4 * cone_edges * n_crystal_padded
-  std::vector<float> crystal_f;       // 4 * n_crystal_padded
+  std::vector<DevAperture> dev_apertures;
+  std::vector<double> edges;
+  std::vector<float> det_forms;       // 4 * 3 * Cp
+  std::vector<float> slit_forms;      // 4 * 6 * Cp
   std::vector<double> crystal_xyz, crystal_normal;
 };
 
@@ -64,5 +69,6 @@ struct ComScene {
   com::DeviceScene dev{};
   std::vector<ComAperture> apertures_h;
   void* d_blob = nullptr;  // single device allocation holding all tables
+  double filter_eps_mm = 0;
   int device = 0;
 };

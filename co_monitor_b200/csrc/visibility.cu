@@ -83,61 +83,37 @@ __device__ __forceinline__ D3 voxel_position(const VoxelSource& v, long long fla
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1a stage B: collimator (periodic, both sides) and port, FP32 with band.
-struct F3 {
-  float x, y, z;
-};
-__device__ __forceinline__ float dotf(const float* a, F3 b) { return fmaf(a[0], b.x, fmaf(a[1], b.y, a[2] * b.z)); }
-
-// Homogeneous in-plane hit of the line c + s*u with the plane: x = X/W, y = Y/W.
-__device__ __forceinline__ void plane_hit_h(const FilterPlane& pl, F3 c, F3 u, float& X, float& Y, float& W) {
-  F3 r = {c.x - pl.q0[0], c.y - pl.q0[1], c.z - pl.q0[2]};
-  float nd = dotf(pl.n, u), a = -dotf(pl.n, r);
-  X = fmaf(dotf(pl.e1, r), nd, a * dotf(pl.e1, u));
-  Y = fmaf(dotf(pl.e2, r), nd, a * dotf(pl.e2, u));
-  W = nd;
+// K1a stage B: periodic collimator, both sides, FP32.  x = X'/W, y = Y'/W are the in-plane hit coordinates
+// relative to slit 0; slit k is slit 0 moved by k*T along x.  Bounding rectangles grown by eps: superset.
+__device__ __forceinline__ float form(const float4 g, const float4 p) {
+  return fmaf(g.x, p.x, fmaf(g.y, p.y, fmaf(g.z, p.z, g.w)));
 }
 
-__device__ __forceinline__ bool poly_pass(const FilterPlane& pl, float x, float y) {
-  float m = 1e30f;
-  for (int k = 0; k < pl.n_edges; ++k) m = fminf(m, fmaf(pl.edge[k][0], x, fmaf(pl.edge[k][1], y, pl.edge[k][2])));
-  return m >= -pl.eps;
-}
-
-__device__ __forceinline__ bool stage_b(const DeviceScene& sc, F3 p, F3 c) {
-  F3 u = {p.x - c.x, p.y - c.y, p.z - c.z};
-  float X, Y, W;
-  // port: homogeneous test, no division
-  plane_hit_h(sc.port, c, u, X, Y, W);
-  {
-    float s = W < 0.f ? -1.f : 1.f, aw = fabsf(W), m = 1e30f;
-    for (int k = 0; k < sc.port.n_edges; ++k) {
-      float e = fmaf(sc.port.edge[k][0], X, fmaf(sc.port.edge[k][1], Y, sc.port.edge[k][2] * W));
-      m = fminf(m, s * e);
-    }
-    if (!(m >= -sc.port.eps * aw) && aw > 1e-3f) return false;
-  }
-  if (sc.slit_crys.n_edges == 0) return true;  // non-periodic collimator: decided in fp64 only
-  float Xp, Yp, Wp;
-  plane_hit_h(sc.slit_crys, c, u, X, Y, W);
-  plane_hit_h(sc.slit_plasma, c, u, Xp, Yp, Wp);
-  if (fabsf(W) < 1e-3f || fabsf(Wp) < 1e-3f) return true;  // grazing: let fp64 decide
-  float x = X / W, y = Y / W, xp = Xp / Wp, yp = Yp / Wp;
-  float kf = floorf(x * sc.slit_inv_period);
+__device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, int cj) {
+  if (!sc.slit_filter) return true;  // non-periodic collimator: decided in fp64 only
+  const int Cp = sc.n_crystal_padded;
+  const float4* f = sc.slit_forms + cj;
+  const float Xc = form(__ldg(f), p), Yc = form(__ldg(f + Cp), p), Wc = form(__ldg(f + 2 * Cp), p);
+  const float Xp = form(__ldg(f + 3 * Cp), p), Yp = form(__ldg(f + 4 * Cp), p), Wp = form(__ldg(f + 5 * Cp), p);
+  if (fabsf(Wc) < 1e-3f || fabsf(Wp) < 1e-3f) return true;  // grazing ray: let fp64 decide
+  const float ic = __frcp_rn(Wc), ip = __frcp_rn(Wp);
+  const float xc = Xc * ic, yc = Yc * ic, xp = Xp * ip, yp = Yp * ip;
+  if (!(yc >= sc.rect_crys.ylo && yc <= sc.rect_crys.yhi && yp >= sc.rect_plasma.ylo && yp <= sc.rect_plasma.yhi))
+    return false;
+  const float kf = floorf(xc * sc.slit_inv_period);
   bool ok = false;
 #pragma unroll
   for (int dk = 0; dk < 2; ++dk) {
-    float k = kf + (float)dk;
-    if (k >= 0.f && k < (float)sc.n_slits) {
-      float sh = k * sc.slit_period;
-      ok |= poly_pass(sc.slit_crys, x - sh, y) && poly_pass(sc.slit_plasma, xp - sh, yp);
-    }
+    const float k = kf + (float)dk;
+    const float sh = k * sc.slit_period;
+    const float a = xc - sh, b = xp - sh;
+    ok |= k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
+          b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
   }
   return ok;
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int NE, bool SINGLE>
 __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_constant__ K1Params P) {
   __shared__ float4 s_tile[kTileVoxels];
   __shared__ unsigned int s_queue[kMaxWarps][kQueueCap];
@@ -146,13 +122,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
   const DeviceScene& sc = P.sc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Cp = sc.n_crystal_padded;
-  const float eps = sc.cone_eps;
-  const bool all_pass = sc.filter_disabled != 0;
   const int n_items = P.n_tiles * P.n_super;
   unsigned int* queue = s_queue[warp];
+  bool all_pass = false;  // filter disabled: every real ray is a candidate (padding lanes never are)
 
   int cur_super = -1;
-  float4 g[NE];
+  float4 gx, gy, gw;  // detector forms of this lane's crystal point
   int ci = 0;
   bool warp_active = false;
 
@@ -166,39 +141,34 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
     const long long tile_base = (long long)tile * kTileVoxels;
     const int nv = (int)min((long long)kTileVoxels, P.n_vox - tile_base);
 
-    // stage the tile: fp64 position -> recentred FP32
+    // stage the tile: fp64 position -> recentred FP32 (w = 1 so that a form is one dot4-like FFMA chain)
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
       D3 p = voxel_position(P.vox, P.vox_begin + tile_base + i);
-      s_tile[i] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 0.f);
+      s_tile[i] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 1.f);
     }
     if (sup != cur_super) {
       cur_super = sup;
       ci = (sup * P.warps_per_cta + warp) * 32 + lane;
       warp_active = (sup * P.warps_per_cta + warp) * 32 < Cp;
+      all_pass = sc.filter_disabled != 0 && ci < sc.n_crystal;
       if (warp_active) {
-#pragma unroll
-        for (int j = 0; j < NE; ++j) g[j] = __ldg(&sc.cone_forms[(size_t)j * Cp + ci]);
+        gx = __ldg(&sc.det_forms[ci]);
+        gy = __ldg(&sc.det_forms[Cp + ci]);
+        gw = __ldg(&sc.det_forms[2 * Cp + ci]);
       }
     }
     __syncthreads();
     if (!warp_active) continue;
 
-    const float4 cf = __ldg(&sc.crystal_f[ci]);
-    const F3 c = {cf.x, cf.y, cf.z};
     int qn = 0;  // warp-uniform queue fill
 
     auto drain = [&](int take) {  // stage B on `take` (<= 32) queued rays, then append survivors
       __syncwarp();
-      const unsigned int ent = lane < take ? queue[qn - take + lane] : 0u;
-      const int src = ent & 31;
-      F3 cc;  // crystal point of the queued ray lives in lane `src` of this warp
-      cc.x = __shfl_sync(0xffffffffu, c.x, src);
-      cc.y = __shfl_sync(0xffffffffu, c.y, src);
-      cc.z = __shfl_sync(0xffffffffu, c.z, src);
       bool keep = false;
+      unsigned int ent = 0;
       if (lane < take) {
-        const float4 pv = s_tile[ent >> 5];
-        keep = all_pass || stage_b(sc, F3{pv.x, pv.y, pv.z}, cc);
+        ent = queue[qn - take + lane];
+        keep = sc.filter_disabled != 0 || stage_b(sc, s_tile[ent >> 5], ci - lane + (int)(ent & 31));
       }
       qn -= take;
       const unsigned int b = __ballot_sync(0xffffffffu, keep);
@@ -209,33 +179,42 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
         if (keep) {
           const unsigned long long pos = base + __popc(b & ((1u << lane) - 1u));
           if (pos < P.cand_capacity)
-            P.cand[pos] = make_uint2((unsigned int)(tile_base + (ent >> 5)), (unsigned int)(ci - lane + src));
+            P.cand[pos] = make_uint2((unsigned int)(tile_base + (ent >> 5)), (unsigned int)(ci - lane + (ent & 31)));
         }
       }
       __syncwarp();
     };
-
-    for (int v0 = 0; v0 < nv; v0 += kUnroll) {
-#pragma unroll
-      for (int i = 0; i < kUnroll; ++i) {
-        const int v = v0 + i;
-        const float4 p = s_tile[v < nv ? v : nv - 1];
-        float m = 1e30f, M = -1e30f;
-#pragma unroll
-        for (int j = 0; j < NE; ++j) {
-          const float e = fmaf(g[j].x, p.x, fmaf(g[j].y, p.y, fmaf(g[j].z, p.z, g[j].w)));
-          m = fminf(m, e);
-          if (!SINGLE) M = fmaxf(M, e);
-        }
-        bool pass = m >= -eps;
-        if (!SINGLE) pass = pass || (M <= eps);
-        pass = (pass || all_pass) && v < nv && ci < sc.n_crystal;
-        const unsigned int b = __ballot_sync(0xffffffffu, pass);
-        if (b) {
-          if (pass) queue[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned int)v << 5) | (unsigned int)lane;
-          qn += __popc(b);
-        }
+    // margin of one ray against the mirrored detector rectangle: >= 0 passes (band folded into the forms)
+    auto margin = [&](int v) {
+      const float4 p = s_tile[v];
+      const float xs = form(gx, p), ys = form(gy, p), w = form(gw, p);
+      return fabsf(w) - fmaxf(fabsf(xs), fabsf(ys));
+    };
+    auto push = [&](int v, bool pass) {
+      const unsigned int b = __ballot_sync(0xffffffffu, pass);
+      if (b) {
+        if (pass) queue[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned int)v << 5) | (unsigned int)lane;
+        qn += __popc(b);
       }
+    };
+
+    int v0 = 0;
+#pragma unroll 1
+    for (; v0 + kUnroll <= nv; v0 += kUnroll) {
+      float t[kUnroll];
+#pragma unroll
+      for (int i = 0; i < kUnroll; ++i) t[i] = margin(v0 + i);
+      float tm = t[0];
+#pragma unroll
+      for (int i = 1; i < kUnroll; ++i) tm = fmaxf(tm, t[i]);
+      if (__any_sync(0xffffffffu, tm >= 0.f || all_pass)) {
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) push(v0 + i, t[i] >= 0.f || all_pass);
+        while (qn >= 32) drain(32);
+      }
+    }
+    for (; v0 < nv; ++v0) {
+      push(v0, margin(v0) >= 0.f || all_pass);
       while (qn >= 32) drain(32);
     }
     if (qn > 0) drain(qn);
@@ -247,32 +226,57 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
 struct HitResult {
   bool pass;
   double margin;
+  double x;  // in-plane coordinate along e1 (used to pick the slit)
 };
 
 // simulation.py:143-173 (+175-207): line through `dst` with direction src - dst against the aperture plane,
-// then the polygon test that replaces Delaunay.find_simplex (geometry_host.cu).
-__device__ __forceinline__ HitResult aperture_hit(const ComAperture& ap, D3 src, D3 dst) {
-  D3 N = ld3(ap.normal), u = src - dst;
-  double ndotu = dot(N, u);
-  if (fabs(ndotu) < 1e-6) return {false, -1e300};  // the reference writes NaN -> never inside
-  D3 w = dst - ld3(ap.p1);
-  double si = -(dot(N, w) / ndotu);
-  D3 r = w + si * u;  // X - p1
-  double x = dot(r, ld3(ap.e1)), y = dot(r, ld3(ap.e2));
+// then the polygon test that replaces Delaunay.find_simplex (geometry_host.cu / apertures.py).
+__device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const double* __restrict__ edges, D3 src,
+                                                  D3 dst) {
+  const D3 N = ld3(ap.normal), u = src - dst;
+  const double ndotu = dot(N, u);
+  if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0};  // the reference writes NaN -> never inside
+  const D3 w = dst - ld3(ap.p1);
+  const double si = -(dot(N, w) / ndotu);
+  const D3 r = w + si * u;  // X - p1
+  const double x = dot(r, ld3(ap.e1)), y = dot(r, ld3(ap.e2));
   double m = 1e300;
-  for (int k = 0; k < ap.n_edges; ++k) m = fmin(m, ap.edge[k][0] * x + ap.edge[k][1] * y + ap.edge[k][2]);
-  return {m >= 0.0, m};
+  const double* e = edges + 3 * ap.edge_offset;
+  for (int k = 0; k < ap.n_edges; ++k) m = fmin(m, e[3 * k] * x + e[3 * k + 1] * y + e[3 * k + 2]);
+  return {m >= 0.0, m, x};
 }
 
-__global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ K1Params P) {
+constexpr int kExactThreads = 128;
+
+__global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_constant__ K1Params P) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const DeviceScene& sc = P.sc;
   const unsigned long long n = min(P.counters[0], P.cand_capacity);
+  if ((unsigned long long)blockIdx.x * kExactThreads >= n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      P.stats->candidates = P.counters[0];
+      P.stats->candidate_capacity = P.cand_capacity;
+      P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
+    }
+    return;
+  }
+  // apertures + edge pool -> shared memory (a few kB)
+  DevAperture* s_ap = reinterpret_cast<DevAperture*>(s_raw);
+  double* s_edges = reinterpret_cast<double*>(s_raw + sizeof(DevAperture) * sc.n_apertures);
+  {
+    const double* src = reinterpret_cast<const double*>(sc.apertures);
+    double* dst = reinterpret_cast<double*>(s_ap);
+    const int n_ap_d = (int)(sizeof(DevAperture) / sizeof(double)) * sc.n_apertures;
+    for (int i = threadIdx.x; i < n_ap_d; i += kExactThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < 3 * sc.n_edges_total; i += kExactThreads) s_edges[i] = sc.edges[i];
+  }
+  __syncthreads();
+
   const int S = sc.n_slits;
   unsigned int n_pass = 0, n_edge = 0, n_vis = 0;
   const double kNear = sc.near_edge_mm;
-
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x;
+  if (i < n) {
     const uint2 e = P.cand[i];
     const long long vloc = e.x;
     const int ci = (int)e.y;
@@ -284,52 +288,59 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ K1Pa
     const D3 reflected = c + r, plasma = c - d, crystal = p + d;
 
     bool near_edge = false;
-    HitResult h = aperture_hit(sc.apertures[2 * S + 1], reflected, crystal);  // detector :387-400
+    HitResult h = aperture_hit(s_ap[2 * S], s_edges, plasma, crystal);  // port :372-384
     near_edge |= fabs(h.margin) < kNear;
     bool ok = h.pass;
-    if (ok) {
-      h = aperture_hit(sc.apertures[2 * S], plasma, crystal);  // port :372-384
-      near_edge |= fabs(h.margin) < kNear;
-      ok = h.pass;
-    }
-    if (ok) {
+    if (ok) {  // collimator :344-369, the same slit on both sides
       ok = false;
-      for (int k = 0; k < S && !ok; ++k) {  // :344-369, same slit on both sides
-        HitResult a = aperture_hit(sc.apertures[2 * k], plasma, crystal);
+      int k_lo = 0, k_hi = S - 1;
+      if (sc.slit_period_d > 0.0) {  // slit k is slit 0 moved by k*T along e1: only k0-1..k0+1 can contain the hit
+        const HitResult h0 = aperture_hit(s_ap[0], s_edges, plasma, crystal);
+        const int k0 = (int)floor(h0.x / sc.slit_period_d);
+        k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
+        if (h0.margin == -1e300) k_hi = -1;  // parallel to the collimator plane: NaN in the reference
+      }
+      for (int k = k_lo; k <= k_hi && !ok; ++k) {
+        const HitResult a = aperture_hit(s_ap[2 * k], s_edges, plasma, crystal);
         near_edge |= fabs(a.margin) < kNear;
         if (!a.pass) continue;
-        HitResult b = aperture_hit(sc.apertures[2 * k + 1], plasma, crystal);
+        const HitResult b = aperture_hit(s_ap[2 * k + 1], s_edges, plasma, crystal);
         near_edge |= fabs(b.margin) < kNear;
         ok = b.pass;
       }
     }
+    if (ok) {
+      h = aperture_hit(s_ap[2 * S + 1], s_edges, reflected, crystal);  // detector :387-400
+      near_edge |= fabs(h.margin) < kNear;
+      ok = h.pass;
+    }
     n_edge += near_edge ? 1u : 0u;
-    if (!ok) continue;
+    if (ok) {
+      // simulation.py:494-497, 516-531, 564-577
+      const D3 v = plasma - crystal, rc = reflected - crystal;
+      const double vv = dot(v, v), dist = sqrt(vv);
+      const double cosang = dot(v, rc) / (sqrt(vv) * sqrt(dot(rc, rc)));
+      const double deg = acos(cosang) * (180.0 / 3.141592653589793);
+      const double aoi = (180.0 - rint(deg * 100.0) / 100.0) / 2.0;
+      const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * (dist * dist));
+      const double da = aoi - sc.aoi0;
+      const double prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
+      const double w = fraction * prof;
 
-    // simulation.py:494-497, 516-531, 564-577
-    const D3 v = plasma - crystal, rc = reflected - crystal;
-    const double vv = dot(v, v), dist = sqrt(vv);
-    const double cosang = dot(v, rc) / (sqrt(vv) * sqrt(dot(rc, rc)));
-    const double deg = acos(cosang) * (180.0 / 3.141592653589793);
-    const double aoi = (180.0 - rint(deg * 100.0) / 100.0) / 2.0;
-    const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * (dist * dist));
-    const double da = aoi - sc.aoi0;
-    const double prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
-    const double w = fraction * prof;
-
-    ++n_pass;
-    atomicAdd(&P.w_out[vloc], w);
-    if (P.nrays_out) {
-      if (atomicAdd(&P.nrays_out[vloc], 1u) == 0u) ++n_vis;
-    }
-    if (P.hist_out) {
-      const int bin = P.reff_bin[P.vox_begin + vloc];
-      if (bin < P.n_bins) atomicAdd(&P.hist_out[bin], w);
-    }
-    if (P.rays_out) {
-      const unsigned long long pos = atomicAdd(P.rays_count, 1ull);
-      if ((long long)pos < P.rays_capacity)
-        P.rays_out[pos] = ComRayRecord{(P.vox_begin + vloc) * (long long)sc.n_crystal + ci, dist, aoi, w};
+      ++n_pass;
+      atomicAdd(&P.w_out[vloc], w);
+      if (P.nrays_out) {
+        if (atomicAdd(&P.nrays_out[vloc], 1u) == 0u) ++n_vis;
+      }
+      if (P.hist_out) {
+        const int bin = P.reff_bin[P.vox_begin + vloc];
+        if (bin < P.n_bins) atomicAdd(&P.hist_out[bin], w);
+      }
+      if (P.rays_out) {
+        const unsigned long long pos = atomicAdd(P.rays_count, 1ull);
+        if ((long long)pos < P.rays_capacity)
+          P.rays_out[pos] = ComRayRecord{(P.vox_begin + vloc) * (long long)sc.n_crystal + ci, dist, aoi, w};
+      }
     }
   }
 
@@ -349,9 +360,9 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ K1Pa
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
-    atomicAdd((unsigned long long*)&P.stats->near_edge_rays, (unsigned long long)s_acc[1]);
-    atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[2]);
+    if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
+    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->near_edge_rays, (unsigned long long)s_acc[1]);
+    if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[2]);
     if (blockIdx.x == 0) {
       const unsigned long long total = P.counters[0];
       P.stats->candidates = total;
@@ -363,6 +374,39 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ K1Pa
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Optional per-kernel timing (bench.py's roofline leg): events on the launching stream around K1a / K1b.
+static bool g_timing_on = false;
+static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static double g_ms_accum[2] = {0, 0};
+static long long g_ms_launches = 0;
+static bool g_ev_pending = false;
+
+static void timing_collect() {
+  if (!g_ev_pending) return;
+  cudaEventSynchronize(g_ev[2]);
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, g_ev[0], g_ev[1]);
+  cudaEventElapsedTime(&b, g_ev[1], g_ev[2]);
+  g_ms_accum[0] += a, g_ms_accum[1] += b, ++g_ms_launches;
+  g_ev_pending = false;
+}
+
+void kernel_timing_enable(int on) {
+  timing_collect();
+  g_timing_on = on != 0;
+  if (g_timing_on && !g_ev[0])
+    for (auto& e : g_ev) cudaEventCreate(&e);
+  g_ms_accum[0] = g_ms_accum[1] = 0;
+  g_ms_launches = 0;
+}
+
+void kernel_timing_read(double* filter_ms, double* exact_ms, long long* launches) {
+  timing_collect();
+  if (filter_ms) *filter_ms = g_ms_accum[0];
+  if (exact_ms) *exact_ms = g_ms_accum[1];
+  if (launches) *launches = g_ms_launches;
+}
+
 static int pick_warps(int n_groups) {  // warps per CTA wasting the fewest idle warps; ties -> larger CTA
   if (n_groups <= kMaxWarps) return n_groups;
   int best = kMaxWarps, best_waste = 1 << 30;
@@ -371,25 +415,6 @@ static int pick_warps(int n_groups) {  // warps per CTA wasting the fewest idle 
     if (waste <= best_waste) best = w, best_waste = waste;
   }
   return best;
-}
-
-template <int NE>
-static cudaError_t launch_filter(const K1Params& P, int grid, int threads, cudaStream_t s) {
-  if (P.sc.single_nappe)
-    filter_kernel<NE, true><<<grid, threads, 0, s>>>(P);
-  else
-    filter_kernel<NE, false><<<grid, threads, 0, s>>>(P);
-  return cudaGetLastError();
-}
-
-template <int NE>
-static int filter_occupancy(bool single, int threads) {
-  int n = 0;
-  if (single)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, filter_kernel<NE, true>, threads, 0);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, filter_kernel<NE, false>, threads, 0);
-  return n;
 }
 
 size_t visibility_workspace_bytes(const DeviceScene& sc, long long n_vox, double frac) {
@@ -467,24 +492,30 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   COM_CUDA(cudaGetDevice(&dev));
   COM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int threads = P.warps_per_cta * 32;
-  const int ne = P.sc.cone_edges;
-  const bool single = P.sc.single_nappe != 0;
-  int occ = ne <= 4 ? filter_occupancy<4>(single, threads)
-            : ne <= 6 ? filter_occupancy<6>(single, threads)
-                      : filter_occupancy<8>(single, threads);
+  int occ = 0;
+  COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, threads, 0));
   if (occ < 1) occ = 1;
   const long long items = (long long)P.n_tiles * P.n_super;
   const int grid = (int)std::min<long long>(items, (long long)sms * occ);
-  // cone_forms is padded to the template width by scene creation (see capi.cu)
-  e = ne <= 4 ? launch_filter<4>(P, grid, threads, stream)
-      : ne <= 6 ? launch_filter<6>(P, grid, threads, stream)
-                : launch_filter<8>(P, grid, threads, stream);
-  if (e != cudaSuccess) {
-    set_error("filter_kernel launch failed: %s", cudaGetErrorString(e));
-    return COM_E_CUDA;
+  if (g_timing_on) {
+    timing_collect();
+    cudaEventRecord(g_ev[0], stream);
   }
-  exact_kernel<<<sms * 8, 128, 0, stream>>>(P);
+  filter_kernel<<<grid, threads, 0, stream>>>(P);
   COM_CUDA(cudaGetLastError());
+  if (g_timing_on) cudaEventRecord(g_ev[1], stream);
+  {
+    // one thread per candidate slot; blocks beyond the actual count exit at once
+    const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
+    const unsigned int blocks = (unsigned int)std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, 0x7fffffffull);
+    const size_t smem = sizeof(DevAperture) * P.sc.n_apertures + sizeof(double) * 3 * P.sc.n_edges_total;
+    exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
+  }
+  COM_CUDA(cudaGetLastError());
+  if (g_timing_on) {
+    cudaEventRecord(g_ev[2], stream);
+    g_ev_pending = true;
+  }
 #undef COM_CUDA
   return COM_OK;
 }

@@ -132,11 +132,11 @@ class ChannelScene:
 
     # -- introspection -------------------------------------------------------------------
     def filter_info(self) -> dict:
-        ce, sn, se, pe = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
-        eps = C.c_double()
-        _lib.check(self._lib.com_scene_filter_info(self.handle, C.byref(ce), C.byref(sn), C.byref(se), C.byref(pe),
+        sf, fd = C.c_int32(), C.c_int32()
+        period, eps = C.c_double(), C.c_double()
+        _lib.check(self._lib.com_scene_filter_info(self.handle, C.byref(sf), C.byref(fd), C.byref(period),
                                                    C.byref(eps)), "com_scene_filter_info")
-        return dict(cone_edges=ce.value, single_nappe=bool(sn.value), slit_edges=se.value, port_edges=pe.value,
+        return dict(slit_filter=bool(sf.value), filter_disabled=bool(fd.value), slit_period_mm=period.value,
                     eps_mm=eps.value)
 
     def aperture(self, index: int) -> _lib.ComAperture:
@@ -223,6 +223,11 @@ class ChannelScene:
                 rays = rays_t[: cnt * 4].cpu().numpy().view(_lib.RAY_RECORD_DTYPE).copy()
         return VisibilityResult(begin=begin, end=end, weight=w, nrays=nr, stats=stats, rays=rays)
 
+    def plan(self, lattice: Lattice, begin: int = 0, end: int | None = None, candidate_fraction: float = 0.0,
+             device=None) -> "VisibilityPlan":
+        """Pre-allocated, sync-free launcher for repeated Stage-1 runs over the same voxel range."""
+        return VisibilityPlan(self, lattice, begin, lattice.n_points if end is None else end, candidate_fraction, device)
+
     def compact(self, result: VisibilityResult):
         """Visible voxels of *result*: (flat indices int64, weights float64), device tensors, ascending."""
         import torch
@@ -242,3 +247,59 @@ class ChannelScene:
             _lib.check(rc, "com_compact_visible")
             m = int(cnt.item())
         return idx[:m], wc[:m]
+
+
+class VisibilityPlan:
+    """Device buffers + arguments of one ``com_visibility_weights`` call, reusable without host syncs."""
+
+    def __init__(self, scene: ChannelScene, lattice: Lattice, begin: int, end: int, candidate_fraction: float, device):
+        import torch
+
+        self.scene, self.begin, self.end = scene, begin, end
+        self.device = torch.device(device if device is not None else "cuda")
+        n = end - begin
+        self._lat = lattice_struct(lattice)
+        with torch.cuda.device(self.device):
+            self.weight = torch.empty(n, dtype=torch.float64, device=self.device)
+            self.nrays = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.stats_t = torch.zeros(8, dtype=torch.int64, device=self.device)
+            self.ws_bytes = scene._lib.com_visibility_workspace_bytes(scene.handle, n, candidate_fraction)
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def launch(self, stream=None) -> None:
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        s = self.scene
+        rc = s._lib.com_visibility_weights(
+            s.handle, C.byref(self._lat), None, self.begin, self.end, C.c_void_p(self.weight.data_ptr()),
+            C.c_void_p(self.nrays.data_ptr()), None, 0, None, None, None, 0, C.c_void_p(self.stats_t.data_ptr()),
+            C.c_void_p(self.ws.data_ptr()), self.ws_bytes, C.c_void_p(stream))
+        _lib.check(rc, "com_visibility_weights")
+
+    def stats(self) -> dict:
+        out = dict(zip([f[0] for f in _lib.ComStats._fields_], self.stats_t.cpu().tolist()))
+        out.pop("reserved", None)
+        return out
+
+
+def make_channel(element: str, slits_number: int = 10, crystal_height_step: int = 20, crystal_length_step: int = 80,
+                 lattice: Lattice | None = None, **scene_kwargs) -> ChannelScene:
+    """Channel scene from the reference's setup classes (what ``Simulation.__init__`` collects, :77-141)."""
+    from .collimator import Collimator
+    from .detector import Detector
+    from .dispersive_element import DispersiveElement
+    from .port import Port
+
+    col = Collimator(element, "top closing side", slits_number)
+    _, crys, plas = col.read_colim_coord()
+    de = DispersiveElement(element, crystal_height_step, crystal_length_step)
+    port, det = Port(), Detector(element)
+    normals = crystal_normals(de.crystal_points, de.radius_central_point, de.B, de.C)
+    area = round(20 * 80 / crystal_height_step / crystal_length_step, 2)
+    corners = lattice.bounding_corners() if lattice is not None else None
+    return ChannelScene(de.crystal_points, normals, crys, plas, col.vector_front_back, port.vertices_coordinates,
+                        port.orientation_vector, det.vertices, det.orientation_vector,
+                        origin=de.crystal_central_point, area_pt=area, refl_max=de.max_reflectivity,
+                        aoi0=float(de.AOI), voxel_corners=corners, **scene_kwargs)

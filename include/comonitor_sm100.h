@@ -102,11 +102,10 @@ typedef struct ComSceneDesc {
                                     Qhull covered with a flat simplex, i.e. up to ~1e-4 mm beyond an edge.     */
   double near_edge_mm;           /* |margin| below which a decided ray is counted in ComStats.near_edge_rays;
                                     <= 0 selects 1e-9 mm                                               */
-  int32_t n_voxel_corners;       /* 0 = unknown (general two-nappe detector filter), else <= 8        */
-  int32_t reserved;
-  double voxel_corners[8][3];    /* points whose convex hull contains every voxel that will be tested
-                                    (the 8 corners of the lattice); lets the filter drop the backward
-                                    nappe of the detector cone when it cannot be reached               */
+  int32_t n_voxel_corners;       /* optional hint, 0..8: points whose convex hull contains every voxel that   */
+  int32_t reserved;              /* will be tested (the lattice corners).  Not needed for correctness: the    */
+  double voxel_corners[8][3];    /* filter accepts both nappes of the detector cone, as the reference's
+                                    infinite-line intersection does (simulation.py:143-173).              */
 } ComSceneDesc;
 
 typedef struct ComScene ComScene; /* opaque: device-resident tables of one channel */
@@ -116,9 +115,10 @@ int com_scene_destroy(ComScene* scene);
 /* number of apertures (2S+2, order: crys_0, plasma_0, crys_1, ..., port, detector) and a host copy of one */
 int com_scene_aperture_count(const ComScene* scene);
 int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* out_h);
-/* what the FP32 filter was built with (any output pointer may be NULL) */
-int com_scene_filter_info(const ComScene* scene, int32_t* cone_edges, int32_t* single_nappe, int32_t* slit_edges,
-                          int32_t* port_edges, double* eps_mm);
+/* what the FP32 filter was built with (any output pointer may be NULL): whether the collimator was found periodic
+ * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
+int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled,
+                          double* slit_period_mm, double* eps_mm);
 
 /* Implicit voxel lattice == CuboidMesh (mesh_calculation.py:119-159):
  *   flat = (iy*nx + ix)*nz + iz ;  p = ((x[ix],y[iy],z[iz]) - centre) . R + centre + shift
@@ -189,6 +189,17 @@ int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64
                         double* w_compact, uint64_t* count_out, void* workspace, size_t workspace_bytes,
                         com_stream_t stream);
 size_t com_compact_workspace_bytes(int64_t n);
+
+/* Measurement aid (not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
+ * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the
+ * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 exact kernel
+ * and the number of calls since the last enable. */
+int com_kernel_timing_enable(int on);
+int com_kernel_timing_read(double* filter_ms, double* exact_ms, int64_t* launches);
+
+/* FP32 FMA throughput of the current device measured by a register-only probe kernel, TFLOP/s (FMA = 2);
+ * the denominator bench.py reports next to the nominal 148 x 128 x 2 x f_max.  < 0 on error. */
+double com_measure_fp32_tflops(void);
 
 const char* com_last_error(void);
 const char* com_error_string(int code);
