@@ -109,6 +109,34 @@ class ComStats(C.Structure):
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
 
 
+COM_MAX_TRANSITIONS = 4
+
+
+class ComPecDesc(C.Structure):
+    _fields_ = [
+        ("n_ne", C.c_int32),
+        ("n_te", C.c_int32),
+        ("n_grid", C.c_int32),
+        ("use_fully_stripped", C.c_int32),
+        ("ne_nodes", C.POINTER(C.c_double)),
+        ("te_nodes", C.POINTER(C.c_double)),
+        ("table", C.POINTER(C.c_double)),
+        ("ne_grid", C.POINTER(C.c_double)),
+        ("te_grid", C.POINTER(C.c_double)),
+    ]
+
+
+class ComTablesDesc(C.Structure):
+    _fields_ = [
+        ("n_fa", C.c_int32),
+        ("n_transitions", C.c_int32),
+        ("fa_T", C.POINTER(C.c_double)),
+        ("fa_ion", C.POINTER(C.c_double)),
+        ("fa_last", C.POINTER(C.c_double)),
+        ("pec", ComPecDesc * COM_MAX_TRANSITIONS),
+    ]
+
+
 RAY_RECORD_DTYPE = np.dtype(
     [("ray_index", np.int64), ("distance", np.float64), ("aoi", np.float64), ("weight", np.float64)]
 )
@@ -141,6 +169,15 @@ def _declare(lib):
     lib.com_compact_workspace_bytes.restype = C.c_size_t
     lib.com_compact_workspace_bytes.argtypes = [i64]
     lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.com_tables_create.argtypes = [C.POINTER(ComTablesDesc), C.POINTER(vp)]
+    lib.com_tables_destroy.argtypes = [vp]
+    lib.com_emissivity_workspace_bytes.restype = C.c_size_t
+    lib.com_emissivity_workspace_bytes.argtypes = [i64]
+    lib.com_emissivity_integrate.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, i64, vp, vp, vp, vp,
+                                             C.c_size_t, vp]
+    lib.com_emissivity_integrate_host.argtypes = [C.POINTER(ComTablesDesc), dp, i32, C.c_double, dp, dp, i64, dp, vp, vp, dp]
+    lib.com_weight_histogram.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, i64, vp, vp, vp, C.c_size_t, vp]
+    lib.com_emissivity_sweep.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, vp]
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
     lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
@@ -156,6 +193,8 @@ EXPORTED_SYMBOLS = [
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
     "com_compact_workspace_bytes", "com_compact_visible",
     "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
+    "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
+    "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep",
 ]
 
 

@@ -1,0 +1,539 @@
+// Stage 2 on sm_100a: line-emissivity integration.
+//
+// Reference semantics (co_monitor/emissivity/reader.py):
+//   :199-243  nearest profile row per voxel: argmin_k |Reff_k - Reff_v| (first minimum), boundary cut Reff >= b dropped,
+//             b = min(max mapped Reff, max profile Reff); NaN Reff dropped (:176)
+//   :282-314  nearest fractional-abundance temperature on arange(5, 20000, 1)
+//   :316-341  per transition: nearest index on the 2000-point linspace ne grid and Te grid, PEC looked up there
+//             (pec.py:153-187: the grid values are the bilinear interpolant of the ADAS nodes)
+//   :343-378  eps_t = FA * pec_t * ne^2 * c   (FA = "Fully stripped" column for RECOM, the ion's column otherwise)
+//   :380-401  flux_t = sum_v eps_t(v) * w_v,   TOTAL = sum_v (sum_t eps_t(v)) * w_v
+//
+// Kernels
+//   K2a reff_max_kernel        max of the finite mapped Reff (for the boundary)
+//   K2  emissivity_kernel      one voxel per thread: three exact nearest-neighbour searches (binary search + the
+//                              reference's first-minimum tie rule), on-the-fly bilinear PEC, fp64 products, block
+//                              reduction of the flux partials; the last block to finish adds the partials in block
+//                              order, so the result does not depend on scheduling.
+//   K2h weight_histogram_kernel  voxel pass for large grids / profile sweeps: w_v accumulated per profile row
+//                              (10 B/voxel of HBM traffic with uint16 Reff bins) - the only per-voxel work a sweep needs
+//   K2s sweep_kernel           flux[s][t] = sum_k H[k] * eps_t(s, k) for a batch of profile time slices
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "scene.h"
+
+namespace com {
+
+constexpr int kMaxTransitions = 4;
+
+struct DevPec {
+  int n_ne, n_te, n_grid, use_stripped;
+  const double* ne_nodes;
+  const double* te_nodes;
+  const double* table;  // (n_ne, n_te) row-major
+  const double* ne_grid;
+  const double* te_grid;
+};
+
+struct DevTables {
+  int n_fa, n_trans;
+  const double* fa_T;
+  const double* fa_ion;
+  const double* fa_last;
+  DevPec pec[kMaxTransitions];
+};
+
+// argmin_k |t[k*STRIDE] - v| with numpy's first-minimum rule, for a non-decreasing table.
+template <int STRIDE>
+__device__ __forceinline__ int nearest_first_sorted(const double* __restrict__ t, int n, double v) {
+  int lo = 0, hi = n;  // lower_bound: first index with t[i] >= v
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t[(size_t)mid * STRIDE] < v) lo = mid + 1; else hi = mid;
+  }
+  if (lo == 0) return 0;
+  int left = lo - 1;
+  const double dl = fabs(t[(size_t)left * STRIDE] - v);
+  if (lo < n) {
+    const double dr = fabs(t[(size_t)lo * STRIDE] - v);
+    if (dr < dl) return lo;
+  }
+  // first index that attains dl: equal table values, or differences that round to the same double
+  while (left > 0 && fabs(t[(size_t)(left - 1) * STRIDE] - v) == dl) --left;
+  return left;
+}
+
+// Same result for an arbitrary table (the reference never sorts): linear scan.
+template <int STRIDE>
+__device__ __forceinline__ int nearest_first_scan(const double* __restrict__ t, int n, double v) {
+  int best = 0;
+  double bd = fabs(t[0] - v);
+  for (int k = 1; k < n; ++k) {
+    const double d = fabs(t[(size_t)k * STRIDE] - v);
+    if (d < bd) bd = d, best = k;
+  }
+  return best;
+}
+
+// Degree-1 tensor spline through the ADAS nodes at (x, y), evaluated in FITPACK's order (fpbspl + fpbisp).
+__device__ __forceinline__ double pec_bilinear(const DevPec& p, double x, double y) {
+  auto cell = [](const double* nodes, int n, double q) {
+    int lo = 0, hi = n;  // upper_bound
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (nodes[mid] <= q) lo = mid + 1; else hi = mid;
+    }
+    return min(max(lo - 1, 0), n - 2);
+  };
+  const int i = cell(p.ne_nodes, p.n_ne, x), j = cell(p.te_nodes, p.n_te, y);
+  const double x0 = p.ne_nodes[i], x1 = p.ne_nodes[i + 1], y0 = p.te_nodes[j], y1 = p.te_nodes[j + 1];
+  const double fx = 1.0 / (x1 - x0), fy = 1.0 / (y1 - y0);
+  const double hx0 = __dmul_rn(fx, x1 - x), hx1 = __dmul_rn(fx, x - x0);
+  const double hy0 = __dmul_rn(fy, y1 - y), hy1 = __dmul_rn(fy, y - y0);
+  const double* c = p.table + (size_t)i * p.n_te + j;
+  double sp = __dmul_rn(__dmul_rn(c[0], hx0), hy0);
+  sp = __dadd_rn(sp, __dmul_rn(__dmul_rn(c[1], hx0), hy1));
+  sp = __dadd_rn(sp, __dmul_rn(__dmul_rn(c[p.n_te], hx1), hy0));
+  sp = __dadd_rn(sp, __dmul_rn(__dmul_rn(c[p.n_te + 1], hx1), hy1));
+  return sp;
+}
+
+struct RowEval {
+  double fa_ion, fa_last;
+  double pec[kMaxTransitions];
+  double emis[kMaxTransitions];
+  double total;
+};
+
+// Everything that depends only on (ne, Te): reader.py:282-378 for one profile row.
+__device__ __forceinline__ void eval_row(const DevTables& T, double ne, double te, double conc, RowEval& r) {
+  const int j = nearest_first_sorted<1>(T.fa_T, T.n_fa, te);
+  r.fa_ion = T.fa_ion[j];
+  r.fa_last = T.fa_last[j];
+  r.total = 0.0;
+  const double ne2 = __dmul_rn(ne, ne);
+  for (int t = 0; t < T.n_trans; ++t) {
+    const DevPec& p = T.pec[t];
+    const int ie = nearest_first_sorted<1>(p.ne_grid, p.n_grid, ne);
+    const int it = nearest_first_sorted<1>(p.te_grid, p.n_grid, te);
+    r.pec[t] = pec_bilinear(p, p.ne_grid[ie], p.te_grid[it]);
+    const double fa = p.use_stripped ? r.fa_last : r.fa_ion;
+    r.emis[t] = __dmul_rn(__dmul_rn(__dmul_rn(fa, r.pec[t]), ne2), conc);
+    r.total = t == 0 ? r.emis[0] : __dadd_rn(r.total, r.emis[t]);
+  }
+}
+
+struct K2Params {
+  DevTables tab;
+  const double* profile;  // (K,3): Reff, T_e, n_e
+  int K;
+  int profile_sorted;
+  double profile_reff_max;
+  double conc;
+  const double* reff;       // (n) or null
+  const uint16_t* reff_mm;  // (n) or null: round(Reff * 1000), 0xFFFF = NaN
+  const double* w;
+  long long n;
+  double* flux_out;          // (n_trans + 1)
+  double* per_voxel;         // (n, 4 + 2*n_trans + 1) or null
+  unsigned char* valid_out;  // (n) or null
+  double* hist_out;          // (K) or null (histogram kernel)
+  double* scratch;           // [0] max mapped reff, [1] boundary, partials from +8
+  unsigned int* done_counter;
+};
+
+__device__ __forceinline__ double voxel_reff(const K2Params& P, long long i) {
+  if (P.reff) return P.reff[i];
+  const uint16_t b = P.reff_mm[i];
+  return b == 0xFFFF ? nan("") : (double)b / 1000.0;
+}
+
+__device__ __forceinline__ int profile_row(const K2Params& P, double reff) {
+  return P.profile_sorted ? nearest_first_sorted<3>(P.profile, P.K, reff) : nearest_first_scan<3>(P.profile, P.K, reff);
+}
+
+__global__ void reff_max_kernel(const K2Params P) {
+  double m = -1.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
+    const double r = voxel_reff(P, i);
+    if (r == r) m = fmax(m, r);
+  }
+  for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m >= 0.0)  // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(&P.scratch[0]), (unsigned long long)__double_as_longlong(m));
+}
+
+constexpr int kK2Threads = 256;
+
+__global__ void __launch_bounds__(kK2Threads) emissivity_kernel(const K2Params P) {
+  const int nt = P.tab.n_trans, nout = nt + 1, ncol = 4 + 2 * nt + 1;
+  const double boundary = fmin(P.scratch[0], P.profile_reff_max);  // reader.py:210-217
+  double acc[kMaxTransitions + 1];
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
+
+  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < P.n; i += (long long)gridDim.x * kK2Threads) {
+    const double reff = voxel_reff(P, i);
+    const bool valid = (reff == reff) && !(reff >= boundary);  // dropna (:176), boundary cut (:240-242)
+    if (P.valid_out) P.valid_out[i] = valid ? 1 : 0;
+    if (!valid) continue;
+    const int k = profile_row(P, reff);
+    const double te = P.profile[3 * k + 1], ne = P.profile[3 * k + 2];
+    RowEval r;
+    eval_row(P.tab, ne, te, P.conc, r);
+    const double w = P.w[i];
+#pragma unroll
+    for (int t = 0; t < kMaxTransitions; ++t)
+      if (t < nt) acc[t] += r.emis[t] * w;
+    acc[kMaxTransitions] += r.total * w;
+    if (P.per_voxel) {
+      double* o = P.per_voxel + (size_t)i * ncol;
+      o[0] = ne, o[1] = te, o[2] = r.fa_ion, o[3] = r.fa_last;
+      for (int t = 0; t < nt; ++t) o[4 + t] = r.pec[t], o[4 + nt + t] = r.emis[t];
+      o[4 + 2 * nt] = r.total;
+    }
+  }
+
+  // block reduction, then the last block adds the per-block partials in block order (deterministic)
+  __shared__ double s_red[kK2Threads / 32][kMaxTransitions + 1];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) {
+    double v = acc[t];
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][t] = v;
+  }
+  __syncthreads();
+  double* partials = P.scratch + 8;
+  if (threadIdx.x <= kMaxTransitions) {
+    double v = 0.0;
+    for (int wq = 0; wq < kK2Threads / 32; ++wq) v += s_red[wq][threadIdx.x];
+    partials[(size_t)blockIdx.x * (kMaxTransitions + 1) + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(P.done_counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x < nout) {
+    const int slot = threadIdx.x == nt ? kMaxTransitions : threadIdx.x;  // TOTAL is kept in the last slot
+    double v = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) v += partials[(size_t)b * (kMaxTransitions + 1) + slot];
+    P.flux_out[threadIdx.x] = v;
+    if (threadIdx.x == 0) P.scratch[1] = boundary;
+  }
+}
+
+// Voxel pass of the factorised form: H[k] += w_v for the profile row k the voxel maps to.
+// Shared-memory histogram per block (K <= 12288 rows = 96 kB), flushed with one fp64 atomic per non-empty bin.
+__global__ void __launch_bounds__(kK2Threads) weight_histogram_kernel(const K2Params P) {
+  extern __shared__ double s_hist[];
+  for (int k = threadIdx.x; k < P.K; k += kK2Threads) s_hist[k] = 0.0;
+  __syncthreads();
+  const double boundary = fmin(P.scratch[0], P.profile_reff_max);
+  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < P.n; i += (long long)gridDim.x * kK2Threads) {
+    const double reff = voxel_reff(P, i);
+    const double w = P.w[i];
+    if ((reff == reff) && !(reff >= boundary) && w != 0.0) atomicAdd(&s_hist[profile_row(P, reff)], w);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < P.K; k += kK2Threads)
+    if (s_hist[k] != 0.0) atomicAdd(&P.hist_out[k], s_hist[k]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.scratch[1] = boundary;
+}
+
+struct SweepParams {
+  DevTables tab;
+  const double* profiles;  // (n_slices, K, 3)
+  const double* hist;      // (K)
+  int K, n_slices;
+  double conc;
+  double* flux_out;        // (n_slices, n_trans + 1)
+};
+
+// One block per time slice: every thread evaluates profile rows (only those with weight) and the block reduces.
+__global__ void __launch_bounds__(kK2Threads) sweep_kernel(const SweepParams P) {
+  const int s = blockIdx.x, nt = P.tab.n_trans;
+  const double* prof = P.profiles + (size_t)s * P.K * 3;
+  double acc[kMaxTransitions + 1];
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
+  for (int k = threadIdx.x; k < P.K; k += kK2Threads) {
+    const double h = P.hist[k];
+    if (h == 0.0) continue;
+    RowEval r;
+    eval_row(P.tab, prof[3 * k + 2], prof[3 * k + 1], P.conc, r);
+#pragma unroll
+    for (int t = 0; t < kMaxTransitions; ++t)
+      if (t < nt) acc[t] += r.emis[t] * h;
+    acc[kMaxTransitions] += r.total * h;
+  }
+  __shared__ double s_red[kK2Threads / 32][kMaxTransitions + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) {
+    double v = acc[t];
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= nt) {
+    const int slot = threadIdx.x == nt ? kMaxTransitions : threadIdx.x;
+    double v = 0.0;
+    for (int wq = 0; wq < kK2Threads / 32; ++wq) v += s_red[wq][slot];
+    P.flux_out[(size_t)s * (nt + 1) + threadIdx.x] = v;
+  }
+}
+
+}  // namespace com
+
+// ---------------------------------------------------------------------------------------------------------
+struct ComTables {
+  com::DevTables dev{};
+  void* d_blob = nullptr;
+  int n_trans = 0;
+};
+
+#define COM_CUDA(x)                                                            \
+  do {                                                                         \
+    cudaError_t e__ = (x);                                                     \
+    if (e__ != cudaSuccess) {                                                  \
+      com::set_error("%s failed: %s", #x, cudaGetErrorString(e__));            \
+      return COM_E_CUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool non_decreasing(const double* a, int n, int stride = 1) {
+  for (int i = 1; i < n; ++i)
+    if (!(a[(size_t)i * stride] >= a[(size_t)(i - 1) * stride])) return false;
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int com_tables_create(const ComTablesDesc* d, ComTables** out) {
+  if (!d || !out || d->n_fa < 1 || !d->fa_T || !d->fa_ion || !d->fa_last || d->n_transitions < 1 ||
+      d->n_transitions > com::kMaxTransitions) {
+    com::set_error("com_tables_create: bad arguments (1..%d transitions)", com::kMaxTransitions);
+    return COM_E_BADARG;
+  }
+  if (!non_decreasing(d->fa_T, d->n_fa)) {
+    com::set_error("com_tables_create: fractional-abundance temperature grid must be non-decreasing");
+    return COM_E_BADARG;
+  }
+  std::vector<double> blob;
+  auto push = [&](const double* p, size_t n) {
+    size_t off = blob.size();
+    blob.insert(blob.end(), p, p + n);
+    while (blob.size() % 32) blob.push_back(0.0);
+    return off;
+  };
+  size_t o_T = push(d->fa_T, d->n_fa), o_ion = push(d->fa_ion, d->n_fa), o_last = push(d->fa_last, d->n_fa);
+  struct Off {
+    size_t ne, te, tab, neg, teg;
+  } off[com::kMaxTransitions];
+  for (int t = 0; t < d->n_transitions; ++t) {
+    const ComPecDesc& p = d->pec[t];
+    if (p.n_ne < 2 || p.n_te < 2 || p.n_grid < 1 || !p.ne_nodes || !p.te_nodes || !p.table || !p.ne_grid || !p.te_grid ||
+        !non_decreasing(p.ne_nodes, p.n_ne) || !non_decreasing(p.te_nodes, p.n_te) ||
+        !non_decreasing(p.ne_grid, p.n_grid) || !non_decreasing(p.te_grid, p.n_grid)) {
+      com::set_error("com_tables_create: PEC block %d incomplete or not sorted", t);
+      return COM_E_BADARG;
+    }
+    off[t] = {push(p.ne_nodes, p.n_ne), push(p.te_nodes, p.n_te), push(p.table, (size_t)p.n_ne * p.n_te),
+              push(p.ne_grid, p.n_grid), push(p.te_grid, p.n_grid)};
+  }
+  ComTables* T = new (std::nothrow) ComTables();
+  if (!T) return COM_E_NOMEM;
+  cudaError_t e = cudaMalloc(&T->d_blob, blob.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(T->d_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    com::set_error("com_tables_create: %s", cudaGetErrorString(e));
+    if (T->d_blob) cudaFree(T->d_blob);
+    delete T;
+    return COM_E_CUDA;
+  }
+  const double* base = static_cast<const double*>(T->d_blob);
+  T->n_trans = d->n_transitions;
+  T->dev.n_fa = d->n_fa;
+  T->dev.n_trans = d->n_transitions;
+  T->dev.fa_T = base + o_T, T->dev.fa_ion = base + o_ion, T->dev.fa_last = base + o_last;
+  for (int t = 0; t < d->n_transitions; ++t) {
+    const ComPecDesc& p = d->pec[t];
+    T->dev.pec[t] = com::DevPec{p.n_ne, p.n_te, p.n_grid, p.use_fully_stripped, base + off[t].ne, base + off[t].te,
+                                base + off[t].tab, base + off[t].neg, base + off[t].teg};
+  }
+  *out = T;
+  return COM_OK;
+}
+
+int com_tables_destroy(ComTables* t) {
+  if (!t) return COM_OK;
+  if (t->d_blob) cudaFree(t->d_blob);
+  delete t;
+  return COM_OK;
+}
+
+size_t com_emissivity_workspace_bytes(int64_t n) {
+  long long blocks = std::min<long long>(std::max<long long>(1, (n + com::kK2Threads - 1) / com::kK2Threads), 148 * 8);
+  return 256 + align_up(sizeof(double) * (8 + (size_t)blocks * (com::kMaxTransitions + 1)), 256);
+}
+
+static int fill_params(com::K2Params& P, const ComTables* tables, const double* profile, int32_t K, int32_t sorted,
+                       double profile_reff_max, double concentration, const double* reff, const uint16_t* reff_mm,
+                       const double* w, int64_t n, void* workspace, size_t workspace_bytes) {
+  if (!tables || !profile || K < 1 || (!reff && !reff_mm) || !w || n < 0 || !workspace ||
+      workspace_bytes < com_emissivity_workspace_bytes(n)) {
+    com::set_error("com_emissivity_*: bad arguments or workspace too small");
+    return COM_E_BADARG;
+  }
+  P.tab = tables->dev;
+  P.profile = profile, P.K = K, P.profile_sorted = sorted, P.profile_reff_max = profile_reff_max;
+  P.conc = concentration;
+  P.reff = reff, P.reff_mm = reff_mm, P.w = w, P.n = n;
+  P.done_counter = reinterpret_cast<unsigned int*>(workspace);
+  P.scratch = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+  return COM_OK;
+}
+
+int com_emissivity_integrate(const ComTables* tables, const double* profile, int32_t K, int32_t profile_sorted,
+                             double profile_reff_max, double concentration, const double* reff,
+                             const uint16_t* reff_mm, const double* w, int64_t n, double* flux_out,
+                             double* per_voxel_out, uint8_t* valid_out, void* workspace, size_t workspace_bytes,
+                             com_stream_t stream) {
+  com::K2Params P{};
+  int rc = fill_params(P, tables, profile, K, profile_sorted, profile_reff_max, concentration, reff, reff_mm, w, n,
+                       workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!flux_out) {
+    com::set_error("com_emissivity_integrate: flux_out is null");
+    return COM_E_BADARG;
+  }
+  P.flux_out = flux_out, P.per_voxel = per_voxel_out, P.valid_out = valid_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  COM_CUDA(cudaMemsetAsync(workspace, 0, 256 + 64, s));
+  COM_CUDA(cudaMemsetAsync(flux_out, 0, sizeof(double) * (tables->n_trans + 1), s));
+  if (n == 0) return COM_OK;
+  const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 8);
+  com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+  com::emissivity_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
+int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                         const double* reff, const uint16_t* reff_mm, const double* w, int64_t n, double* hist_out,
+                         double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream) {
+  com::K2Params P{};
+  ComTables dummy;
+  int rc = fill_params(P, &dummy, profile, K, profile_sorted, profile_reff_max, 0.0, reff, reff_mm, w, n, workspace,
+                       workspace_bytes);
+  if (rc) return rc;
+  if (!hist_out || K > 12288) {
+    com::set_error("com_weight_histogram: hist_out null or more than 12288 profile rows");
+    return COM_E_BADARG;
+  }
+  P.hist_out = hist_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  COM_CUDA(cudaMemsetAsync(workspace, 0, 256 + 64, s));
+  COM_CUDA(cudaMemsetAsync(hist_out, 0, sizeof(double) * K, s));
+  if (n > 0) {
+    const size_t smem = sizeof(double) * K;
+    static bool attr_set = false;
+    if (!attr_set) {
+      COM_CUDA(cudaFuncSetAttribute(com::weight_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+      attr_set = true;
+    }
+    const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 4);
+    com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+    com::weight_histogram_kernel<<<blocks, com::kK2Threads, smem, s>>>(P);
+    COM_CUDA(cudaGetLastError());
+  }
+  if (boundary_out) COM_CUDA(cudaMemcpyAsync(boundary_out, P.scratch + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return COM_OK;
+}
+
+int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
+                         const double* hist, double concentration, double* flux_out, com_stream_t stream) {
+  if (!tables || !profiles || !hist || !flux_out || n_slices < 0 || K < 1) {
+    com::set_error("com_emissivity_sweep: bad arguments");
+    return COM_E_BADARG;
+  }
+  if (n_slices == 0) return COM_OK;
+  com::SweepParams P{tables->dev, profiles, hist, K, n_slices, concentration, flux_out};
+  com::sweep_kernel<<<n_slices, com::kK2Threads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
+int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                                  double concentration, const double* reff_h, const double* w_h, int64_t n,
+                                  double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                                  double* boundary_out_h) {
+  if (!tables_h || !profile_h || !reff_h || !w_h || !flux_out_h || n < 0 || K < 1) {
+    com::set_error("com_emissivity_integrate_host: bad arguments");
+    return COM_E_BADARG;
+  }
+  ComTables* T = nullptr;
+  int rc = com_tables_create(tables_h, &T);
+  if (rc) return rc;
+  const int nt = T->n_trans, ncol = 4 + 2 * nt + 1;
+  const int sorted = non_decreasing(profile_h, K, 3) ? 1 : 0;
+  double pmax = profile_h[0];
+  for (int k = 1; k < K; ++k) pmax = std::max(pmax, profile_h[3 * (size_t)k]);
+  const size_t ws = com_emissivity_workspace_bytes(n);
+  const size_t b_prof = align_up(sizeof(double) * 3 * K, 256), b_n = align_up(sizeof(double) * (size_t)n, 256);
+  const size_t b_pv = per_voxel_out_h ? align_up(sizeof(double) * (size_t)n * ncol, 256) : 0;
+  const size_t b_valid = valid_out_h ? align_up((size_t)n, 256) : 0;
+  char* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, b_prof + 2 * b_n + b_pv + b_valid + 256 + ws);
+  auto fail = [&](int code, const char* what, cudaError_t err) {
+    com::set_error("com_emissivity_integrate_host: %s: %s", what, cudaGetErrorString(err));
+    if (d) cudaFree(d);
+    com_tables_destroy(T);
+    return code;
+  };
+  if (e != cudaSuccess) return fail(COM_E_NOMEM, "cudaMalloc", e);
+  double* d_prof = reinterpret_cast<double*>(d);
+  double* d_reff = reinterpret_cast<double*>(d + b_prof);
+  double* d_w = reinterpret_cast<double*>(d + b_prof + b_n);
+  double* d_pv = b_pv ? reinterpret_cast<double*>(d + b_prof + 2 * b_n) : nullptr;
+  uint8_t* d_valid = b_valid ? reinterpret_cast<uint8_t*>(d + b_prof + 2 * b_n + b_pv) : nullptr;
+  double* d_flux = reinterpret_cast<double*>(d + b_prof + 2 * b_n + b_pv + b_valid);
+  void* d_ws = d + b_prof + 2 * b_n + b_pv + b_valid + 256;
+  if ((e = cudaMemcpy(d_prof, profile_h, sizeof(double) * 3 * K, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_reff, reff_h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_w, w_h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail(COM_E_CUDA, "H2D", e);
+  rc = com_emissivity_integrate(T, d_prof, K, sorted, pmax, concentration, d_reff, nullptr, d_w, n, d_flux, d_pv,
+                                d_valid, d_ws, ws, nullptr);
+  if (rc) {
+    cudaFree(d);
+    com_tables_destroy(T);
+    return rc;
+  }
+  if ((e = cudaMemcpy(flux_out_h, d_flux, sizeof(double) * (nt + 1), cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return fail(COM_E_CUDA, "D2H flux", e);
+  if (d_pv && (e = cudaMemcpy(per_voxel_out_h, d_pv, sizeof(double) * (size_t)n * ncol, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return fail(COM_E_CUDA, "D2H per-voxel", e);
+  if (d_valid && (e = cudaMemcpy(valid_out_h, d_valid, (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return fail(COM_E_CUDA, "D2H valid", e);
+  if (boundary_out_h &&
+      (e = cudaMemcpy(boundary_out_h, static_cast<char*>(d_ws) + 256 + 8, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return fail(COM_E_CUDA, "D2H boundary", e);
+  cudaFree(d);
+  com_tables_destroy(T);
+  return COM_OK;
+}
+
+}  // extern "C"

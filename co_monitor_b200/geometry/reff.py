@@ -1,0 +1,115 @@
+"""Effective-radius (Reff) grids without the VMEC web service.
+
+The reference obtains Reff per voxel from a W7-X REST service (co_monitor/geometry/reff_VMEC.py:18,
+85-136; no network here) and stores it as ``input_files/geometry/reff/Reff_coordinates-<s>_mm.dat``
+(``idx;x [m];y [m];z [m];Reff [m]``, coordinates rounded to 4 and Reff to 3 decimals, ``NaN`` outside
+the last closed flux surface; reff_VMEC.py:138-176).  The 10 mm file both entry scripts ask for is a
+missing blob of the reference checkout (.MISSING_LARGE_BLOBS), only 15/20/25/30 mm grids ship.
+
+This module provides the replacements the north-star allows:
+  * ``upsample_reff``   trilinear resampling of a shipped grid onto a finer CuboidMesh lattice.  All lattices
+                        span the same cuboid (linspace end points are shared), so the interpolation runs in
+                        fractional lattice-index space; a voxel whose interpolation stencil touches a NaN
+                        is NaN (outside the LCFS), exactly how the reference treats NaN rows (reader.py:176).
+  * ``QuadraticReff``   an analytic flux-surface model fitted to a shipped grid (Reff^2 as a quadratic form of
+                        position: nested elliptic cylinders), evaluable for 1e8-1e9 voxel lattices without a file.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+from .json_reader import input_root
+from .mesh_calculation import CuboidMesh
+
+REFF_COLUMNS = ["idx", "x [m]", "y [m]", "z [m]", "Reff [m]"]
+
+
+def reff_path(name_or_spacing, root: Path | None = None) -> Path:
+    root = Path(root) if root is not None else input_root()
+    name = name_or_spacing if isinstance(name_or_spacing, str) else f"Reff_coordinates-{name_or_spacing}_mm"
+    return root / "geometry" / "reff" / f"{name}.dat"
+
+
+def load_reff(name_or_spacing, root: Path | None = None) -> pd.DataFrame:
+    return pd.read_csv(reff_path(name_or_spacing, root), sep=";")
+
+
+def _quiet_mesh(spacing) -> CuboidMesh:
+    with contextlib.redirect_stdout(io.StringIO()):
+        return CuboidMesh(spacing)
+
+
+def upsample_reff(source_spacing: int = 15, target_spacing: int = 10, root: Path | None = None) -> pd.DataFrame:
+    """Reff on the *target_spacing* lattice by trilinear interpolation of the shipped *source_spacing* grid."""
+    src = load_reff(source_spacing, root)
+    ms, mt = _quiet_mesh(source_spacing), _quiet_mesh(target_spacing)
+    ls, lt = ms.lattice, mt.lattice
+    if len(src) != ls.n_points:
+        raise ValueError(f"{reff_path(source_spacing, root)} has {len(src)} rows, lattice has {ls.n_points}")
+    vol = src["Reff [m]"].to_numpy(dtype=float).reshape(ls.ny, ls.nx, ls.nz)  # (iy, ix, iz), z fastest
+
+    def axis(n_t, n_s):
+        f = np.arange(n_t) * ((n_s - 1) / (n_t - 1))
+        i0 = np.minimum(np.floor(f).astype(int), n_s - 2)
+        return i0, f - i0
+
+    (y0, fy), (x0, fx), (z0, fz) = axis(lt.ny, ls.ny), axis(lt.nx, ls.nx), axis(lt.nz, ls.nz)
+    out = np.zeros((lt.ny, lt.nx, lt.nz))
+    bad = np.zeros(out.shape, dtype=bool)
+    for dy, wy in ((0, 1 - fy), (1, fy)):
+        for dx, wx in ((0, 1 - fx), (1, fx)):
+            for dz, wz in ((0, 1 - fz), (1, fz)):
+                w = wy[:, None, None] * wx[None, :, None] * wz[None, None, :]
+                v = vol[(y0 + dy)[:, None, None], (x0 + dx)[None, :, None], (z0 + dz)[None, None, :]]
+                nanv = np.isnan(v)
+                bad |= nanv & (w > 0)
+                out += np.where(nanv, 0.0, v) * w
+    out[bad] = np.nan
+    pts = mt.outer_cube_mesh / 1000.0
+    rounded = np.round(pts, decimals=4)
+    return pd.DataFrame(
+        {
+            "idx": np.arange(lt.n_points),
+            "x [m]": rounded[:, 0],
+            "y [m]": rounded[:, 1],
+            "z [m]": rounded[:, 2],
+            "Reff [m]": np.round(out.ravel(), decimals=3),
+        }
+    )
+
+
+def write_reff_file(df: pd.DataFrame, path) -> Path:
+    """Same CSV dialect as reff_VMEC.py:167-176."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    df.to_csv(path, sep=";", index=False, na_rep="NaN")
+    return path
+
+
+class QuadraticReff:
+    """Analytic flux surfaces: ``Reff(r)^2 = (r - r0)^T A (r - r0)`` (nested elliptic cylinders), least-squares
+    fitted to a shipped grid; NaN beyond ``reff_max`` (the LCFS of the fitted grid)."""
+
+    def __init__(self, source_spacing: int = 15, root: Path | None = None):
+        src = load_reff(source_spacing, root)
+        pts = _quiet_mesh(source_spacing).outer_cube_mesh / 1000.0
+        reff = src["Reff [m]"].to_numpy(dtype=float)
+        ok = np.isfinite(reff)
+        x, y, z = (pts[ok, i] for i in range(3))
+        design = np.column_stack((x * x, y * y, z * z, x * y, x * z, y * z, x, y, z, np.ones_like(x)))
+        self.coef, *_ = np.linalg.lstsq(design, reff[ok] ** 2, rcond=None)
+        self.reff_max = float(np.nanmax(reff))
+
+    def __call__(self, points_mm: np.ndarray) -> np.ndarray:
+        p = np.asarray(points_mm, dtype=float) / 1000.0
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        c = self.coef
+        q = (c[0] * x * x + c[1] * y * y + c[2] * z * z + c[3] * x * y + c[4] * x * z + c[5] * y * z
+             + c[6] * x + c[7] * y + c[8] * z + c[9])
+        r = np.sqrt(np.maximum(q, 0.0))
+        return np.where(r <= self.reff_max, r, np.nan)

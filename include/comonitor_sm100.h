@@ -190,6 +190,73 @@ int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64
                         com_stream_t stream);
 size_t com_compact_workspace_bytes(int64_t n);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage 2: line-emissivity integration (reader.py:199-401).
+ * All tables are fp64 host arrays copied to the device by com_tables_create. */
+#define COM_MAX_TRANSITIONS 4
+
+typedef struct ComPecDesc {
+  int32_t n_ne, n_te;        /* ADAS block size (24 x 24; B: 8 x 11), pec.py:122-151                           */
+  int32_t n_grid;            /* interp_step = 2000, pec.py:169-174                                            */
+  int32_t use_fully_stripped;/* 1 for RECOM (multiplies the last FA column), 0 otherwise (reader.py:355-369)  */
+  const double* ne_nodes;    /* (n_ne)                                                                        */
+  const double* te_nodes;    /* (n_te)                                                                        */
+  const double* table;       /* (n_ne, n_te) row-major PEC values                                             */
+  const double* ne_grid;     /* (n_grid) linspace(ne_nodes[0], ne_nodes[-1], n_grid): the nearest-index axis  */
+  const double* te_grid;     /* (n_grid)                                                                      */
+} ComPecDesc;
+
+typedef struct ComTablesDesc {
+  int32_t n_fa;              /* rows of the interpolated fractional-abundance table (19 995)                  */
+  int32_t n_transitions;     /* 1..COM_MAX_TRANSITIONS                                                        */
+  const double* fa_T;        /* (n_fa) arange(T[0], T[-1], 1), fractional_abundance.py:72                     */
+  const double* fa_ion;      /* (n_fa) column of the requested ion, already / 100                             */
+  const double* fa_last;     /* (n_fa) last column ("Fully stripped")                                         */
+  ComPecDesc pec[COM_MAX_TRANSITIONS];
+} ComTablesDesc;
+
+typedef struct ComTables ComTables; /* opaque: device-resident Stage-2 tables of one line */
+
+int com_tables_create(const ComTablesDesc* desc_h, ComTables** out);
+int com_tables_destroy(ComTables* tables);
+
+size_t com_emissivity_workspace_bytes(int64_t n);
+
+/* Per-voxel pass == Emissivity.read_ne_te ... calculate_total_emissivity for n voxels.
+ *   profile        DEVICE (K,3) row-major [Reff, T_e, n_e] (the reference's profiles_df column order)
+ *   profile_sorted 1 when the Reff column is non-decreasing (binary search); 0 = literal linear argmin
+ *   reff / reff_mm per-voxel Reff in metres (NaN = outside the LCFS), or as uint16 millimetres (0xFFFF = NaN);
+ *                  exactly one of the two
+ *   w              per-voxel total_intensity_fraction
+ *   flux_out       DEVICE (n_transitions + 1): sum of Emissivity_<t> * w, then of Emissivity_TOTAL * w
+ *   per_voxel_out  DEVICE (n, 4 + 2*n_transitions + 1) or NULL: n_e, T_e, FA_ion, FA_stripped, pec_t..., Emissivity_t...,
+ *                  Emissivity_TOTAL (rows of dropped voxels are left untouched)
+ *   valid_out      DEVICE (n) bytes or NULL: 1 for voxels the reference keeps (finite Reff < boundary)
+ * The boundary min(max mapped Reff, profile_reff_max) is computed on the device (reader.py:210-217). */
+int com_emissivity_integrate(const ComTables* tables, const double* profile, int32_t K, int32_t profile_sorted,
+                             double profile_reff_max, double concentration, const double* reff,
+                             const uint16_t* reff_mm, const double* w, int64_t n, double* flux_out,
+                             double* per_voxel_out, uint8_t* valid_out, void* workspace, size_t workspace_bytes,
+                             com_stream_t stream);
+
+/* Host-buffer variant (the reference-facing call): everything host, synchronous. */
+int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                                  double concentration, const double* reff_h, const double* w_h, int64_t n,
+                                  double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                                  double* boundary_out_h);
+
+/* Factorised form for profile sweeps and very large grids: the flux only depends on the voxels through
+ * H[k] = sum of w over the voxels whose nearest profile row is k.
+ *   com_weight_histogram  one pass over the voxels (10 B/voxel with uint16 Reff), hist_out DEVICE (K) overwritten,
+ *                         boundary_out DEVICE (1) or NULL
+ *   com_emissivity_sweep  flux_out DEVICE (n_slices, n_transitions + 1) for profiles DEVICE (n_slices, K, 3) that share
+ *                         the Reff column the histogram was built with */
+int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                         const double* reff, const uint16_t* reff_mm, const double* w, int64_t n, double* hist_out,
+                         double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream);
+int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
+                         const double* hist, double concentration, double* flux_out, com_stream_t stream);
+
 /* Measurement aid (not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
  * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the
  * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 exact kernel

@@ -18,3 +18,24 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def reff10():
+    """Reff per voxel of the 10 mm lattice.  The reference's own 10 mm file is a missing blob; the repo's
+    deterministic trilinear up-sampling of the shipped 15 mm grid stands in for it (also used when the golden
+    Stage-2 vectors were generated).  Written once next to the shipped grids."""
+    import contextlib
+    import io
+
+    import numpy as np
+
+    from co_monitor_b200.geometry.reff import reff_path, upsample_reff, write_reff_file
+
+    path = reff_path(10)
+    if not path.exists():
+        with contextlib.redirect_stdout(io.StringIO()):
+            write_reff_file(upsample_reff(15, 10), path)
+    import pandas as pd
+
+    return pd.read_csv(path, sep=";").iloc[:, 4].to_numpy(dtype=float)
