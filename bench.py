@@ -33,6 +33,8 @@ ELEMENTS = "BCNO"
 SPACING, H, L, SLITS = 10, 30, 20, 10
 FLOP_PER_TEST = 247  # canonical no-early-out count, FMA = 2
 METRIC = "voxel-detector visibility tests/s"
+NE_MAIN = [7e13, 0, 0.37, 9.8e12, 0.5, 0.11]  # reference __main__.py:35-36
+TE_MAIN = [1870, 0, 0.155, 210, 0.38, 0.07]
 
 
 def nominal_fp32_tflops(sm_mhz: float, sms: int = 148) -> float:
@@ -146,11 +148,18 @@ def run_reference(args):
 
 
 def run_ours(args):
+    import contextlib
+    import io
+
     import torch
     import torch.distributed as dist
 
     from co_monitor_b200 import _lib
-    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.emissivity.engine import LineTables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.geometry.engine import lattice_struct, make_channel
+    from co_monitor_b200.geometry.reff import interpolate_reff
+    from co_monitor_b200.pipeline import LYMAN_ALPHA, ChannelPipeline
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,34 +175,44 @@ def run_ours(args):
     lattice = refined_lattice(world)
     P = lattice.n_points
     lo, hi = rank * P // world, (rank + 1) * P // world
-    scenes, plans = {}, {}
-    import contextlib
-    import io
-
+    # Reff of every lattice voxel: the shipped 15 mm VMEC grid resampled onto the lattice (no VMEC service here)
+    reff_table = torch.from_numpy(interpolate_reff(lattice, 15)).to(device)
+    profile = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy()
+    scenes, pipes = {}, {}
     with contextlib.redirect_stdout(io.StringIO()):
         for el in ELEMENTS:
             scenes[el] = make_channel(el, SLITS, H, L, lattice=lattice)
-            plans[el] = scenes[el].plan(lattice, lo, hi, device=device)
+            ion, wl = LYMAN_ALPHA[el]
+            tables = LineTables(el, ion, wl, ["EXCIT", "RECOM"])
+            pipes[el] = ChannelPipeline(scenes[el], tables, lattice, reff_table, lo, hi, 2.0, device=device)
+            pipes[el].set_profile(profile)
     tests_per_step_rank = (hi - lo) * H * L * len(ELEMENTS)
-    sums = torch.zeros(len(ELEMENTS), dtype=torch.float64, device=device)
+    mapped = torch.zeros(len(ELEMENTS), dtype=torch.float64, device=device)
+    flux = torch.zeros((len(ELEMENTS), 3), dtype=torch.float64, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step():
-        for i, el in enumerate(ELEMENTS):
-            plans[el].launch()
-            sums[i] = plans[el].weight.sum()  # torch reduction: plumbing for the cross-rank check only
-        if world > 1:
-            dist.all_reduce(sums)
-
-    def device_step():
+        """Stage 1 + Stage 2 for the four channels; at N > 1 the per-rank maxima of the mapped Reff are max-reduced
+        before Stage 2 and the per-channel fluxes sum-reduced after it (two small NCCL all-reduces)."""
         for el in ELEMENTS:
-            plans[el].launch()
+            pipes[el].launch_geometry()
+        if world > 1:
+            for i, el in enumerate(ELEMENTS):
+                mapped[i:i + 1].copy_(pipes[el].mapped_max)
+            dist.all_reduce(mapped, op=dist.ReduceOp.MAX)
+            for i, el in enumerate(ELEMENTS):
+                pipes[el].mapped_max.copy_(mapped[i:i + 1])
+        for i, el in enumerate(ELEMENTS):
+            pipes[el].launch_emissivity()
+            flux[i].copy_(pipes[el].flux)
+        if world > 1:
+            dist.all_reduce(flux)
 
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
         step()
     torch.cuda.synchronize()
-    stats = {el: plans[el].stats() for el in ELEMENTS}
+    stats = {el: pipes[el].plan.stats() for el in ELEMENTS}
 
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps (untimed) ----
     sampler = ClockSampler(local)
@@ -226,35 +245,51 @@ def run_ours(args):
     ms_max = float(t.item())
     total_tests = tests_per_step_rank * world * args.steps
     value = total_tests / (ms_max * 1e-3)
+    flux_h = flux.cpu().numpy()
 
-    # ---- e2e: the reference-facing host-buffer call (scene upload, kernels, D2H of weights + counts) ----
+    # ---- e2e: the reference-facing host-buffer calls, per channel: com_visibility_weights_host (scene upload,
+    # kernels, D2H of per-voxel weights + ray counts) then com_emissivity_integrate_host on the visible voxels ----
     n = hi - lo
-    w_h = torch.empty(n, dtype=torch.float64).pin_memory()
-    n_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    cap = n
+    idx_np = np.empty(cap, dtype=np.int64)
+    w_np = np.empty(cap, dtype=np.float64)
+    reff_np = reff_table.cpu().numpy()
+    prof_np = np.ascontiguousarray(profile)
     st = _lib.ComStats()
-    from co_monitor_b200.geometry.engine import lattice_struct
-
+    cnt = C.c_uint64()
     lat_s = lattice_struct(lattice)
-    h2d = d2h = 0
-    for el in ELEMENTS:
-        k = scenes[el]._keep
-        h2d += sum(k[x].nbytes for x in ("xyz", "nrm", "sc", "sp", "pv", "dv")) + C.sizeof(_lib.ComAperture) * (2 * SLITS + 2)
-        d2h += n * 12 + C.sizeof(_lib.ComStats)
+    flux_e2e = np.zeros((len(ELEMENTS), 3))
+    bytes_io = {"h2d": 0, "d2h": 0}
 
-    def e2e_step():
-        for el in ELEMENTS:
-            rc = lib.com_visibility_weights_host(C.byref(scenes[el].desc), C.byref(lat_s), None, lo, hi,
-                                                 C.c_void_p(w_h.data_ptr()), C.c_void_p(n_h.data_ptr()), None, 0, None,
-                                                 C.byref(st))
-            _lib.check(rc, "com_visibility_weights_host")
+    def e2e_step(count_bytes=False):
+        for i, el in enumerate(ELEMENTS):
+            rc = lib.com_visible_weights_host(C.byref(scenes[el].desc), C.byref(lat_s), None, lo, hi,
+                                              C.c_void_p(idx_np.ctypes.data), C.c_void_p(w_np.ctypes.data), cap,
+                                              C.byref(cnt), C.byref(st))
+            _lib.check(rc, "com_visible_weights_host")
+            m = cnt.value
+            reff_v = reff_np[idx_np[:m]]  # host-side join with the Reff table, as reader.py:161-197 does
+            rc = lib.com_emissivity_integrate_host(C.byref(pipes[el].tables.desc), _lib.as_double_ptr(prof_np), len(prof_np),
+                                                   0.02, _lib.as_double_ptr(reff_v), _lib.as_double_ptr(w_np), m,
+                                                   _lib.as_double_ptr(flux_e2e[i]), None, None, None)
+            _lib.check(rc, "com_emissivity_integrate_host")
+            if count_bytes:
+                k = scenes[el]._keep
+                bytes_io["h2d"] += sum(k[x].nbytes for x in ("xyz", "nrm", "sc", "sp", "pv", "dv"))
+                bytes_io["h2d"] += C.sizeof(_lib.ComAperture) * (2 * SLITS + 2) + prof_np.nbytes + 16 * m
+                bytes_io["h2d"] += sum(a.nbytes for a in pipes[el].tables._keep)
+                bytes_io["d2h"] += 16 * m + 512 + 24
 
-    for _ in range(2):
-        e2e_step()
+    e2e_step(count_bytes=True)
+    e2e_step()
     if world > 1:
         dist.barrier()
+    e2e_times = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         e2e_step()
+        e2e_times.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
@@ -284,9 +319,12 @@ def run_ours(args):
         "measured_fp32_tflops": measured_peak,
         "kernel": "com::filter_kernel (K1a)", "kernel_ms_per_launch": filter_ms, "exact_kernel_ms_per_launch": exact_ms,
         "kernel_share_of_step": (f_ms.value + x_ms.value) / ms if ms > 0 else None,
+        "filter_kernel_share_of_step": f_ms.value / ms if ms > 0 else None,
         "algorithmic_flop_per_test": FLOP_PER_TEST,
-        "note": "achieved counts the canonical 247 FLOP/test; the kernel's mirrored-cone formulation executes far fewer "
-                "(see DESIGN.md and profiles/), so frac can exceed 1 - the ncu issue-slot utilisation is the hardware figure",
+        "executed_fp32_flop_per_test": 18 + 4,
+        "note": "achieved counts the canonical 247 FLOP/test of SURVEY.md 8(d); K1a's mirrored-detector formulation executes "
+                "9 FFMA + 4 ALU ops per test (about 22 FLOP), so the canonical fraction can exceed 1 - the issue-slot "
+                "utilisation in profiles/ is the hardware figure",
     }
 
     base = None
@@ -296,21 +334,27 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 filter + f64 decision/weight", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 filter + f64 decision/weight/emissivity", "data": "synthetic",
         "config": {
-            "workload": f"configs[1]: B/C/N/O Stage 1, 10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} "
-                        f"({P} voxels, {hi - lo} per GPU) x {H}x{L} crystal points x {SLITS} slits",
+            "workload": f"configs[1]: B/C/N/O, Stage 1 (visibility + weight) then Stage 2 (EXCIT + RECOM emissivity -> flux), "
+                        f"10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} ({P} voxels, {hi - lo} per GPU) "
+                        f"x {H}x{L} crystal points x {SLITS} slits, Reff = shipped 15 mm VMEC grid resampled",
             "tests_per_step": tests_per_step_rank * world,
             "l2": "256 MB buffer written between timed steps (L2 flushed, untimed)",
             "timing": "sum of per-step CUDA-event intervals, max over ranks",
             "passing_rays": {el: stats[el]["passing_rays"] for el in ELEMENTS},
             "fp64_candidates": {el: stats[el]["candidates"] for el in ELEMENTS},
             "near_edge_rays": {el: stats[el]["near_edge_rays"] for el in ELEMENTS},
-            "weight_sums": [float(x) for x in sums.cpu().tolist()],
+            "flux_excit_recom_total": {el: [float(x) for x in flux_h[i]] for i, el in enumerate(ELEMENTS)},
+            "flux_e2e_total": {el: float(flux_e2e[i, 2]) for i, el in enumerate(ELEMENTS)},
         },
-        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "call": "com_visibility_weights_host per channel: scene upload + kernels + D2H of per-voxel weights and ray counts"},
-        "gpu_launches": int(launches * 2),
+        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(bytes_io["h2d"]),
+                "d2h_bytes_per_step": int(bytes_io["d2h"]),
+                "ms_per_step": 1e3 * e2e_s / args.steps, "ms_per_step_median": 1e3 * float(np.median(e2e_times)),
+                "ms_per_step_max": 1e3 * float(np.max(e2e_times)),
+                "call": "per channel: com_visible_weights_host (geometry up, K1a/K1b + compaction, visible voxels' indices and "
+                        "weights down) then com_emissivity_integrate_host (tables, profile, Reff and weights up, flux down)"},
+        "gpu_launches": int(args.steps * len(ELEMENTS) * pipes[ELEMENTS[0]].kernels_per_launch),
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": roofline,

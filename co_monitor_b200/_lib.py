@@ -166,6 +166,9 @@ def _declare(lib):
     lib.com_visibility_weights_host.argtypes = [
         C.POINTER(ComSceneDesc), C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, u64p, C.POINTER(ComStats),
     ]
+    lib.com_visible_weights_host.argtypes = [
+        C.POINTER(ComSceneDesc), C.POINTER(ComLattice), vp, i64, i64, vp, vp, i64, u64p, C.POINTER(ComStats),
+    ]
     lib.com_compact_workspace_bytes.restype = C.c_size_t
     lib.com_compact_workspace_bytes.argtypes = [i64]
     lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
@@ -173,10 +176,12 @@ def _declare(lib):
     lib.com_tables_destroy.argtypes = [vp]
     lib.com_emissivity_workspace_bytes.restype = C.c_size_t
     lib.com_emissivity_workspace_bytes.argtypes = [i64]
-    lib.com_emissivity_integrate.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, i64, vp, vp, vp, vp,
-                                             C.c_size_t, vp]
+    lib.com_emissivity_integrate.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, i64, vp,
+                                             vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.com_reff_max.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.com_emissivity_integrate_host.argtypes = [C.POINTER(ComTablesDesc), dp, i32, C.c_double, dp, dp, i64, dp, vp, vp, dp]
-    lib.com_weight_histogram.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, i64, vp, vp, vp, C.c_size_t, vp]
+    lib.com_weight_histogram.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp,
+                                         C.c_size_t, vp]
     lib.com_emissivity_sweep.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, vp]
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
@@ -191,10 +196,11 @@ EXPORTED_SYMBOLS = [
     "com_scene_create", "com_scene_destroy", "com_scene_aperture_count", "com_scene_get_aperture",
     "com_scene_filter_info",
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
+    "com_visible_weights_host", "com_host_arena_release",
     "com_compact_workspace_bytes", "com_compact_visible",
     "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
-    "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep",
+    "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
 ]
 
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -27,9 +28,101 @@ void kernel_timing_read(double*, double*, long long*);
     }                                                                          \
   } while (0)
 
+namespace com {
+namespace {
+std::mutex g_arena_mu;
+char* g_arena_dev = nullptr;
+size_t g_arena_dev_cap = 0;
+int g_arena_device = -1;
+char* g_arena_pinned = nullptr;
+size_t g_arena_pinned_cap = 0;
+}  // namespace
+
+void HostArena::lock() { g_arena_mu.lock(); }
+void HostArena::unlock() { g_arena_mu.unlock(); }
+
+void HostArena::release_all() {
+  if (g_arena_dev) cudaFree(g_arena_dev);
+  if (g_arena_pinned) cudaFreeHost(g_arena_pinned);
+  g_arena_dev = g_arena_pinned = nullptr;
+  g_arena_dev_cap = g_arena_pinned_cap = 0;
+  g_arena_device = -1;
+}
+
+int HostArena::reserve(size_t device_bytes, size_t pinned_bytes, char** device_out, char** pinned_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return COM_E_CUDA;
+  }
+  if (dev != g_arena_device) {
+    release_all();
+    g_arena_device = dev;
+  }
+  if (device_bytes > g_arena_dev_cap) {
+    if (g_arena_dev) cudaFree(g_arena_dev);
+    g_arena_dev = nullptr, g_arena_dev_cap = 0;
+    const size_t want = device_bytes + device_bytes / 4;
+    e = cudaMalloc(reinterpret_cast<void**>(&g_arena_dev), want);
+    if (e != cudaSuccess) {
+      set_error("host-call arena: cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+      cudaGetLastError();
+      return e == cudaErrorMemoryAllocation ? COM_E_NOMEM : COM_E_CUDA;
+    }
+    g_arena_dev_cap = want;
+  }
+  if (pinned_bytes > g_arena_pinned_cap) {
+    if (g_arena_pinned) cudaFreeHost(g_arena_pinned);
+    g_arena_pinned = nullptr, g_arena_pinned_cap = 0;
+    const size_t want = pinned_bytes + pinned_bytes / 4;
+    e = cudaMallocHost(reinterpret_cast<void**>(&g_arena_pinned), want);
+    if (e != cudaSuccess) {
+      set_error("host-call arena: cudaMallocHost(%zu): %s", want, cudaGetErrorString(e));
+      cudaGetLastError();
+      return COM_E_NOMEM;
+    }
+    g_arena_pinned_cap = want;
+  }
+  if (device_out) *device_out = g_arena_dev;
+  if (pinned_out) *pinned_out = g_arena_pinned;
+  return COM_OK;
+}
+}  // namespace com
+
 namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Scene tables as one blob; offsets[i] are the section starts (256-byte aligned).
+struct SceneBlob {
+  std::vector<char> bytes;
+  size_t offset[6];
+};
+
+void make_scene_blob(const com::HostScene& hs, SceneBlob& b) {
+  const void* src[6] = {hs.crystal_xyz.data(), hs.crystal_normal.data(), hs.dev_apertures.data(),
+                        hs.edges.data(),       hs.det_forms.data(),      hs.slit_forms.data()};
+  const size_t bytes[6] = {hs.crystal_xyz.size() * sizeof(double),       hs.crystal_normal.size() * sizeof(double),
+                           hs.dev_apertures.size() * sizeof(com::DevAperture), hs.edges.size() * sizeof(double),
+                           hs.det_forms.size() * sizeof(float),          hs.slit_forms.size() * sizeof(float)};
+  size_t total = 0;
+  for (int i = 0; i < 6; ++i) {
+    b.offset[i] = total;
+    total += align_up(bytes[i], 256);
+  }
+  b.bytes.assign(total, 0);
+  for (int i = 0; i < 6; ++i) std::memcpy(b.bytes.data() + b.offset[i], src[i], bytes[i]);
+}
+
+void bind_scene(com::DeviceScene& dev, char* d, const SceneBlob& b) {
+  dev.crystal_xyz = reinterpret_cast<const double*>(d + b.offset[0]);
+  dev.crystal_normal = reinterpret_cast<const double*>(d + b.offset[1]);
+  dev.apertures = reinterpret_cast<const com::DevAperture*>(d + b.offset[2]);
+  dev.edges = reinterpret_cast<const double*>(d + b.offset[3]);
+  dev.det_forms = reinterpret_cast<const float4*>(d + b.offset[4]);
+  dev.slit_forms = reinterpret_cast<const float4*>(d + b.offset[5]);
+}
 
 // ---- visible-voxel compaction: count per 1024-block, scan the block counts, scatter -------------------
 constexpr int kCompactBlock = 1024;
@@ -150,43 +243,18 @@ int com_scene_create(const ComSceneDesc* desc_h, ComScene** out) {
   sc->apertures_h = hs.apertures;
   sc->filter_eps_mm = desc_h->filter_eps_mm > 0 ? desc_h->filter_eps_mm : 5e-3;
 
-  // one device allocation, sections 256-byte aligned
-  struct Section {
-    const void* src;
-    size_t bytes;
-    size_t offset;
-  } sec[] = {
-      {hs.crystal_xyz.data(), hs.crystal_xyz.size() * sizeof(double), 0},
-      {hs.crystal_normal.data(), hs.crystal_normal.size() * sizeof(double), 0},
-      {hs.dev_apertures.data(), hs.dev_apertures.size() * sizeof(com::DevAperture), 0},
-      {hs.edges.data(), hs.edges.size() * sizeof(double), 0},
-      {hs.det_forms.data(), hs.det_forms.size() * sizeof(float), 0},
-      {hs.slit_forms.data(), hs.slit_forms.size() * sizeof(float), 0},
-  };
-  size_t total = 0;
-  for (auto& x : sec) {
-    x.offset = total;
-    total += align_up(x.bytes, 256);
-  }
-  std::vector<char> blob(total, 0);
-  for (auto& x : sec) std::memcpy(blob.data() + x.offset, x.src, x.bytes);
-
+  SceneBlob blob;
+  make_scene_blob(hs, blob);
   cudaError_t e = cudaGetDevice(&sc->device);
-  if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.size());
-  if (e == cudaSuccess) e = cudaMemcpy(sc->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.bytes.size());
+  if (e == cudaSuccess) e = cudaMemcpy(sc->d_blob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     com::set_error("com_scene_create: %s", cudaGetErrorString(e));
     if (sc->d_blob) cudaFree(sc->d_blob);
     delete sc;
     return COM_E_CUDA;
   }
-  char* d = static_cast<char*>(sc->d_blob);
-  sc->dev.crystal_xyz = reinterpret_cast<const double*>(d + sec[0].offset);
-  sc->dev.crystal_normal = reinterpret_cast<const double*>(d + sec[1].offset);
-  sc->dev.apertures = reinterpret_cast<const com::DevAperture*>(d + sec[2].offset);
-  sc->dev.edges = reinterpret_cast<const double*>(d + sec[3].offset);
-  sc->dev.det_forms = reinterpret_cast<const float4*>(d + sec[4].offset);
-  sc->dev.slit_forms = reinterpret_cast<const float4*>(d + sec[5].offset);
+  bind_scene(sc->dev, static_cast<char*>(sc->d_blob), blob);
   *out = sc;
   return COM_OK;
 }
@@ -232,6 +300,115 @@ int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, c
                                 static_cast<cudaStream_t>(stream));
 }
 
+// Shared body of the two host-buffer Stage-1 calls.  dense: per-voxel arrays come back; otherwise the visible voxels
+// are compacted on the device and only (flat index, weight) pairs come back.
+static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                int64_t vox_begin, int64_t vox_end, bool dense, double* w_out_h, uint32_t* nrays_out_h,
+                                int64_t* idx_out_h, int64_t visible_capacity, uint64_t* visible_count_h,
+                                ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
+                                ComStats* stats_out_h) {
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  SceneBlob blob;
+  make_scene_blob(hs, blob);
+  ComScene scene;  // tables live in the arena: nothing to free
+  scene.dev = hs.dev;
+  scene.filter_eps_mm = desc_h->filter_eps_mm;
+
+  const int64_t n = vox_end - vox_begin;
+  const size_t ws_bytes = com::visibility_workspace_bytes(scene.dev, n, 0.0);
+  const size_t cws_bytes = dense ? 0 : com_compact_workspace_bytes(n);
+  const size_t b_scene = align_up(blob.bytes.size(), 256);
+  const size_t b_w = align_up(sizeof(double) * (size_t)n, 256), b_n = align_up(sizeof(uint32_t) * (size_t)n, 256);
+  const size_t b_vox = (!lattice_h) ? align_up(sizeof(double) * 3 * (size_t)n, 256) : 0;
+  const size_t b_rays = rays_out_h ? align_up(sizeof(ComRayRecord) * (size_t)rays_capacity, 256) : 0;
+  const size_t b_idx = dense ? 0 : align_up(sizeof(int64_t) * (size_t)n, 256);
+  const size_t b_wc = dense ? 0 : b_w;
+  const size_t b_misc = 512;
+  const size_t total = b_scene + b_w + b_n + b_vox + b_rays + b_idx + b_wc + b_misc + align_up(cws_bytes, 256) + ws_bytes;
+  com::HostArenaGuard guard;
+  char *d = nullptr, *pin = nullptr;
+  rc = com::HostArena::reserve(total, align_up(blob.bytes.size(), 256) + 512, &d, &pin);
+  if (rc) return rc;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    char* p = d + o;
+    o += bytes;
+    return p;
+  };
+  char* d_scene = take(b_scene);
+  double* d_w = reinterpret_cast<double*>(take(b_w));
+  uint32_t* d_n = reinterpret_cast<uint32_t*>(take(b_n));
+  double* d_vox = b_vox ? reinterpret_cast<double*>(take(b_vox)) : nullptr;
+  ComRayRecord* d_rays = b_rays ? reinterpret_cast<ComRayRecord*>(take(b_rays)) : nullptr;
+  int64_t* d_idx = b_idx ? reinterpret_cast<int64_t*>(take(b_idx)) : nullptr;
+  double* d_wc = b_wc ? reinterpret_cast<double*>(take(b_wc)) : nullptr;
+  char* d_misc = take(b_misc);
+  ComStats* d_stats = reinterpret_cast<ComStats*>(d_misc);
+  uint64_t* d_rcount = reinterpret_cast<uint64_t*>(d_misc + 256);
+  uint64_t* d_vcount = reinterpret_cast<uint64_t*>(d_misc + 264);
+  void* d_cws = take(align_up(cws_bytes, 256));
+  void* d_ws = take(ws_bytes);
+
+  cudaStream_t s = nullptr;  // legacy default stream: ordered with everything else the caller did
+  std::memcpy(pin, blob.bytes.data(), blob.bytes.size());
+  COM_CUDA(cudaMemcpyAsync(d_scene, pin, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+  bind_scene(scene.dev, d_scene, blob);
+  const double* d_vox_base = nullptr;
+  if (d_vox) {  // explicit voxels: the caller passes rows [vox_begin, vox_end) only; shift so that flat indexing works
+    COM_CUDA(cudaMemcpyAsync(d_vox, vox_xyz_h, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+    d_vox_base = d_vox - 3 * vox_begin;
+  }
+  rc = com::visibility_launch(&scene, lattice_h, d_vox_base, vox_begin, vox_end, d_w, d_n, d_rays, rays_capacity,
+                              d_rays ? reinterpret_cast<unsigned long long*>(d_rcount) : nullptr, nullptr, nullptr, 0,
+                              d_stats, d_ws, ws_bytes, s);
+  if (rc) return rc;
+  char* pin_misc = pin + align_up(blob.bytes.size(), 256);
+  if (dense) {
+    COM_CUDA(cudaMemcpyAsync(w_out_h, d_w, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (nrays_out_h) COM_CUDA(cudaMemcpyAsync(nrays_out_h, d_n, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  } else {
+    rc = com_compact_visible(d_n, d_w, n, vox_begin, d_idx, d_wc, d_vcount, d_cws, cws_bytes, s);
+    if (rc) return rc;
+  }
+  COM_CUDA(cudaMemcpyAsync(pin_misc, d_misc, 512, cudaMemcpyDeviceToHost, s));
+  COM_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(stats_out_h, pin_misc, sizeof(ComStats));
+  if (!dense) {
+    uint64_t count = 0;
+    std::memcpy(&count, pin_misc + 264, sizeof(count));
+    *visible_count_h = count;
+    const size_t m = (size_t)std::min<uint64_t>(count, (uint64_t)visible_capacity);
+    if (m) {
+      COM_CUDA(cudaMemcpyAsync(idx_out_h, d_idx, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, s));
+      COM_CUDA(cudaMemcpyAsync(w_out_h, d_wc, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (d_rays) {
+    uint64_t count = 0;
+    std::memcpy(&count, pin_misc + 256, sizeof(count));
+    *rays_count_out_h = count;
+    const size_t m = (size_t)std::min<uint64_t>(count, (uint64_t)rays_capacity);
+    if (m) COM_CUDA(cudaMemcpyAsync(rays_out_h, d_rays, sizeof(ComRayRecord) * m, cudaMemcpyDeviceToHost, s));
+  }
+  COM_CUDA(cudaStreamSynchronize(s));
+  if (stats_out_h->overflow) {
+    com::set_error("candidate list overflow: %llu candidates > capacity %llu",
+                   (unsigned long long)stats_out_h->candidates, (unsigned long long)stats_out_h->candidate_capacity);
+    return COM_E_OVERFLOW;
+  }
+  if (!dense && *visible_count_h > (uint64_t)visible_capacity) {
+    com::set_error("%llu visible voxels > capacity %lld", (unsigned long long)*visible_count_h, (long long)visible_capacity);
+    return COM_E_OVERFLOW;
+  }
+  if (stats_out_h->passing_rays == 0) {
+    com::set_error("Not enough points to perform calculations!");
+    return COM_E_EMPTY;
+  }
+  return COM_OK;
+}
+
 int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
                                 int64_t vox_begin, int64_t vox_end, double* w_out_h, uint32_t* nrays_out_h,
                                 ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
@@ -241,73 +418,25 @@ int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* la
     com::set_error("com_visibility_weights_host: bad arguments");
     return COM_E_BADARG;
   }
-  ComScene* scene = nullptr;
-  int rc = com_scene_create(desc_h, &scene);
-  if (rc) return rc;
-  const int64_t n = vox_end - vox_begin;
-  const size_t ws_bytes = com_visibility_workspace_bytes(scene, n, 0.0);
-  char* d_all = nullptr;
-  const size_t b_w = align_up(sizeof(double) * (size_t)n, 256), b_n = align_up(sizeof(uint32_t) * (size_t)n, 256);
-  const size_t b_vox = (!lattice_h) ? align_up(sizeof(double) * 3 * (size_t)n, 256) : 0;
-  const size_t b_rays = rays_out_h ? align_up(sizeof(ComRayRecord) * (size_t)rays_capacity, 256) : 0;
-  const size_t b_misc = 512;
-  cudaError_t e = cudaMalloc(&d_all, b_w + b_n + b_vox + b_rays + b_misc + ws_bytes);
-  if (e != cudaSuccess) {
-    com::set_error("com_visibility_weights_host: cudaMalloc: %s", cudaGetErrorString(e));
-    com_scene_destroy(scene);
-    return e == cudaErrorMemoryAllocation ? COM_E_NOMEM : COM_E_CUDA;
+  return visibility_host_impl(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, true, w_out_h, nrays_out_h, nullptr, 0,
+                              nullptr, rays_out_h, rays_capacity, rays_count_out_h, stats_out_h);
+}
+
+int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
+                             int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
+                             int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h) {
+  if (!desc_h || (!lattice_h && !vox_xyz_h) || !idx_out_h || !w_out_h || !count_out_h || !stats_out_h ||
+      vox_end < vox_begin || capacity < 0) {
+    com::set_error("com_visible_weights_host: bad arguments");
+    return COM_E_BADARG;
   }
-  double* d_w = reinterpret_cast<double*>(d_all);
-  uint32_t* d_n = reinterpret_cast<uint32_t*>(d_all + b_w);
-  double* d_vox = b_vox ? reinterpret_cast<double*>(d_all + b_w + b_n) : nullptr;
-  ComRayRecord* d_rays = b_rays ? reinterpret_cast<ComRayRecord*>(d_all + b_w + b_n + b_vox) : nullptr;
-  ComStats* d_stats = reinterpret_cast<ComStats*>(d_all + b_w + b_n + b_vox + b_rays);
-  uint64_t* d_rcount = reinterpret_cast<uint64_t*>(d_all + b_w + b_n + b_vox + b_rays + 256);
-  void* d_ws = d_all + b_w + b_n + b_vox + b_rays + b_misc;
-  auto fail = [&](int code) {
-    cudaFree(d_all);
-    com_scene_destroy(scene);
-    return code;
-  };
-  // explicit voxels: the caller passes rows [vox_begin, vox_end) only; shift so that flat indexing works
-  const double* d_vox_base = nullptr;
-  if (d_vox) {
-    e = cudaMemcpy(d_vox, vox_xyz_h, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-      com::set_error("H2D voxels: %s", cudaGetErrorString(e));
-      return fail(COM_E_CUDA);
-    }
-    d_vox_base = d_vox - 3 * vox_begin;
-  }
-  rc = com_visibility_weights(scene, lattice_h, d_vox_base, vox_begin, vox_end, d_w, nrays_out_h ? d_n : d_n, d_rays,
-                              rays_capacity, d_rays ? d_rcount : nullptr, nullptr, nullptr, 0, d_stats, d_ws, ws_bytes,
-                              nullptr);
-  if (rc) return fail(rc);
-  e = cudaMemcpy(w_out_h, d_w, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && nrays_out_h) e = cudaMemcpy(nrays_out_h, d_n, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess) e = cudaMemcpy(stats_out_h, d_stats, sizeof(ComStats), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && d_rays) {
-    e = cudaMemcpy(rays_count_out_h, d_rcount, sizeof(uint64_t), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) {
-      size_t m = (size_t)std::min<uint64_t>(*rays_count_out_h, (uint64_t)rays_capacity);
-      e = cudaMemcpy(rays_out_h, d_rays, sizeof(ComRayRecord) * m, cudaMemcpyDeviceToHost);
-    }
-  }
-  if (e != cudaSuccess) {
-    com::set_error("com_visibility_weights_host: %s", cudaGetErrorString(e));
-    return fail(COM_E_CUDA);
-  }
-  cudaFree(d_all);
-  com_scene_destroy(scene);
-  if (stats_out_h->overflow) {
-    com::set_error("candidate list overflow: %llu candidates > capacity %llu",
-                   (unsigned long long)stats_out_h->candidates, (unsigned long long)stats_out_h->candidate_capacity);
-    return COM_E_OVERFLOW;
-  }
-  if (stats_out_h->passing_rays == 0) {
-    com::set_error("Not enough points to perform calculations!");
-    return COM_E_EMPTY;
-  }
+  return visibility_host_impl(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, false, w_out_h, nullptr, idx_out_h,
+                              capacity, count_out_h, nullptr, 0, nullptr, stats_out_h);
+}
+
+int com_host_arena_release(void) {
+  com::HostArenaGuard guard;
+  com::HostArena::release_all();
   return COM_OK;
 }
 

@@ -138,8 +138,11 @@ struct K2Params {
   double conc;
   const double* reff;       // (n) or null
   const uint16_t* reff_mm;  // (n) or null: round(Reff * 1000), 0xFFFF = NaN
+  const long long* reff_index;  // null, or (n): the Reff of voxel i is reff[reff_index[i]]
   const double* w;
   long long n;
+  const unsigned long long* n_device;  // null, or device count overriding n (n is then the upper bound)
+  const double* mapped_max;  // null, or device scalar: max mapped Reff already reduced (over ranks) by the caller
   double* flux_out;          // (n_trans + 1)
   double* per_voxel;         // (n, 4 + 2*n_trans + 1) or null
   unsigned char* valid_out;  // (n) or null
@@ -149,9 +152,18 @@ struct K2Params {
 };
 
 __device__ __forceinline__ double voxel_reff(const K2Params& P, long long i) {
-  if (P.reff) return P.reff[i];
-  const uint16_t b = P.reff_mm[i];
+  const long long j = P.reff_index ? P.reff_index[i] : i;
+  if (P.reff) return P.reff[j];
+  const uint16_t b = P.reff_mm[j];
   return b == 0xFFFF ? nan("") : (double)b / 1000.0;
+}
+
+__device__ __forceinline__ long long voxel_count(const K2Params& P) {
+  return P.n_device ? (long long)min((unsigned long long)P.n, *P.n_device) : P.n;
+}
+
+__device__ __forceinline__ double cut_boundary(const K2Params& P) {  // reader.py:210-217
+  return fmin(P.mapped_max ? *P.mapped_max : P.scratch[0], P.profile_reff_max);
 }
 
 __device__ __forceinline__ int profile_row(const K2Params& P, double reff) {
@@ -160,7 +172,8 @@ __device__ __forceinline__ int profile_row(const K2Params& P, double reff) {
 
 __global__ void reff_max_kernel(const K2Params P) {
   double m = -1.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
+  const long long n = voxel_count(P);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double r = voxel_reff(P, i);
     if (r == r) m = fmax(m, r);
   }
@@ -173,12 +186,13 @@ constexpr int kK2Threads = 256;
 
 __global__ void __launch_bounds__(kK2Threads) emissivity_kernel(const K2Params P) {
   const int nt = P.tab.n_trans, nout = nt + 1, ncol = 4 + 2 * nt + 1;
-  const double boundary = fmin(P.scratch[0], P.profile_reff_max);  // reader.py:210-217
+  const double boundary = cut_boundary(P);
+  const long long n = voxel_count(P);
   double acc[kMaxTransitions + 1];
 #pragma unroll
   for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
 
-  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < P.n; i += (long long)gridDim.x * kK2Threads) {
+  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < n; i += (long long)gridDim.x * kK2Threads) {
     const double reff = voxel_reff(P, i);
     const bool valid = (reff == reff) && !(reff >= boundary);  // dropna (:176), boundary cut (:240-242)
     if (P.valid_out) P.valid_out[i] = valid ? 1 : 0;
@@ -236,8 +250,9 @@ __global__ void __launch_bounds__(kK2Threads) weight_histogram_kernel(const K2Pa
   extern __shared__ double s_hist[];
   for (int k = threadIdx.x; k < P.K; k += kK2Threads) s_hist[k] = 0.0;
   __syncthreads();
-  const double boundary = fmin(P.scratch[0], P.profile_reff_max);
-  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < P.n; i += (long long)gridDim.x * kK2Threads) {
+  const double boundary = cut_boundary(P);
+  const long long n = voxel_count(P);
+  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < n; i += (long long)gridDim.x * kK2Threads) {
     const double reff = voxel_reff(P, i);
     const double w = P.w[i];
     if ((reff == reff) && !(reff >= boundary) && w != 0.0) atomicAdd(&s_hist[profile_row(P, reff)], w);
@@ -321,38 +336,64 @@ bool non_decreasing(const double* a, int n, int stride = 1) {
 
 extern "C" {
 
-int com_tables_create(const ComTablesDesc* d, ComTables** out) {
-  if (!d || !out || d->n_fa < 1 || !d->fa_T || !d->fa_ion || !d->fa_last || d->n_transitions < 1 ||
+// Validates the description and lays all tables out in one fp64 blob; `dev` gets pointers relative to a null base
+// (offsets), rebased by bind_tables once the blob has a device address.
+static int build_tables_blob(const ComTablesDesc* d, std::vector<double>& blob, com::DevTables& dev) {
+  if (!d || d->n_fa < 1 || !d->fa_T || !d->fa_ion || !d->fa_last || d->n_transitions < 1 ||
       d->n_transitions > com::kMaxTransitions) {
-    com::set_error("com_tables_create: bad arguments (1..%d transitions)", com::kMaxTransitions);
+    com::set_error("Stage-2 tables: bad arguments (1..%d transitions)", com::kMaxTransitions);
     return COM_E_BADARG;
   }
   if (!non_decreasing(d->fa_T, d->n_fa)) {
-    com::set_error("com_tables_create: fractional-abundance temperature grid must be non-decreasing");
+    com::set_error("Stage-2 tables: fractional-abundance temperature grid must be non-decreasing");
     return COM_E_BADARG;
   }
-  std::vector<double> blob;
+  blob.clear();
   auto push = [&](const double* p, size_t n) {
     size_t off = blob.size();
     blob.insert(blob.end(), p, p + n);
     while (blob.size() % 32) blob.push_back(0.0);
-    return off;
+    return reinterpret_cast<const double*>(off * sizeof(double));
   };
-  size_t o_T = push(d->fa_T, d->n_fa), o_ion = push(d->fa_ion, d->n_fa), o_last = push(d->fa_last, d->n_fa);
-  struct Off {
-    size_t ne, te, tab, neg, teg;
-  } off[com::kMaxTransitions];
+  dev = com::DevTables{};
+  dev.n_fa = d->n_fa;
+  dev.n_trans = d->n_transitions;
+  dev.fa_T = push(d->fa_T, d->n_fa), dev.fa_ion = push(d->fa_ion, d->n_fa), dev.fa_last = push(d->fa_last, d->n_fa);
   for (int t = 0; t < d->n_transitions; ++t) {
     const ComPecDesc& p = d->pec[t];
     if (p.n_ne < 2 || p.n_te < 2 || p.n_grid < 1 || !p.ne_nodes || !p.te_nodes || !p.table || !p.ne_grid || !p.te_grid ||
         !non_decreasing(p.ne_nodes, p.n_ne) || !non_decreasing(p.te_nodes, p.n_te) ||
         !non_decreasing(p.ne_grid, p.n_grid) || !non_decreasing(p.te_grid, p.n_grid)) {
-      com::set_error("com_tables_create: PEC block %d incomplete or not sorted", t);
+      com::set_error("Stage-2 tables: PEC block %d incomplete or not sorted", t);
       return COM_E_BADARG;
     }
-    off[t] = {push(p.ne_nodes, p.n_ne), push(p.te_nodes, p.n_te), push(p.table, (size_t)p.n_ne * p.n_te),
-              push(p.ne_grid, p.n_grid), push(p.te_grid, p.n_grid)};
+    dev.pec[t] = com::DevPec{p.n_ne, p.n_te, p.n_grid, p.use_fully_stripped, push(p.ne_nodes, p.n_ne),
+                             push(p.te_nodes, p.n_te), push(p.table, (size_t)p.n_ne * p.n_te),
+                             push(p.ne_grid, p.n_grid), push(p.te_grid, p.n_grid)};
   }
+  return COM_OK;
+}
+
+static void bind_tables(com::DevTables& dev, const void* base) {
+  auto fix = [&](const double*& p) {
+    p = reinterpret_cast<const double*>(static_cast<const char*>(base) + reinterpret_cast<size_t>(p));
+  };
+  fix(dev.fa_T), fix(dev.fa_ion), fix(dev.fa_last);
+  for (int t = 0; t < dev.n_trans; ++t) {
+    fix(dev.pec[t].ne_nodes), fix(dev.pec[t].te_nodes), fix(dev.pec[t].table);
+    fix(dev.pec[t].ne_grid), fix(dev.pec[t].te_grid);
+  }
+}
+
+int com_tables_create(const ComTablesDesc* d, ComTables** out) {
+  if (!out) {
+    com::set_error("com_tables_create: null argument");
+    return COM_E_BADARG;
+  }
+  std::vector<double> blob;
+  com::DevTables dev;
+  int rc = build_tables_blob(d, blob, dev);
+  if (rc) return rc;
   ComTables* T = new (std::nothrow) ComTables();
   if (!T) return COM_E_NOMEM;
   cudaError_t e = cudaMalloc(&T->d_blob, blob.size() * sizeof(double));
@@ -363,16 +404,9 @@ int com_tables_create(const ComTablesDesc* d, ComTables** out) {
     delete T;
     return COM_E_CUDA;
   }
-  const double* base = static_cast<const double*>(T->d_blob);
+  bind_tables(dev, T->d_blob);
+  T->dev = dev;
   T->n_trans = d->n_transitions;
-  T->dev.n_fa = d->n_fa;
-  T->dev.n_trans = d->n_transitions;
-  T->dev.fa_T = base + o_T, T->dev.fa_ion = base + o_ion, T->dev.fa_last = base + o_last;
-  for (int t = 0; t < d->n_transitions; ++t) {
-    const ComPecDesc& p = d->pec[t];
-    T->dev.pec[t] = com::DevPec{p.n_ne, p.n_te, p.n_grid, p.use_fully_stripped, base + off[t].ne, base + off[t].te,
-                                base + off[t].tab, base + off[t].neg, base + off[t].teg};
-  }
   *out = T;
   return COM_OK;
 }
@@ -391,7 +425,8 @@ size_t com_emissivity_workspace_bytes(int64_t n) {
 
 static int fill_params(com::K2Params& P, const ComTables* tables, const double* profile, int32_t K, int32_t sorted,
                        double profile_reff_max, double concentration, const double* reff, const uint16_t* reff_mm,
-                       const double* w, int64_t n, void* workspace, size_t workspace_bytes) {
+                       const int64_t* reff_index, const double* w, int64_t n, const uint64_t* n_device,
+                       const double* mapped_max, void* workspace, size_t workspace_bytes) {
   if (!tables || !profile || K < 1 || (!reff && !reff_mm) || !w || n < 0 || !workspace ||
       workspace_bytes < com_emissivity_workspace_bytes(n)) {
     com::set_error("com_emissivity_*: bad arguments or workspace too small");
@@ -401,6 +436,9 @@ static int fill_params(com::K2Params& P, const ComTables* tables, const double* 
   P.profile = profile, P.K = K, P.profile_sorted = sorted, P.profile_reff_max = profile_reff_max;
   P.conc = concentration;
   P.reff = reff, P.reff_mm = reff_mm, P.w = w, P.n = n;
+  P.reff_index = reinterpret_cast<const long long*>(reff_index);
+  P.n_device = reinterpret_cast<const unsigned long long*>(n_device);
+  P.mapped_max = mapped_max;
   P.done_counter = reinterpret_cast<unsigned int*>(workspace);
   P.scratch = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
   return COM_OK;
@@ -408,12 +446,13 @@ static int fill_params(com::K2Params& P, const ComTables* tables, const double* 
 
 int com_emissivity_integrate(const ComTables* tables, const double* profile, int32_t K, int32_t profile_sorted,
                              double profile_reff_max, double concentration, const double* reff,
-                             const uint16_t* reff_mm, const double* w, int64_t n, double* flux_out,
+                             const uint16_t* reff_mm, const int64_t* reff_index, const double* w, int64_t n,
+                             const uint64_t* n_device, const double* mapped_reff_max, double* flux_out,
                              double* per_voxel_out, uint8_t* valid_out, void* workspace, size_t workspace_bytes,
                              com_stream_t stream) {
   com::K2Params P{};
-  int rc = fill_params(P, tables, profile, K, profile_sorted, profile_reff_max, concentration, reff, reff_mm, w, n,
-                       workspace, workspace_bytes);
+  int rc = fill_params(P, tables, profile, K, profile_sorted, profile_reff_max, concentration, reff, reff_mm,
+                       reff_index, w, n, n_device, mapped_reff_max, workspace, workspace_bytes);
   if (rc) return rc;
   if (!flux_out) {
     com::set_error("com_emissivity_integrate: flux_out is null");
@@ -425,19 +464,20 @@ int com_emissivity_integrate(const ComTables* tables, const double* profile, int
   COM_CUDA(cudaMemsetAsync(flux_out, 0, sizeof(double) * (tables->n_trans + 1), s));
   if (n == 0) return COM_OK;
   const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 8);
-  com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+  if (!mapped_reff_max) com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
   com::emissivity_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
   COM_CUDA(cudaGetLastError());
   return COM_OK;
 }
 
 int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
-                         const double* reff, const uint16_t* reff_mm, const double* w, int64_t n, double* hist_out,
+                         const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, const double* w,
+                         int64_t n, const uint64_t* n_device, const double* mapped_reff_max, double* hist_out,
                          double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream) {
   com::K2Params P{};
   ComTables dummy;
-  int rc = fill_params(P, &dummy, profile, K, profile_sorted, profile_reff_max, 0.0, reff, reff_mm, w, n, workspace,
-                       workspace_bytes);
+  int rc = fill_params(P, &dummy, profile, K, profile_sorted, profile_reff_max, 0.0, reff, reff_mm, reff_index, w, n,
+                       n_device, mapped_reff_max, workspace, workspace_bytes);
   if (rc) return rc;
   if (!hist_out || K > 12288) {
     com::set_error("com_weight_histogram: hist_out null or more than 12288 profile rows");
@@ -455,11 +495,32 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
       attr_set = true;
     }
     const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 4);
-    com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+    if (!mapped_reff_max) com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
     com::weight_histogram_kernel<<<blocks, com::kK2Threads, smem, s>>>(P);
     COM_CUDA(cudaGetLastError());
   }
   if (boundary_out) COM_CUDA(cudaMemcpyAsync(boundary_out, P.scratch + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return COM_OK;
+}
+
+int com_reff_max(const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, int64_t n,
+                 const uint64_t* n_device, double* max_out, com_stream_t stream) {
+  if ((!reff && !reff_mm) || n < 0 || !max_out) {
+    com::set_error("com_reff_max: bad arguments");
+    return COM_E_BADARG;
+  }
+  com::K2Params P{};
+  P.reff = reff, P.reff_mm = reff_mm, P.n = n;
+  P.reff_index = reinterpret_cast<const long long*>(reff_index);
+  P.n_device = reinterpret_cast<const unsigned long long*>(n_device);
+  P.scratch = max_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  COM_CUDA(cudaMemsetAsync(max_out, 0, sizeof(double), s));
+  if (n > 0) {
+    const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 8);
+    com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+    COM_CUDA(cudaGetLastError());
+  }
   return COM_OK;
 }
 
@@ -484,55 +545,50 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
     com::set_error("com_emissivity_integrate_host: bad arguments");
     return COM_E_BADARG;
   }
-  ComTables* T = nullptr;
-  int rc = com_tables_create(tables_h, &T);
+  std::vector<double> blob;
+  ComTables T;  // tables live in the shared host-call arena: nothing to free
+  int rc = build_tables_blob(tables_h, blob, T.dev);
   if (rc) return rc;
-  const int nt = T->n_trans, ncol = 4 + 2 * nt + 1;
+  T.n_trans = tables_h->n_transitions;
+  const int nt = T.n_trans, ncol = 4 + 2 * nt + 1;
   const int sorted = non_decreasing(profile_h, K, 3) ? 1 : 0;
   double pmax = profile_h[0];
   for (int k = 1; k < K; ++k) pmax = std::max(pmax, profile_h[3 * (size_t)k]);
   const size_t ws = com_emissivity_workspace_bytes(n);
+  const size_t b_tab = align_up(blob.size() * sizeof(double), 256);
   const size_t b_prof = align_up(sizeof(double) * 3 * K, 256), b_n = align_up(sizeof(double) * (size_t)n, 256);
   const size_t b_pv = per_voxel_out_h ? align_up(sizeof(double) * (size_t)n * ncol, 256) : 0;
   const size_t b_valid = valid_out_h ? align_up((size_t)n, 256) : 0;
-  char* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, b_prof + 2 * b_n + b_pv + b_valid + 256 + ws);
-  auto fail = [&](int code, const char* what, cudaError_t err) {
-    com::set_error("com_emissivity_integrate_host: %s: %s", what, cudaGetErrorString(err));
-    if (d) cudaFree(d);
-    com_tables_destroy(T);
-    return code;
-  };
-  if (e != cudaSuccess) return fail(COM_E_NOMEM, "cudaMalloc", e);
-  double* d_prof = reinterpret_cast<double*>(d);
-  double* d_reff = reinterpret_cast<double*>(d + b_prof);
-  double* d_w = reinterpret_cast<double*>(d + b_prof + b_n);
-  double* d_pv = b_pv ? reinterpret_cast<double*>(d + b_prof + 2 * b_n) : nullptr;
-  uint8_t* d_valid = b_valid ? reinterpret_cast<uint8_t*>(d + b_prof + 2 * b_n + b_pv) : nullptr;
-  double* d_flux = reinterpret_cast<double*>(d + b_prof + 2 * b_n + b_pv + b_valid);
-  void* d_ws = d + b_prof + 2 * b_n + b_pv + b_valid + 256;
-  if ((e = cudaMemcpy(d_prof, profile_h, sizeof(double) * 3 * K, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(d_reff, reff_h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(d_w, w_h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess)
-    return fail(COM_E_CUDA, "H2D", e);
-  rc = com_emissivity_integrate(T, d_prof, K, sorted, pmax, concentration, d_reff, nullptr, d_w, n, d_flux, d_pv,
-                                d_valid, d_ws, ws, nullptr);
-  if (rc) {
-    cudaFree(d);
-    com_tables_destroy(T);
-    return rc;
-  }
-  if ((e = cudaMemcpy(flux_out_h, d_flux, sizeof(double) * (nt + 1), cudaMemcpyDeviceToHost)) != cudaSuccess)
-    return fail(COM_E_CUDA, "D2H flux", e);
-  if (d_pv && (e = cudaMemcpy(per_voxel_out_h, d_pv, sizeof(double) * (size_t)n * ncol, cudaMemcpyDeviceToHost)) != cudaSuccess)
-    return fail(COM_E_CUDA, "D2H per-voxel", e);
-  if (d_valid && (e = cudaMemcpy(valid_out_h, d_valid, (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess)
-    return fail(COM_E_CUDA, "D2H valid", e);
-  if (boundary_out_h &&
-      (e = cudaMemcpy(boundary_out_h, static_cast<char*>(d_ws) + 256 + 8, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
-    return fail(COM_E_CUDA, "D2H boundary", e);
-  cudaFree(d);
-  com_tables_destroy(T);
+  const size_t up = b_tab + b_prof + 2 * b_n;  // staged through pinned memory in one copy
+  com::HostArenaGuard guard;
+  char *d = nullptr, *pin = nullptr;
+  rc = com::HostArena::reserve(up + b_pv + b_valid + 256 + ws, up + 256, &d, &pin);
+  if (rc) return rc;
+  std::memcpy(pin, blob.data(), blob.size() * sizeof(double));
+  std::memcpy(pin + b_tab, profile_h, sizeof(double) * 3 * K);
+  std::memcpy(pin + b_tab + b_prof, reff_h, sizeof(double) * (size_t)n);
+  std::memcpy(pin + b_tab + b_prof + b_n, w_h, sizeof(double) * (size_t)n);
+  cudaStream_t s = nullptr;
+  COM_CUDA(cudaMemcpyAsync(d, pin, up, cudaMemcpyHostToDevice, s));
+  bind_tables(T.dev, d);
+  double* d_prof = reinterpret_cast<double*>(d + b_tab);
+  double* d_reff = reinterpret_cast<double*>(d + b_tab + b_prof);
+  double* d_w = reinterpret_cast<double*>(d + b_tab + b_prof + b_n);
+  double* d_pv = b_pv ? reinterpret_cast<double*>(d + up) : nullptr;
+  uint8_t* d_valid = b_valid ? reinterpret_cast<uint8_t*>(d + up + b_pv) : nullptr;
+  double* d_flux = reinterpret_cast<double*>(d + up + b_pv + b_valid);
+  char* d_ws = d + up + b_pv + b_valid + 256;
+  rc = com_emissivity_integrate(&T, d_prof, K, sorted, pmax, concentration, d_reff, nullptr, nullptr, d_w, n, nullptr,
+                                nullptr, d_flux, d_pv, d_valid, d_ws, ws, s);
+  if (rc) return rc;
+  char* pin_out = pin + up;
+  COM_CUDA(cudaMemcpyAsync(pin_out, d_flux, sizeof(double) * (nt + 1), cudaMemcpyDeviceToHost, s));
+  COM_CUDA(cudaMemcpyAsync(pin_out + 128, d_ws + 256 + 8, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (d_pv) COM_CUDA(cudaMemcpyAsync(per_voxel_out_h, d_pv, sizeof(double) * (size_t)n * ncol, cudaMemcpyDeviceToHost, s));
+  if (d_valid) COM_CUDA(cudaMemcpyAsync(valid_out_h, d_valid, (size_t)n, cudaMemcpyDeviceToHost, s));
+  COM_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(flux_out_h, pin_out, sizeof(double) * (nt + 1));
+  if (boundary_out_h) std::memcpy(boundary_out_h, pin_out + 128, sizeof(double));
   return COM_OK;
 }
 

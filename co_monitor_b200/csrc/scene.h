@@ -63,6 +63,21 @@ int build_host_scene(const ComSceneDesc& d, HostScene& out);
 
 void set_error(const char* fmt, ...);
 
+// Grow-only device block + pinned staging block shared by the synchronous *_host entry points, so that a
+// reference-facing call does not pay cudaMalloc/cudaFree (both synchronise the device) every time.
+// lock() serialises the host entry points; reserve() returns COM_OK or COM_E_*.
+struct HostArena {
+  static void lock();
+  static void unlock();
+  static int reserve(size_t device_bytes, size_t pinned_bytes, char** device_out, char** pinned_out);
+  static void release_all();  // frees both blocks (com_host_arena_release)
+};
+
+struct HostArenaGuard {
+  HostArenaGuard() { HostArena::lock(); }
+  ~HostArenaGuard() { HostArena::unlock(); }
+};
+
 }  // namespace com
 
 struct ComScene {

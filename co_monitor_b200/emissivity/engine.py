@@ -101,7 +101,7 @@ class LineTables:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             rc = self._lib.com_emissivity_integrate(
                 self.handle, _ptr(prof_d), K, sorted_flag, float(prof[:, 0].max()), float(concentration),
-                _ptr(reff_d), None, _ptr(w_d), n, _ptr(flux), _ptr(cols), _ptr(valid), _ptr(ws), ws_bytes,
+                _ptr(reff_d), None, None, _ptr(w_d), n, None, None, _ptr(flux), _ptr(cols), _ptr(valid), _ptr(ws), ws_bytes,
                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
             _lib.check(rc, "com_emissivity_integrate")
             boundary = float(ws[256 + 8:256 + 16].view(torch.float64).item())
@@ -110,7 +110,8 @@ class LineTables:
                         columns=cols.cpu().numpy() if per_voxel else None)
 
     # ---- factorised form ----------------------------------------------------------------------------------
-    def weight_histogram(self, profile_reff: np.ndarray, reff, w, device=None, reff_mm=None):
+    def weight_histogram(self, profile_reff: np.ndarray, reff, w, device=None, reff_mm=None, reff_index=None,
+                         n_device=None, mapped_reff_max=None):
         """H[k] = sum of w over the voxels mapped to profile row k.  Returns (hist CUDA tensor (K,), boundary float)."""
         import torch
 
@@ -130,8 +131,9 @@ class LineTables:
             ws_bytes = self._lib.com_emissivity_workspace_bytes(n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             rc = self._lib.com_weight_histogram(
-                _ptr(prof_d), K, sorted_flag, float(prof[:, 0].max()), _ptr(reff), _ptr(reff_mm), _ptr(w_d), n,
-                _ptr(hist), _ptr(bnd), _ptr(ws), ws_bytes, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                _ptr(prof_d), K, sorted_flag, float(prof[:, 0].max()), _ptr(reff), _ptr(reff_mm), _ptr(reff_index),
+                _ptr(w_d), n, _ptr(n_device), _ptr(mapped_reff_max), _ptr(hist), _ptr(bnd), _ptr(ws), ws_bytes,
+                C.c_void_p(torch.cuda.current_stream().cuda_stream))
             _lib.check(rc, "com_weight_histogram")
             return hist, float(bnd.item())
 

@@ -44,11 +44,10 @@ def _quiet_mesh(spacing) -> CuboidMesh:
         return CuboidMesh(spacing)
 
 
-def upsample_reff(source_spacing: int = 15, target_spacing: int = 10, root: Path | None = None) -> pd.DataFrame:
-    """Reff on the *target_spacing* lattice by trilinear interpolation of the shipped *source_spacing* grid."""
+def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None = None, decimals: int | None = 3) -> np.ndarray:
+    """Reff [m] on every voxel of *target_lattice* (any lattice spanning the standard cuboid), flat index order."""
     src = load_reff(source_spacing, root)
-    ms, mt = _quiet_mesh(source_spacing), _quiet_mesh(target_spacing)
-    ls, lt = ms.lattice, mt.lattice
+    ls, lt = _quiet_mesh(source_spacing).lattice, target_lattice
     if len(src) != ls.n_points:
         raise ValueError(f"{reff_path(source_spacing, root)} has {len(src)} rows, lattice has {ls.n_points}")
     vol = src["Reff [m]"].to_numpy(dtype=float).reshape(ls.ny, ls.nx, ls.nz)  # (iy, ix, iz), z fastest
@@ -70,15 +69,23 @@ def upsample_reff(source_spacing: int = 15, target_spacing: int = 10, root: Path
                 bad |= nanv & (w > 0)
                 out += np.where(nanv, 0.0, v) * w
     out[bad] = np.nan
-    pts = mt.outer_cube_mesh / 1000.0
-    rounded = np.round(pts, decimals=4)
+    out = out.ravel()
+    return np.round(out, decimals=decimals) if decimals is not None else out
+
+
+def upsample_reff(source_spacing: int = 15, target_spacing: int = 10, root: Path | None = None) -> pd.DataFrame:
+    """Reff file contents for the *target_spacing* lattice by trilinear interpolation of the shipped
+    *source_spacing* grid (same columns and rounding as reff_VMEC.py:138-165)."""
+    mt = _quiet_mesh(target_spacing)
+    reff = interpolate_reff(mt.lattice, source_spacing, root, decimals=3)
+    rounded = np.round(mt.outer_cube_mesh / 1000.0, decimals=4)
     return pd.DataFrame(
         {
-            "idx": np.arange(lt.n_points),
+            "idx": np.arange(mt.lattice.n_points),
             "x [m]": rounded[:, 0],
             "y [m]": rounded[:, 1],
             "z [m]": rounded[:, 2],
-            "Reff [m]": np.round(out.ravel(), decimals=3),
+            "Reff [m]": reff,
         }
     )
 

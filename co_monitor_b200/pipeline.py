@@ -1,0 +1,94 @@
+"""Device-resident Stage 1 -> Stage 2 pipeline of one channel, free of host synchronisation.
+
+    visibility (K1a filter + K1b exact)  ->  compaction of the visible voxels  ->  max mapped Reff
+    [-> all-reduce(MAX) over ranks]      ->  emissivity integration (K2)       [-> all-reduce(SUM) of the flux]
+
+Everything is enqueued on the current CUDA stream through the C ABI; the only values that ever leave the device
+are the (T+1) flux numbers the caller reads at the end.  This is what ``bench.py`` times and what a sweep over
+voxel grids would call; the file-level drop-ins (``Simulation``, ``Emissivity``) go through the same entry points
+but stop in between to build the reference's DataFrames and files.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .emissivity.engine import LineTables, _ptr
+from .geometry.engine import ChannelScene, VisibilityPlan
+from .geometry.mesh_calculation import Lattice
+
+#: Lyman-alpha lines of the four monitor channels (reader.py:469-474)
+LYMAN_ALPHA = {"B": ("Z4", 48.6), "C": ("Z5", 33.7), "N": ("Z6", 24.8), "O": ("Z7", 19.0)}
+
+
+class ChannelPipeline:
+    def __init__(self, scene: ChannelScene, tables: LineTables, lattice: Lattice, reff_table, begin: int, end: int,
+                 concentration_percent: float = 2.0, device=None):
+        """*reff_table*: CUDA float64 tensor with Reff [m] of every lattice voxel (NaN outside the LCFS)."""
+        import torch
+
+        self._lib = _lib.load()
+        self.scene, self.tables = scene, tables
+        self.plan: VisibilityPlan = scene.plan(lattice, begin, end, device=device)
+        dev = self.plan.device
+        self.device = dev
+        n = end - begin
+        self.n = n
+        self.reff_table = reff_table
+        self.conc = concentration_percent / 100.0
+        with torch.cuda.device(dev):
+            self.idx = torch.empty(n, dtype=torch.int64, device=dev)
+            self.w_compact = torch.empty(n, dtype=torch.float64, device=dev)
+            self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.cws_bytes = self._lib.com_compact_workspace_bytes(n)
+            self.cws = torch.empty(self.cws_bytes, dtype=torch.uint8, device=dev)
+            self.mapped_max = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.flux = torch.zeros(tables.n_out, dtype=torch.float64, device=dev)
+            self.ews_bytes = self._lib.com_emissivity_workspace_bytes(n)
+            self.ews = torch.empty(self.ews_bytes, dtype=torch.uint8, device=dev)
+        self._profile = None
+        self.kernels_per_launch = 2 + 3 + 1 + 1  # filter, exact, 3 x compaction, reff max, emissivity
+
+    def set_profile(self, profile: np.ndarray):
+        """(K,3) [Reff, T_e, n_e] host array -> device."""
+        import torch
+
+        prof = np.ascontiguousarray(profile, dtype=np.float64)
+        self._profile = torch.from_numpy(prof.copy()).to(self.device)
+        self._K = len(prof)
+        self._sorted = int(np.all(np.diff(prof[:, 0]) >= 0))
+        self._pmax = float(prof[:, 0].max())
+
+    def _stream(self):
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_geometry(self):
+        """Stage 1, compaction and this rank's maximum mapped Reff (into ``mapped_max``)."""
+        s = self._stream()
+        self.plan.launch()
+        rc = self._lib.com_compact_visible(_ptr(self.plan.nrays), _ptr(self.plan.weight), self.n, self.plan.begin,
+                                           _ptr(self.idx), _ptr(self.w_compact), _ptr(self.count), _ptr(self.cws),
+                                           self.cws_bytes, s)
+        _lib.check(rc, "com_compact_visible")
+        rc = self._lib.com_reff_max(_ptr(self.reff_table), None, _ptr(self.idx), self.n, _ptr(self.count),
+                                    _ptr(self.mapped_max), s)
+        _lib.check(rc, "com_reff_max")
+
+    def launch_emissivity(self):
+        """Stage 2 over the compacted voxels; ``mapped_max`` may have been max-reduced over ranks in between."""
+        if self._profile is None:
+            raise RuntimeError("set_profile() first")
+        rc = self._lib.com_emissivity_integrate(
+            self.tables.handle, _ptr(self._profile), self._K, self._sorted, self._pmax, self.conc,
+            _ptr(self.reff_table), None, _ptr(self.idx), _ptr(self.w_compact), self.n, _ptr(self.count),
+            _ptr(self.mapped_max), _ptr(self.flux), None, None, _ptr(self.ews), self.ews_bytes, self._stream())
+        _lib.check(rc, "com_emissivity_integrate")
+
+    def launch(self):
+        self.launch_geometry()
+        self.launch_emissivity()
+        return self.flux

@@ -183,6 +183,16 @@ int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* la
                                 ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
                                 ComStats* stats_out_h);
 
+/* Same, but only the visible voxels come back (what Simulation.ddf holds, simulation.py:579-594): ascending flat
+ * indices idx_out_h[i] and their weights w_out_h[i], i < *count_out_h <= capacity (COM_E_OVERFLOW beyond). */
+int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
+                             int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
+                             int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h);
+
+/* The *_host calls keep one grow-only device block and one pinned staging block between calls (cudaMalloc and
+ * cudaFree synchronise the device); this frees them. */
+int com_host_arena_release(void);
+
 /* Compaction of the visible voxels (nrays > 0), ascending flat index: idx_out[i] = vox_begin + position,
  * w_compact[i] = w[position].  *count_out (device u64).  idx_out / w_compact need room for n entries. */
 int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
@@ -225,19 +235,29 @@ size_t com_emissivity_workspace_bytes(int64_t n);
 /* Per-voxel pass == Emissivity.read_ne_te ... calculate_total_emissivity for n voxels.
  *   profile        DEVICE (K,3) row-major [Reff, T_e, n_e] (the reference's profiles_df column order)
  *   profile_sorted 1 when the Reff column is non-decreasing (binary search); 0 = literal linear argmin
- *   reff / reff_mm per-voxel Reff in metres (NaN = outside the LCFS), or as uint16 millimetres (0xFFFF = NaN);
- *                  exactly one of the two
+ *   reff / reff_mm Reff in metres (NaN = outside the LCFS), or as uint16 millimetres (0xFFFF = NaN); exactly one
+ *   reff_index     NULL: voxel i uses reff[i].  Else (n) int64: voxel i uses reff[reff_index[i]] - lets the compacted
+ *                  visible-voxel list of com_compact_visible address a whole-lattice Reff table
  *   w              per-voxel total_intensity_fraction
+ *   n / n_device   number of voxels; n_device (DEVICE u64, nullable) overrides n with a count produced on the device
+ *                  (n is then only the upper bound) so that Stage 1 -> compaction -> Stage 2 needs no host sync
+ *   mapped_reff_max NULL: the maximum mapped Reff is computed here and the cut is min(that, profile_reff_max)
+ *                  (reader.py:210-217).  Else DEVICE (1) double holding the maximum already reduced by the caller -
+ *                  sharded runs take com_reff_max per rank and all-reduce(MAX) it, all on the device
  *   flux_out       DEVICE (n_transitions + 1): sum of Emissivity_<t> * w, then of Emissivity_TOTAL * w
  *   per_voxel_out  DEVICE (n, 4 + 2*n_transitions + 1) or NULL: n_e, T_e, FA_ion, FA_stripped, pec_t..., Emissivity_t...,
  *                  Emissivity_TOTAL (rows of dropped voxels are left untouched)
- *   valid_out      DEVICE (n) bytes or NULL: 1 for voxels the reference keeps (finite Reff < boundary)
- * The boundary min(max mapped Reff, profile_reff_max) is computed on the device (reader.py:210-217). */
+ *   valid_out      DEVICE (n) bytes or NULL: 1 for voxels the reference keeps (finite Reff < boundary) */
 int com_emissivity_integrate(const ComTables* tables, const double* profile, int32_t K, int32_t profile_sorted,
                              double profile_reff_max, double concentration, const double* reff,
-                             const uint16_t* reff_mm, const double* w, int64_t n, double* flux_out,
+                             const uint16_t* reff_mm, const int64_t* reff_index, const double* w, int64_t n,
+                             const uint64_t* n_device, const double* mapped_reff_max, double* flux_out,
                              double* per_voxel_out, uint8_t* valid_out, void* workspace, size_t workspace_bytes,
                              com_stream_t stream);
+
+/* Maximum finite Reff of the addressed voxels into max_out (DEVICE, 1 double); 0 when there is none. */
+int com_reff_max(const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, int64_t n,
+                 const uint64_t* n_device, double* max_out, com_stream_t stream);
 
 /* Host-buffer variant (the reference-facing call): everything host, synchronous. */
 int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
@@ -252,7 +272,8 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
  *   com_emissivity_sweep  flux_out DEVICE (n_slices, n_transitions + 1) for profiles DEVICE (n_slices, K, 3) that share
  *                         the Reff column the histogram was built with */
 int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
-                         const double* reff, const uint16_t* reff_mm, const double* w, int64_t n, double* hist_out,
+                         const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, const double* w,
+                         int64_t n, const uint64_t* n_device, const double* mapped_reff_max, double* hist_out,
                          double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream);
 int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
                          const double* hist, double concentration, double* flux_out, com_stream_t stream);

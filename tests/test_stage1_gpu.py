@@ -132,3 +132,51 @@ def test_no_visible_voxel_exits_like_the_reference():
         Simulation("C", slits_number=1, distance_between_points=120, crystal_height_step=1, crystal_length_step=1,
                    plot=False, verbose=False)
     assert "Not enough points" in str(exc.value)
+
+
+def test_host_buffer_entry_points(sims):
+    """com_visibility_weights_host (dense) and com_visible_weights_host (compacted) against the device-buffer path."""
+    import ctypes as C
+
+    from co_monitor_b200 import _lib
+    from co_monitor_b200.geometry.engine import lattice_struct
+
+    sim = sims("C")
+    lib = _lib.load()
+    lat = lattice_struct(sim.mesh.lattice)
+    lo, hi = 100000, 160000
+    ref = sim.scene.visibility(lattice=sim.mesh.lattice, begin=lo, end=hi)
+    w = np.empty(hi - lo)
+    nr = np.empty(hi - lo, dtype=np.uint32)
+    st = _lib.ComStats()
+    rc = lib.com_visibility_weights_host(C.byref(sim.scene.desc), C.byref(lat), None, lo, hi, C.c_void_p(w.ctypes.data),
+                                         C.c_void_p(nr.ctypes.data), None, 0, None, C.byref(st))
+    assert rc == 0
+    assert np.array_equal(nr, ref.nrays.cpu().numpy().view(np.uint32))
+    np.testing.assert_allclose(w, ref.weight.cpu().numpy(), rtol=1e-13, atol=0)
+    assert st.passing_rays == ref.stats["passing_rays"] and st.visible_voxels == ref.stats["visible_voxels"]
+    idx = np.empty(hi - lo, dtype=np.int64)
+    wc = np.empty(hi - lo)
+    cnt = C.c_uint64()
+    for _ in range(2):  # second call reuses the arena
+        rc = lib.com_visible_weights_host(C.byref(sim.scene.desc), C.byref(lat), None, lo, hi, C.c_void_p(idx.ctypes.data),
+                                          C.c_void_p(wc.ctypes.data), hi - lo, C.byref(cnt), C.byref(st))
+        assert rc == 0
+        m = cnt.value
+        assert m == st.visible_voxels == int((nr > 0).sum())
+        assert np.array_equal(idx[:m], np.flatnonzero(nr) + lo)
+        np.testing.assert_allclose(wc[:m], w[nr > 0], rtol=1e-13, atol=0)
+    # explicit host voxels, same range
+    pts = np.ascontiguousarray(sim.mesh.points_at(np.arange(lo, hi)))
+    rc = lib.com_visible_weights_host(C.byref(sim.scene.desc), None, C.c_void_p(pts.ctypes.data), lo, hi,
+                                      C.c_void_p(idx.ctypes.data), C.c_void_p(wc.ctypes.data), hi - lo, C.byref(cnt),
+                                      C.byref(st))
+    assert rc == 0 and cnt.value == m
+    # too small a capacity is reported, an empty range is the reference's "Not enough points" condition
+    rc = lib.com_visible_weights_host(C.byref(sim.scene.desc), C.byref(lat), None, lo, hi, C.c_void_p(idx.ctypes.data),
+                                      C.c_void_p(wc.ctypes.data), 10, C.byref(cnt), C.byref(st))
+    assert rc == _lib.COM_E_OVERFLOW
+    rc = lib.com_visible_weights_host(C.byref(sim.scene.desc), C.byref(lat), None, 0, 2000, C.c_void_p(idx.ctypes.data),
+                                      C.c_void_p(wc.ctypes.data), hi - lo, C.byref(cnt), C.byref(st))
+    assert rc == _lib.COM_E_EMPTY and b"Not enough points" in lib.com_last_error()
+    assert lib.com_host_arena_release() == 0

@@ -126,3 +126,81 @@ def test_find_nearest_reference_unit_test():
     assert Emissivity._find_nearest(nrs, 75) == 2
     assert Emissivity._find_nearest(nrs, 76) == 6
     assert Emissivity._find_nearest(nrs, 0) == 0
+
+
+def test_device_pipeline_matches_reference_flux(gold, reff10):
+    """Stage 1 -> compaction -> Stage 2 without leaving the device (co_monitor_b200.pipeline) reproduces the
+    reference's per-channel flux (computed there from the shipped Stage-1 files)."""
+    import contextlib
+    import io
+
+    import torch
+
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.pipeline import LYMAN_ALPHA, ChannelPipeline
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        lattice = CuboidMesh(10).lattice
+    reff = torch.from_numpy(reff10).cuda()
+    prof = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy()
+    for el in "CO":
+        ion, wl = LYMAN_ALPHA[el]
+        scene = make_channel(el, 10, 30, 20, lattice=lattice)
+        pipe = ChannelPipeline(scene, cached_line_tables(el, ion, wl, ("EXCIT", "RECOM"), None), lattice, reff, 0,
+                               lattice.n_points, 2.0)
+        pipe.set_profile(prof)
+        flux = pipe.launch().cpu().numpy()
+        np.testing.assert_allclose(flux, gold[f"main_{el}_flux"], rtol=1e-11)
+        # sharded: two half-ranges with the max mapped Reff exchanged in between (what N = 2 ranks do over NCCL)
+        halves = [ChannelPipeline(scene, pipe.tables, lattice, reff, a, b, 2.0) for a, b in ((0, 135000), (135000, 270000))]
+        for h in halves:
+            h.set_profile(prof)
+            h.launch_geometry()
+        m = torch.maximum(halves[0].mapped_max, halves[1].mapped_max)
+        total = np.zeros(3)
+        for h in halves:
+            h.mapped_max.copy_(m)
+            h.launch_emissivity()
+            total += h.flux.cpu().numpy()
+        np.testing.assert_allclose(total, flux, rtol=1e-12)
+        scene.close()
+
+
+def test_host_buffer_emissivity_call(gold, reff10):
+    """com_emissivity_integrate_host (host in, host out) against the reference's C-channel result."""
+    import ctypes as C
+
+    import pandas as pd
+
+    from co_monitor_b200 import _lib
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from oracle import stage2 as o2
+
+    lib = _lib.load()
+    obs = o2.read_observed_volume("C")
+    reff = reff10[obs[:, 0].astype(np.int64)]
+    keep = ~np.isnan(reff)
+    reff, w = np.ascontiguousarray(reff[keep]), np.ascontiguousarray(obs[keep, 4])
+    prof = np.ascontiguousarray(TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy())
+    tables = cached_line_tables("C", "Z5", 33.7, ("EXCIT", "RECOM"), None)
+    n = len(reff)
+    flux = np.zeros(3)
+    cols = np.zeros((n, 9))
+    valid = np.zeros(n, dtype=np.uint8)
+    bnd = C.c_double()
+    for _ in range(2):
+        rc = lib.com_emissivity_integrate_host(C.byref(tables.desc), _lib.as_double_ptr(prof), len(prof), 0.02,
+                                               _lib.as_double_ptr(reff), _lib.as_double_ptr(w), n, _lib.as_double_ptr(flux),
+                                               C.c_void_p(cols.ctypes.data), C.c_void_p(valid.ctypes.data), C.byref(bnd))
+        assert rc == 0
+        np.testing.assert_allclose(flux, gold["main_C_flux"], rtol=RTOL)
+        assert bnd.value == float(gold["main_C_reff_boundary"][0])
+        assert valid.sum() == int(gold["main_C_nrows"][0])
+    ref_rows = gold["main_C_rows"]  # stride 1 for C, sorted by idx
+    mine = cols[valid.astype(bool)]
+    order = np.argsort(obs[keep][valid.astype(bool), 0], kind="stable")
+    np.testing.assert_allclose(mine[order], ref_rows[:, 6:], rtol=RTOL, atol=0)
