@@ -22,7 +22,8 @@
 
 namespace com {
 
-constexpr int kTileVoxels = 512;
+constexpr int kTileVoxels = 512;       // voxels per work item, explicit-voxel kernel
+constexpr int kSegmentMax = 64;        // longest run of z-consecutive voxels advanced by forward differences
 constexpr int kMaxWarps = 16;
 constexpr int kUnroll = 4;
 constexpr int kQueueCap = 32 * kUnroll + 32;
@@ -41,6 +42,9 @@ struct K1Params {
   int n_tiles;
   int n_super;       // crystal super-groups (warps_per_cta * 32 points each)
   int warps_per_cta;
+  int tile_voxels;
+  int segs_per_item;  // lattice kernel: segments per work item
+  float dz[3];       // lattice kernel: recentred position step between z-consecutive voxels (FP32)
   uint2* cand;       // (voxel_local, crystal) pairs
   unsigned long long cand_capacity;
   unsigned long long* counters;  // [0] candidates, [1] next work item
@@ -216,6 +220,160 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
     for (; v0 < nv; ++v0) {
       push(v0, margin(v0) >= 0.f || all_pass);
       while (qn >= 32) drain(32);
+    }
+    if (qn > 0) drain(qn);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1a for the implicit CuboidMesh lattice.  z is the fastest lattice axis and the three detector forms are linear
+// in the voxel position, so along a run of z-consecutive voxels each form advances by a per-lane constant
+// (G . dz): 3 FADD per ray instead of 9 FFMA.  Runs ("segments") are re-based from an fp64-evaluated position
+// every kSegmentMax voxels at most, which keeps the accumulated FP32 rounding (<= 64 ulp of |W| ~ 0.02) far
+// inside the band folded into the forms (>= 0.4 in the same units).
+//
+// Warps are independent: a work item is (a few consecutive segments) x (32 crystal points), fetched by one warp
+// with an atomic; there is no block-level barrier, so a warp that has to run stage B more often delays nobody.
+// Only the segment bases are staged (per warp, in shared memory); stage B rebuilds a queued voxel's position as
+// base + k * dz.
+constexpr int kLatticeWarps = 8;
+constexpr int kSegsPerItemMax = 16;
+
+__device__ __forceinline__ D3 lattice_position_u32(const ComLattice& L, unsigned int flat) {
+  const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx;
+  const unsigned int t = flat / nz, iz = flat - t * nz, iy = t / nx, ix = t - iy * nx;
+  const double x = ix == nx - 1 ? L.stop[0] : __dadd_rn(__dmul_rn((double)ix, L.step[0]), L.start[0]);
+  const double y = iy == (unsigned int)L.ny - 1 ? L.stop[1] : __dadd_rn(__dmul_rn((double)iy, L.step[1]), L.start[1]);
+  const double z = iz == nz - 1 ? L.stop[2] : __dadd_rn(__dmul_rn((double)iz, L.step[2]), L.start[2]);
+  const double mx = x - L.centre[0], my = y - L.centre[1], mz = z - L.centre[2];
+  D3 q;
+  q.x = mx * L.rotation[0] + my * L.rotation[3] + mz * L.rotation[6];
+  q.y = mx * L.rotation[1] + my * L.rotation[4] + mz * L.rotation[7];
+  q.z = mx * L.rotation[2] + my * L.rotation[5] + mz * L.rotation[8];
+  return {__dadd_rn(__dadd_rn(q.x, L.centre[0]), L.shift[0]), __dadd_rn(__dadd_rn(q.y, L.centre[1]), L.shift[1]),
+          __dadd_rn(__dadd_rn(q.z, L.centre[2]), L.shift[2])};
+}
+
+__global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(const __grid_constant__ K1Params P) {
+  __shared__ float4 s_base[kLatticeWarps][kSegsPerItemMax];  // segment base positions (recentred FP32, w = 1)
+  __shared__ int2 s_seg[kLatticeWarps][kSegsPerItemMax];     // (first launch-local voxel, length)
+  __shared__ unsigned int s_queue[kLatticeWarps][kQueueCap];
+
+  const DeviceScene& sc = P.sc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Cp = sc.n_crystal_padded, n_cgroups = Cp >> 5;
+  const unsigned int nz = (unsigned int)P.vox.lat.nz;
+  const unsigned int cpc = (nz + kSegmentMax - 1) / kSegmentMax;  // segments (chunks) per z-column
+  const unsigned int flat_lo = (unsigned int)P.vox_begin, flat_hi = (unsigned int)(P.vox_begin + P.n_vox);
+  // absolute segment index of a flat voxel index: column * cpc + chunk
+  const unsigned int colA = flat_lo / nz, gA = colA * cpc + (flat_lo - colA * nz) / kSegmentMax;
+  unsigned int* queue = s_queue[warp];
+  float4* base = s_base[warp];
+  int2* segs = s_seg[warp];
+  const long long n_items = (long long)P.n_tiles * n_cgroups;
+
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&P.counters[1], 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((long long)item >= n_items) break;
+    const unsigned int sg = (unsigned int)(item / n_cgroups);
+    const int cg = (int)(item - (unsigned long long)sg * n_cgroups);
+    const int ci = cg * 32 + lane;
+    const bool all_pass = sc.filter_disabled != 0 && ci < sc.n_crystal;
+
+    // stage this item's segments: lane l describes segment gA + sg * segs_per_item + l, clipped to the launch range
+    __syncwarp();
+    int nseg = 0;
+    {
+      const unsigned int g = gA + sg * (unsigned int)P.segs_per_item + (unsigned int)lane;
+      const unsigned int col = g / cpc, iz0 = (g - col * cpc) * kSegmentMax;
+      const unsigned long long a64 = (unsigned long long)col * nz + iz0;
+      bool live = lane < P.segs_per_item && a64 < flat_hi;
+      unsigned int a = 0, b = 0;
+      if (live) {
+        a = max((unsigned int)a64, flat_lo);
+        b = (unsigned int)min((unsigned long long)flat_hi, a64 + min(nz - iz0, (unsigned int)kSegmentMax));
+        live = b > a;
+      }
+      if (live) {
+        const D3 p = lattice_position_u32(P.vox.lat, a);
+        base[lane] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 1.f);
+        segs[lane] = make_int2((int)(a - flat_lo), (int)(b - a));
+      }
+      nseg = __popc(__ballot_sync(0xffffffffu, live));  // live segments are a prefix of the lanes
+    }
+    const float4 gx = __ldg(&sc.det_forms[ci]), gy = __ldg(&sc.det_forms[Cp + ci]), gw = __ldg(&sc.det_forms[2 * Cp + ci]);
+    const float dxs = fmaf(gx.x, P.dz[0], fmaf(gx.y, P.dz[1], gx.z * P.dz[2]));
+    const float dys = fmaf(gy.x, P.dz[0], fmaf(gy.y, P.dz[1], gy.z * P.dz[2]));
+    const float dws = fmaf(gw.x, P.dz[0], fmaf(gw.y, P.dz[1], gw.z * P.dz[2]));
+    __syncwarp();
+
+    int qn = 0;
+    auto drain = [&](int take) {
+      __syncwarp();
+      bool keep = false;
+      unsigned int ent = 0;
+      int vloc = 0;
+      if (lane < take) {
+        ent = queue[qn - take + lane];
+        const int seg = ent >> 11, k = (ent >> 5) & 63;
+        const float4 b = base[seg];
+        const float kf = (float)k;
+        const float4 p = make_float4(fmaf(kf, P.dz[0], b.x), fmaf(kf, P.dz[1], b.y), fmaf(kf, P.dz[2], b.z), 1.f);
+        vloc = segs[seg].x + k;
+        keep = sc.filter_disabled != 0 || stage_b(sc, p, cg * 32 + (int)(ent & 31));
+      }
+      qn -= take;
+      const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+      if (bal) {
+        unsigned long long pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&P.counters[0], (unsigned long long)__popc(bal));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (keep) {
+          const unsigned long long pos = pos0 + __popc(bal & ((1u << lane) - 1u));
+          if (pos < P.cand_capacity) P.cand[pos] = make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)));
+        }
+      }
+      __syncwarp();
+    };
+    auto push = [&](int seg, int k, bool pass) {
+      const unsigned int b = __ballot_sync(0xffffffffu, pass);
+      if (b) {
+        if (pass) queue[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned int)seg << 11) | ((unsigned int)k << 5) | (unsigned int)lane;
+        qn += __popc(b);
+      }
+    };
+
+#pragma unroll 1
+    for (int seg = 0; seg < nseg; ++seg) {
+      const float4 p0 = base[seg];
+      const int len = segs[seg].y;
+      float xs = form(gx, p0), ys = form(gy, p0), w = form(gw, p0);
+      int k = 0;
+#pragma unroll 1
+      for (; k + kUnroll <= len; k += kUnroll) {
+        float t[kUnroll];
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+          t[i] = fabsf(w) - fmaxf(fabsf(xs), fabsf(ys));
+          xs += dxs, ys += dys, w += dws;
+        }
+        float tm = t[0];
+#pragma unroll
+        for (int i = 1; i < kUnroll; ++i) tm = fmaxf(tm, t[i]);
+        if (__any_sync(0xffffffffu, tm >= 0.f || all_pass)) {
+#pragma unroll
+          for (int i = 0; i < kUnroll; ++i) push(seg, k + i, t[i] >= 0.f || all_pass);
+          while (qn >= 32) drain(32);
+        }
+      }
+      for (; k < len; ++k) {
+        const float t = fabsf(w) - fmaxf(fabsf(xs), fabsf(ys));
+        xs += dxs, ys += dys, w += dws;
+        push(seg, k, t >= 0.f || all_pass);
+        while (qn >= 32) drain(32);
+      }
     }
     if (qn > 0) drain(qn);
   }
@@ -458,10 +616,29 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   P.vox.xyz = vox_xyz;
   P.vox_begin = vox_begin;
   P.n_vox = n_vox;
-  P.n_tiles = (int)((n_vox + kTileVoxels - 1) / kTileVoxels);
+  // the lattice kernel indexes voxels with 32 bits
+  const bool lattice_kernel = lattice_h != nullptr && lattice_h->nz >= 1 &&
+                              lattice_h->nx * lattice_h->ny * lattice_h->nz < (1ll << 32);
   const int n_groups = P.sc.n_crystal_padded / 32;
-  P.warps_per_cta = pick_warps(n_groups);
-  P.n_super = (n_groups + P.warps_per_cta - 1) / P.warps_per_cta;
+  if (lattice_kernel) {
+    // recentred position step along z: step_z * (row 2 of R), mesh_calculation.py:150
+    for (int i = 0; i < 3; ++i) P.dz[i] = (float)(lattice_h->step[2] * lattice_h->rotation[6 + i]);
+    const long long nz = lattice_h->nz, cpc = (nz + kSegmentMax - 1) / kSegmentMax;
+    const long long seg_len = (nz + cpc - 1) / cpc;  // typical segment length
+    P.segs_per_item = (int)std::max<long long>(1, std::min<long long>(kSegsPerItemMax, 256 / seg_len));
+    const long long colA = vox_begin / nz, gA = colA * cpc + (vox_begin - colA * nz) / kSegmentMax;
+    const long long colB = (vox_end - 1) / nz, gB = colB * cpc + ((vox_end - 1) - colB * nz) / kSegmentMax;
+    const long long n_segments = n_vox > 0 ? gB - gA + 1 : 0;
+    P.n_tiles = (int)((n_segments + P.segs_per_item - 1) / P.segs_per_item);  // segment groups
+    P.tile_voxels = 0;
+    P.warps_per_cta = kLatticeWarps;
+    P.n_super = n_groups;
+  } else {
+    P.tile_voxels = kTileVoxels;
+    P.n_tiles = (int)((n_vox + P.tile_voxels - 1) / P.tile_voxels);
+    P.warps_per_cta = pick_warps(n_groups);
+    P.n_super = (n_groups + P.warps_per_cta - 1) / P.warps_per_cta;
+  }
   P.counters = reinterpret_cast<unsigned long long*>(workspace);
   P.cand = reinterpret_cast<uint2*>(static_cast<char*>(workspace) + 256);
   P.cand_capacity = (workspace_bytes - 256) / sizeof(uint2);
@@ -493,15 +670,23 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   COM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int threads = P.warps_per_cta * 32;
   int occ = 0;
-  COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, threads, 0));
+  if (lattice_kernel) {
+    COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel_lattice, threads, 0));
+  } else {
+    COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, threads, 0));
+  }
   if (occ < 1) occ = 1;
-  const long long items = (long long)P.n_tiles * P.n_super;
-  const int grid = (int)std::min<long long>(items, (long long)sms * occ);
+  const long long items = (long long)P.n_tiles * P.n_super;  // lattice kernel: warp-level items
+  const long long ctas_wanted = lattice_kernel ? (items + kLatticeWarps - 1) / kLatticeWarps : items;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ctas_wanted, (long long)sms * occ));
   if (g_timing_on) {
     timing_collect();
     cudaEventRecord(g_ev[0], stream);
   }
-  filter_kernel<<<grid, threads, 0, stream>>>(P);
+  if (lattice_kernel)
+    filter_kernel_lattice<<<grid, threads, 0, stream>>>(P);
+  else
+    filter_kernel<<<grid, threads, 0, stream>>>(P);
   COM_CUDA(cudaGetLastError());
   if (g_timing_on) cudaEventRecord(g_ev[1], stream);
   {
