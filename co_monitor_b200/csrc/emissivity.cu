@@ -50,8 +50,35 @@ struct DevTables {
 };
 
 // argmin_k |t[k*STRIDE] - v| with numpy's first-minimum rule, for a non-decreasing table.
+// All tables of this path are (nearly) uniform grids - arange(0, 0.539, 0.001), arange(5, 20000, 1), linspace(.., 2000)
+// - so the search starts from the index a uniform grid would give and walks to the minimum of |t - v|, which is
+// unimodal along a sorted table; a few steps at most.  If the walk does not settle (non-uniform table) it falls back
+// to a binary search.  Either way the result is exactly numpy's argmin.
 template <int STRIDE>
 __device__ __forceinline__ int nearest_first_sorted(const double* __restrict__ t, int n, double v) {
+  if (n > 4) {
+    const double t0 = t[0], t1 = t[(size_t)(n - 1) * STRIDE];
+    if (t1 > t0) {
+      const double g = (v - t0) * ((double)(n - 1) / (t1 - t0));
+      int i = g <= 0.0 ? 0 : (g >= (double)(n - 1) ? n - 1 : (int)(g + 0.5));
+      double d = fabs(t[(size_t)i * STRIDE] - v);
+      int moves = 0;
+      bool settled = true;
+      while (i + 1 < n) {  // towards larger values while not farther
+        const double dn = fabs(t[(size_t)(i + 1) * STRIDE] - v);
+        if (!(dn <= d)) break;
+        if (++moves > 6) { settled = false; break; }
+        ++i, d = dn;
+      }
+      while (settled && i > 0) {  // back to the first index attaining the minimum
+        const double dp = fabs(t[(size_t)(i - 1) * STRIDE] - v);
+        if (!(dp <= d)) break;
+        if (++moves > 12) { settled = false; break; }
+        --i, d = dp;
+      }
+      if (settled) return i;
+    }
+  }
   int lo = 0, hi = n;  // lower_bound: first index with t[i] >= v
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;

@@ -275,6 +275,10 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
     period = 1e9;
   }
   dv.slit_filter = periodic ? 1 : 0;
+  {
+    const V3 nc = (1.0 / norm(load(c0.normal))) * load(c0.normal), np = (1.0 / norm(load(p0.normal))) * load(p0.normal);
+    dv.slit_same_w = norm(nc - np) < 1e-9 ? 1 : 0;
+  }
   dv.slit_period = (float)period;
   dv.slit_inv_period = (float)(1.0 / period);
   dv.slit_period_d = periodic ? period : 0.0;

@@ -31,6 +31,7 @@ struct DeviceScene {
   int n_edges_total;
   int filter_disabled;   // 1: every ray goes to the fp64 stage
   int slit_filter;       // 1: the collimator is periodic and stage B of the filter tests it
+  int slit_same_w;       // 1: both collimator planes share their normal, so one W form serves both sides
   float slit_period;     // slit pitch along e1 (2 |vector_top_bottom|)
   float slit_inv_period;
   SlitRect rect_crys, rect_plasma;

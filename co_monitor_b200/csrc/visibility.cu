@@ -72,8 +72,16 @@ __device__ __forceinline__ D3 ld3(const double* p) { return {p[0], p[1], p[2]}; 
 __device__ __forceinline__ D3 voxel_position(const VoxelSource& v, long long flat) {
   if (!v.use_lattice) return ld3(v.xyz + 3 * flat);
   const ComLattice& L = v.lat;
-  long long iz = flat % L.nz, t = flat / L.nz;
-  long long ix = t % L.nx, iy = t / L.nx;
+  long long iz, ix, iy;
+  if (flat < (1ll << 32)) {  // 32-bit divisions are several times cheaper
+    const unsigned int f = (unsigned int)flat, nz = (unsigned int)L.nz, nx = (unsigned int)L.nx;
+    const unsigned int t = f / nz, y = t / nx;
+    iz = f - t * nz, iy = y, ix = t - y * nx;
+  } else {
+    iz = flat % L.nz;
+    const long long t = flat / L.nz;
+    ix = t % L.nx, iy = t / L.nx;
+  }
   double x = ix == L.nx - 1 ? L.stop[0] : __dadd_rn(__dmul_rn((double)ix, L.step[0]), L.start[0]);
   double y = iy == L.ny - 1 ? L.stop[1] : __dadd_rn(__dmul_rn((double)iy, L.step[1]), L.start[1]);
   double z = iz == L.nz - 1 ? L.stop[2] : __dadd_rn(__dmul_rn((double)iz, L.step[2]), L.start[2]);
@@ -98,12 +106,13 @@ __device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, i
   const int Cp = sc.n_crystal_padded;
   const float4* f = sc.slit_forms + cj;
   const float Xc = form(__ldg(f), p), Yc = form(__ldg(f + Cp), p), Wc = form(__ldg(f + 2 * Cp), p);
-  const float Xp = form(__ldg(f + 3 * Cp), p), Yp = form(__ldg(f + 4 * Cp), p), Wp = form(__ldg(f + 5 * Cp), p);
+  const float Xp = form(__ldg(f + 3 * Cp), p), Yp = form(__ldg(f + 4 * Cp), p);
+  const float Wp = sc.slit_same_w ? Wc : form(__ldg(f + 5 * Cp), p);
   if (fabsf(Wc) < 1e-3f || fabsf(Wp) < 1e-3f) return true;  // grazing ray: let fp64 decide
-  const float ic = __frcp_rn(Wc), ip = __frcp_rn(Wp);
+  const float ic = __frcp_rn(Wc), ip = sc.slit_same_w ? ic : __frcp_rn(Wp);
   const float xc = Xc * ic, yc = Yc * ic, xp = Xp * ip, yp = Yp * ip;
-  if (!(yc >= sc.rect_crys.ylo && yc <= sc.rect_crys.yhi && yp >= sc.rect_plasma.ylo && yp <= sc.rect_plasma.yhi))
-    return false;
+  const bool y_ok = yc >= sc.rect_crys.ylo && yc <= sc.rect_crys.yhi && yp >= sc.rect_plasma.ylo && yp <= sc.rect_plasma.yhi;
+  // slit index from the crystal side; the polygon of slit k sticks out below k*T by |xlo| < T, so k and k+1 are tried
   const float kf = floorf(xc * sc.slit_inv_period);
   bool ok = false;
 #pragma unroll
@@ -114,7 +123,7 @@ __device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, i
     ok |= k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
           b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
   }
-  return ok;
+  return ok && y_ok;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -404,7 +413,7 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
   return {m >= 0.0, m, x};
 }
 
-constexpr int kExactThreads = 128;
+constexpr int kExactThreads = 256;
 
 __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_constant__ K1Params P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -451,20 +460,40 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     bool ok = h.pass;
     if (ok) {  // collimator :344-369, the same slit on both sides
       ok = false;
-      int k_lo = 0, k_hi = S - 1;
-      if (sc.slit_period_d > 0.0) {  // slit k is slit 0 moved by k*T along e1: only k0-1..k0+1 can contain the hit
+      int k_first = 0, k_lo = 0, k_hi = S - 1;
+      bool try_neighbours = true;
+      if (sc.slit_period_d > 0.0) {
+        // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slit that can contain it
         const HitResult h0 = aperture_hit(s_ap[0], s_edges, plasma, crystal);
-        const int k0 = (int)floor(h0.x / sc.slit_period_d);
-        k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
-        if (h0.margin == -1e300) k_hi = -1;  // parallel to the collimator plane: NaN in the reference
+        if (h0.margin == -1e300) {
+          k_hi = -1;  // parallel to the collimator plane: NaN in the reference
+        } else {
+          const double q = h0.x / sc.slit_period_d;
+          const int k0 = (int)floor(q);
+          k_first = min(max(k0, 0), S - 1);
+          k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
+          // neighbours matter only within 1e-3 periods of a period boundary (polygon skew is 0.02 mm at most)
+          const double fr = q - floor(q);
+          try_neighbours = fr < 0.05 || fr > 0.95;
+        }
       }
-      for (int k = k_lo; k <= k_hi && !ok; ++k) {
+      auto both_sides = [&](int k) {
         const HitResult a = aperture_hit(s_ap[2 * k], s_edges, plasma, crystal);
         near_edge |= fabs(a.margin) < kNear;
-        if (!a.pass) continue;
+        if (!a.pass) return false;
         const HitResult b = aperture_hit(s_ap[2 * k + 1], s_edges, plasma, crystal);
         near_edge |= fabs(b.margin) < kNear;
-        ok = b.pass;
+        return b.pass;
+      };
+      if (k_hi >= 0) {
+        if (sc.slit_period_d > 0.0) {
+          ok = both_sides(k_first);
+          if (!ok && try_neighbours)
+            for (int k = k_lo; k <= k_hi && !ok; ++k)
+              if (k != k_first) ok = both_sides(k);
+        } else {
+          for (int k = k_lo; k <= k_hi && !ok; ++k) ok = both_sides(k);
+        }
       }
     }
     if (ok) {
