@@ -1,0 +1,1 @@
+"""Drop-in import path: `co_monitor.emissivity` of tfornal/co_monitor, served by co_monitor_b200 (B200 implementation)."""

@@ -1,0 +1,5 @@
+"""Drop-in import path: `co_monitor.emissivity.reader` of tfornal/co_monitor, served by co_monitor_b200 (B200 implementation)."""
+from co_monitor_b200.emissivity.reader import *  # noqa: F401,F403
+from co_monitor_b200.emissivity import reader as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith('__')})

@@ -309,10 +309,15 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
     return (1.0 / norm(N)) * N;
   };
   // value(p') = F.(c' - p')  ->  g = -F, h = F.c'
-  auto put = [&](std::vector<float>& tab, int form, int c, V3 F, V3 cl) {
-    float* f = &tab[((size_t)form * Cp + c) * 4];
+  auto put_at = [&](float* f, V3 F, V3 cl) {
     f[0] = (float)-F.x, f[1] = (float)-F.y, f[2] = (float)-F.z, f[3] = (float)dot(F, cl);
   };
+  // detector forms are read by the lane that owns the crystal point: form-major keeps the loads coalesced;
+  // slit forms are gathered by arbitrary lanes: crystal-major keeps one point's six forms in 96 contiguous bytes
+  auto put = [&](std::vector<float>& tab, int form, int c, V3 F, V3 cl) {
+    put_at(&tab[((size_t)form * Cp + c) * 4], F, cl);
+  };
+  auto put_slit = [&](int form, int c, V3 F, V3 cl) { put_at(&hs.slit_forms[((size_t)c * 6 + form) * 4], F, cl); };
   for (int c = 0; c < Cp; ++c) {
     if (c >= C) {  // padding lanes: |Xs| = 1e30 can never be <= |W| = 0
       hs.det_forms[((size_t)0 * Cp + c) * 4 + 3] = 1e30f;
@@ -334,9 +339,9 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
       const ComAperture& ap = hs.apertures[side];
       const V3 nh = unit_normal(ap), q = load(ap.p1) - cp;
       const double a = dot(nh, q), cx0 = dot(load(ap.e1), q), cy0 = dot(load(ap.e2), q);
-      put(hs.slit_forms, 3 * side + 0, c, a * load(ap.e1) - cx0 * nh, cl);
-      put(hs.slit_forms, 3 * side + 1, c, a * load(ap.e2) - cy0 * nh, cl);
-      put(hs.slit_forms, 3 * side + 2, c, nh, cl);
+      put_slit(3 * side + 0, c, a * load(ap.e1) - cx0 * nh, cl);
+      put_slit(3 * side + 1, c, a * load(ap.e2) - cy0 * nh, cl);
+      put_slit(3 * side + 2, c, nh, cl);
     }
   }
   return COM_OK;

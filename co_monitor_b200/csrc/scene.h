@@ -45,7 +45,7 @@ struct DeviceScene {
   const double* edges;           // (n_edges_total,3)
   // FP32 filter tables: linear forms in the recentred voxel position p' = p - origin, value = g.p' + h
   const float4* det_forms;       // [3][Cp]: Xs, Ys, W of the mirrored detector; passes iff max(|Xs|,|Ys|) <= |W|
-  const float4* slit_forms;      // [6][Cp]: X', Y', W on the crystal-side slit plane, then on the plasma side
+  const float4* slit_forms;      // [Cp][6]: X', Y', W on the crystal-side slit plane, then on the plasma side
 };
 
 // Host-side result of analysing a ComSceneDesc (pure CPU, no CUDA).

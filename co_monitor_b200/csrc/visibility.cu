@@ -101,15 +101,20 @@ __device__ __forceinline__ float form(const float4 g, const float4 p) {
   return fmaf(g.x, p.x, fmaf(g.y, p.y, fmaf(g.z, p.z, g.w)));
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, ~1 ulp: ample for a test with a 5e-3 mm band
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, int cj) {
   if (!sc.slit_filter) return true;  // non-periodic collimator: decided in fp64 only
-  const int Cp = sc.n_crystal_padded;
-  const float4* f = sc.slit_forms + cj;
-  const float Xc = form(__ldg(f), p), Yc = form(__ldg(f + Cp), p), Wc = form(__ldg(f + 2 * Cp), p);
-  const float Xp = form(__ldg(f + 3 * Cp), p), Yp = form(__ldg(f + 4 * Cp), p);
-  const float Wp = sc.slit_same_w ? Wc : form(__ldg(f + 5 * Cp), p);
-  if (fabsf(Wc) < 1e-3f || fabsf(Wp) < 1e-3f) return true;  // grazing ray: let fp64 decide
-  const float ic = __frcp_rn(Wc), ip = sc.slit_same_w ? ic : __frcp_rn(Wp);
+  const float4* f = sc.slit_forms + 6 * cj;  // six forms of one crystal point are contiguous (96 B)
+  const float Xc = form(__ldg(f), p), Yc = form(__ldg(f + 1), p), Wc = form(__ldg(f + 2), p);
+  const float Xp = form(__ldg(f + 3), p), Yp = form(__ldg(f + 4), p);
+  const float Wp = sc.slit_same_w ? Wc : form(__ldg(f + 5), p);
+  if (fminf(fabsf(Wc), fabsf(Wp)) < 1e-3f) return true;  // grazing ray: let fp64 decide
+  const float ic = rcp_approx(Wc), ip = sc.slit_same_w ? ic : rcp_approx(Wp);
   const float xc = Xc * ic, yc = Yc * ic, xp = Xp * ip, yp = Yp * ip;
   const bool y_ok = yc >= sc.rect_crys.ylo && yc <= sc.rect_crys.yhi && yp >= sc.rect_plasma.ylo && yp <= sc.rect_plasma.yhi;
   // slit index from the crystal side; the polygon of slit k sticks out below k*T by |xlo| < T, so k and k+1 are tried
@@ -118,8 +123,7 @@ __device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, i
 #pragma unroll
   for (int dk = 0; dk < 2; ++dk) {
     const float k = kf + (float)dk;
-    const float sh = k * sc.slit_period;
-    const float a = xc - sh, b = xp - sh;
+    const float a = fmaf(-k, sc.slit_period, xc), b = fmaf(-k, sc.slit_period, xp);
     ok |= k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
           b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
   }
