@@ -172,11 +172,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
 
-    lattice = refined_lattice(world)
-    P = lattice.n_points
-    lo, hi = rank * P // world, (rank + 1) * P // world
-    # Reff of every lattice voxel: the shipped 15 mm VMEC grid resampled onto the lattice (no VMEC service here)
-    reff_table = torch.from_numpy(interpolate_reff(lattice, 15)).to(device)
+    full_lattice = refined_lattice(world)
+    P = full_lattice.n_points
+    # block-cyclic shard of the z-columns: the visible voxels are spatially clustered, contiguous ranges would not balance
+    lattice = full_lattice.shard(world, rank, cols_per_block=8)
+    lo, hi = 0, lattice.n_points
+    # Reff of every lattice voxel: the shipped 15 mm VMEC grid resampled onto the lattice (no VMEC service here),
+    # re-ordered to this shard's local voxel order
+    reff_all = interpolate_reff(full_lattice, 15)
+    reff_table = torch.from_numpy(reff_all[lattice.local_to_global(np.arange(lattice.n_points))]).to(device)
     profile = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy()
     scenes, pipes = {}, {}
     with contextlib.redirect_stdout(io.StringIO()):
@@ -215,8 +219,8 @@ def run_ours(args):
 
     def step():
         """Stage 1 + Stage 2 for the four channels, each channel on its own stream (they are independent); at N > 1
-        the per-rank maxima of the mapped Reff are max-reduced before Stage 2 and the per-channel fluxes sum-reduced
-        after it (two small NCCL all-reduces on the main stream)."""
+        the per-rank maximum of the mapped Reff is max-reduced per channel on the channel's stream before Stage 2 and
+        the per-channel fluxes are sum-reduced after the join (small NCCL all-reduces, latency bound)."""
         cur = torch.cuda.current_stream(device)
         fork_ev.record(cur)
         for i, el in enumerate(ELEMENTS):
@@ -228,17 +232,8 @@ def run_ours(args):
                     flux[i].copy_(pipes[el].flux)
                     join_ev[el].record(streams[el])
                 else:
-                    mapped[i:i + 1].copy_(pipes[el].mapped_max)
-                    mid_ev[el].record(streams[el])
-        if world > 1:
-            for el in ELEMENTS:
-                cur.wait_event(mid_ev[el])
-            dist.all_reduce(mapped, op=dist.ReduceOp.MAX)
-            fork_ev.record(cur)
-            for i, el in enumerate(ELEMENTS):
-                with torch.cuda.stream(streams[el]):
-                    streams[el].wait_event(fork_ev)
-                    pipes[el].mapped_max.copy_(mapped[i:i + 1])
+                    # per-channel exchange on the channel's own stream: no cross-channel join in mid-step
+                    dist.all_reduce(pipes[el].mapped_max, op=dist.ReduceOp.MAX)
                     pipes[el].launch_emissivity()
                     flux[i].copy_(pipes[el].flux)
                     join_ev[el].record(streams[el])
@@ -255,19 +250,31 @@ def run_ours(args):
 
     # one CUDA graph of the whole step (every launch of the path is stream-ordered, nothing syncs with the host)
     graph = None
+    # N > 1: NCCL collectives inside a captured graph gain ~3 % here and make process-group teardown hang; not used
     if world == 1 and not args.no_graph:
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(main_stream)
-        with torch.cuda.stream(side):
-            step()
-        main_stream.wait_stream(side)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph):
-            step()
-        for _ in range(3):
-            graph.replay()
-        torch.cuda.synchronize()
+        try:
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(main_stream)
+            with torch.cuda.stream(side):
+                step()
+            main_stream.wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                step()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:  # e.g. an NCCL build that cannot be captured: launch kernel by kernel instead
+            if rank == 0:
+                print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); running without", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    if world > 1:  # all ranks must take the same path
+        flag = torch.tensor([1 if graph is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            graph = None
     run_step = graph.replay if graph is not None else step
 
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps (untimed) ----
@@ -408,7 +415,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 filter + f64 decision/weight/emissivity", "data": "synthetic",
         "config": {
             "workload": f"configs[1]: B/C/N/O, Stage 1 (visibility + weight) then Stage 2 (EXCIT + RECOM emissivity -> flux), "
-                        f"10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} ({P} voxels, {hi - lo} per GPU) "
+                        f"10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} ({P} voxels, {hi - lo} per GPU, "
+                        f"block-cyclic shards of 8 z-columns) "
                         f"x {H}x{L} crystal points x {SLITS} slits, Reff = shipped 15 mm VMEC grid resampled",
             "tests_per_step": tests_per_step_rank * world,
             "l2": "256 MB buffer written between timed steps (L2 flushed, untimed)",

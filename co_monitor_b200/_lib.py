@@ -90,6 +90,9 @@ class ComLattice(C.Structure):
         ("centre", c_double3),
         ("rotation", C.c_double * 9),
         ("shift", c_double3),
+        ("shard_cols_per_block", C.c_int64),
+        ("shard_count", C.c_int64),
+        ("shard_index", C.c_int64),
     ]
 
 
@@ -155,6 +158,8 @@ def _declare(lib):
     lib.com_aperture_contains.argtypes = [C.POINTER(ComAperture), dp]
     lib.com_scene_create.argtypes = [C.POINTER(ComSceneDesc), C.POINTER(vp)]
     lib.com_scene_destroy.argtypes = [vp]
+    lib.com_lattice_local_voxels.restype = C.c_int64
+    lib.com_lattice_local_voxels.argtypes = [C.POINTER(ComLattice)]
     lib.com_scene_aperture_count.argtypes = [vp]
     lib.com_scene_get_aperture.argtypes = [vp, i32, C.POINTER(ComAperture)]
     lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), dp, dp]
@@ -194,7 +199,7 @@ EXPORTED_SYMBOLS = [
     "com_abi_version", "com_last_error", "com_error_string",
     "com_aperture_from_slab", "com_aperture_contains",
     "com_scene_create", "com_scene_destroy", "com_scene_aperture_count", "com_scene_get_aperture",
-    "com_scene_filter_info",
+    "com_scene_filter_info", "com_lattice_local_voxels",
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
     "com_visible_weights_host", "com_host_arena_release",
     "com_compact_workspace_bytes", "com_compact_visible",

@@ -15,6 +15,7 @@ int visibility_launch(const ComScene*, const ComLattice*, const double*, long lo
                       ComRayRecord*, long long, unsigned long long*, const uint16_t*, double*, int, ComStats*, void*,
                       size_t, cudaStream_t);
 size_t visibility_workspace_bytes(const DeviceScene&, long long, double);
+long long lattice_local_voxels(const ComLattice&);
 void kernel_timing_enable(int on);
 void kernel_timing_read(double*, double*, long long*);
 }  // namespace com
@@ -257,6 +258,10 @@ int com_scene_create(const ComSceneDesc* desc_h, ComScene** out) {
   bind_scene(sc->dev, static_cast<char*>(sc->d_blob), blob);
   *out = sc;
   return COM_OK;
+}
+
+int64_t com_lattice_local_voxels(const ComLattice* lattice_h) {
+  return lattice_h ? com::lattice_local_voxels(*lattice_h) : 0;
 }
 
 int com_scene_destroy(ComScene* scene) {

@@ -446,7 +446,7 @@ int com_tables_destroy(ComTables* t) {
 }
 
 size_t com_emissivity_workspace_bytes(int64_t n) {
-  long long blocks = std::min<long long>(std::max<long long>(1, (n + com::kK2Threads - 1) / com::kK2Threads), 148 * 8);
+  long long blocks = std::min<long long>(std::max<long long>(1, (n + com::kK2Threads - 1) / com::kK2Threads), 148 * 8);  // upper bound of any launch below
   return 256 + align_up(sizeof(double) * (8 + (size_t)blocks * (com::kMaxTransitions + 1)), 256);
 }
 
@@ -490,7 +490,7 @@ int com_emissivity_integrate(const ComTables* tables, const double* profile, int
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256 + 64, s));
   COM_CUDA(cudaMemsetAsync(flux_out, 0, sizeof(double) * (tables->n_trans + 1), s));
   if (n == 0) return COM_OK;
-  const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 8);
+  const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 2);
   if (!mapped_reff_max) com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
   com::emissivity_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
   COM_CUDA(cudaGetLastError());

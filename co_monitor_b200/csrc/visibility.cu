@@ -68,18 +68,25 @@ __device__ __forceinline__ D3 operator*(double s, D3 a) { return {s * a.x, s * a
 __device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ D3 ld3(const double* p) { return {p[0], p[1], p[2]}; }
 
+// Local column of a block-cyclic shard -> global column (identity when the lattice is not sharded).
+__device__ __forceinline__ long long global_column(const ComLattice& L, long long cl) {
+  if (L.shard_count <= 1 || L.shard_cols_per_block <= 0) return cl;
+  const long long lb = cl / L.shard_cols_per_block, o = cl - lb * L.shard_cols_per_block;
+  return (lb * L.shard_count + L.shard_index) * L.shard_cols_per_block + o;
+}
+
 // CuboidMesh closed form (mesh_calculation.py:128-155); mul/add kept separate like numpy.linspace.
 __device__ __forceinline__ D3 voxel_position(const VoxelSource& v, long long flat) {
   if (!v.use_lattice) return ld3(v.xyz + 3 * flat);
   const ComLattice& L = v.lat;
   long long iz, ix, iy;
-  if (flat < (1ll << 32)) {  // 32-bit divisions are several times cheaper
+  if (flat < (1ll << 32) && L.shard_count <= 1) {  // 32-bit divisions are several times cheaper
     const unsigned int f = (unsigned int)flat, nz = (unsigned int)L.nz, nx = (unsigned int)L.nx;
     const unsigned int t = f / nz, y = t / nx;
     iz = f - t * nz, iy = y, ix = t - y * nx;
   } else {
     iz = flat % L.nz;
-    const long long t = flat / L.nz;
+    const long long t = global_column(L, flat / L.nz);
     ix = t % L.nx, iy = t / L.nx;
   }
   double x = ix == L.nx - 1 ? L.stop[0] : __dadd_rn(__dmul_rn((double)ix, L.step[0]), L.start[0]);
@@ -254,7 +261,8 @@ constexpr int kSegsPerItemMax = 16;
 
 __device__ __forceinline__ D3 lattice_position_u32(const ComLattice& L, unsigned int flat) {
   const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx;
-  const unsigned int t = flat / nz, iz = flat - t * nz, iy = t / nx, ix = t - iy * nx;
+  const unsigned int tl = flat / nz, iz = flat - tl * nz;
+  const unsigned int t = (unsigned int)global_column(L, tl), iy = t / nx, ix = t - iy * nx;
   const double x = ix == nx - 1 ? L.stop[0] : __dadd_rn(__dmul_rn((double)ix, L.step[0]), L.start[0]);
   const double y = iy == (unsigned int)L.ny - 1 ? L.stop[1] : __dadd_rn(__dmul_rn((double)iy, L.step[1]), L.start[1]);
   const double z = iz == nz - 1 ? L.stop[2] : __dadd_rn(__dmul_rn((double)iz, L.step[2]), L.start[2]);
@@ -598,6 +606,18 @@ void kernel_timing_read(double* filter_ms, double* exact_ms, long long* launches
   if (launches) *launches = g_ms_launches;
 }
 
+long long lattice_local_voxels(const ComLattice& L) {
+  const long long cols = L.nx * L.ny;
+  if (L.shard_count <= 1 || L.shard_cols_per_block <= 0) return cols * L.nz;
+  const long long cpb = L.shard_cols_per_block, blocks = (cols + cpb - 1) / cpb;
+  if (L.shard_index < 0 || L.shard_index >= L.shard_count) return 0;
+  const long long mine = blocks > L.shard_index ? (blocks - L.shard_index + L.shard_count - 1) / L.shard_count : 0;
+  long long local_cols = mine * cpb;
+  // the last global block may be partial; it belongs to shard (blocks - 1) % shard_count
+  if (mine > 0 && (blocks - 1) % L.shard_count == L.shard_index) local_cols -= blocks * cpb - cols;
+  return local_cols * L.nz;
+}
+
 static int pick_warps(int n_groups) {  // warps per CTA wasting the fewest idle warps; ties -> larger CTA
   if (n_groups <= kMaxWarps) return n_groups;
   int best = kMaxWarps, best_waste = 1 << 30;
@@ -641,8 +661,8 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   P.vox.use_lattice = lattice_h ? 1 : 0;
   if (lattice_h) {
     P.vox.lat = *lattice_h;
-    if (vox_end > lattice_h->nx * lattice_h->ny * lattice_h->nz || vox_begin < 0) {
-      set_error("voxel range [%lld,%lld) outside the lattice", vox_begin, vox_end);
+    if (vox_end > lattice_local_voxels(*lattice_h) || vox_begin < 0) {
+      set_error("voxel range [%lld,%lld) outside the lattice (shard)", vox_begin, vox_end);
       return COM_E_BADARG;
     }
   }

@@ -43,6 +43,7 @@ def lattice_struct(lat: Lattice) -> _lib.ComLattice:
         out.centre[i], out.shift[i] = lat.centre[i], lat.shift[i]
     for i, v in enumerate(np.asarray(lat.rotation, dtype=float).reshape(9)):
         out.rotation[i] = v
+    out.shard_cols_per_block, out.shard_count, out.shard_index = lat.shard_cols_per_block, lat.shard_count, lat.shard_index
     return out
 
 

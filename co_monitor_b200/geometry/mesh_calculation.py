@@ -41,13 +41,51 @@ class Lattice:
     centre: np.ndarray  # (3,) plasma central point c
     rotation: np.ndarray  # (3, 3) R, row-vector convention
     shift: np.ndarray  # (3,)
+    # block-cyclic shard of the z-columns (multi-GPU): every flat index is then local to the shard
+    shard_cols_per_block: int = 0
+    shard_count: int = 1
+    shard_index: int = 0
+
+    @property
+    def n_points_global(self) -> int:
+        return self.nx * self.ny * self.nz
 
     @property
     def n_points(self) -> int:
-        return self.nx * self.ny * self.nz
+        """Voxels of this lattice, or of this shard of it."""
+        cols = self.nx * self.ny
+        if self.shard_count <= 1 or self.shard_cols_per_block <= 0:
+            return cols * self.nz
+        cpb = self.shard_cols_per_block
+        blocks = -(-cols // cpb)
+        mine = len(range(self.shard_index, blocks, self.shard_count))
+        local_cols = mine * cpb
+        if mine and (blocks - 1) % self.shard_count == self.shard_index:
+            local_cols -= blocks * cpb - cols
+        return local_cols * self.nz
+
+    def shard(self, count: int, index: int, cols_per_block: int = 8) -> "Lattice":
+        """Shard *index* of *count*: z-columns dealt round-robin in blocks of *cols_per_block*."""
+        from dataclasses import replace
+
+        if not 0 <= index < count:
+            raise ValueError(f"shard {index} outside {count}")
+        if count == 1:
+            return replace(self, shard_cols_per_block=0, shard_count=1, shard_index=0)
+        return replace(self, shard_cols_per_block=int(cols_per_block), shard_count=int(count), shard_index=int(index))
+
+    def local_to_global(self, flat):
+        """Global flat index of the shard-local flat index (identity when not sharded)."""
+        flat = np.asarray(flat, dtype=np.int64)
+        if self.shard_count <= 1 or self.shard_cols_per_block <= 0:
+            return flat
+        cpb = self.shard_cols_per_block
+        cl, iz = flat // self.nz, flat % self.nz
+        cg = ((cl // cpb) * self.shard_count + self.shard_index) * cpb + cl % cpb
+        return cg * self.nz + iz
 
     def unravel(self, flat):
-        flat = np.asarray(flat, dtype=np.int64)
+        flat = self.local_to_global(flat)
         iz = flat % self.nz
         t = flat // self.nz
         return t % self.nx, t // self.nx, iz  # ix, iy, iz

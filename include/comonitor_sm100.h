@@ -122,7 +122,12 @@ int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* 
 
 /* Implicit voxel lattice == CuboidMesh (mesh_calculation.py:119-159):
  *   flat = (iy*nx + ix)*nz + iz ;  p = ((x[ix],y[iy],z[iz]) - centre) . R + centre + shift
- *   x[i] = start[0] + i*step[0]  (last sample = stop[0], as numpy.linspace does) */
+ *   x[i] = start[0] + i*step[0]  (last sample = stop[0], as numpy.linspace does)
+ * Sharding (multi-GPU): with shard_count > 1 the structure describes ONE SHARD of the lattice.  The nx*ny z-columns are
+ * dealt round-robin in blocks of shard_cols_per_block columns; shard shard_index owns blocks shard_index,
+ * shard_index + shard_count, ...  Every flat index the API takes or returns is then LOCAL to the shard:
+ *   local column cl = flat / nz  ->  global column ((cl / cpb) * shard_count + shard_index) * cpb + cl % cpb.
+ * Block-cyclic shards keep the (spatially clustered) visible voxels balanced over the ranks. */
 typedef struct ComLattice {
   int64_t nx, ny, nz;
   double start[3];
@@ -131,7 +136,13 @@ typedef struct ComLattice {
   double centre[3];
   double rotation[9]; /* row-major R, row-vector convention (p_row . R) */
   double shift[3];
+  int64_t shard_cols_per_block; /* 0 or shard_count <= 1: not sharded */
+  int64_t shard_count;
+  int64_t shard_index;
 } ComLattice;
+
+/* Number of voxels of the shard described by *lattice_h* (nx*ny*nz when not sharded). */
+int64_t com_lattice_local_voxels(const ComLattice* lattice_h);
 
 typedef struct ComStats {
   uint64_t tests;           /* voxel x crystal-point rays examined                                   */
