@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   __shared__ float4 s_base[kLatticeWarps][kSegsPerItemMax];  // segment base positions (recentred FP32, w = 1)
   __shared__ int2 s_seg[kLatticeWarps][kSegsPerItemMax];     // (first launch-local voxel, length)
   __shared__ unsigned int s_queue[kLatticeWarps][kQueueCap];
+  __shared__ uint2 s_out[kLatticeWarps][64];                 // survivors of stage B waiting for a 32-wide flush
 
   const DeviceScene& sc = P.sc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -289,6 +290,22 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   // absolute segment index of a flat voxel index: column * cpc + chunk
   const unsigned int colA = flat_lo / nz, gA = colA * cpc + (flat_lo - colA * nz) / kSegmentMax;
   unsigned int* queue = s_queue[warp];
+  uint2* outq = s_out[warp];
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  int on = 0;  // warp-uniform number of pending survivors
+  // append `count` (<= 32) pending survivors to the global candidate list: one atomic, one coalesced store
+  auto flush = [&](int count) {
+    __syncwarp();
+    unsigned long long pos0 = 0;
+    if (lane == 0) pos0 = atomicAdd(&P.counters[0], (unsigned long long)count);
+    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+    if (lane < count && pos0 + lane < P.cand_capacity) P.cand[pos0 + lane] = outq[lane];
+    const uint2 carry = outq[min(lane + count, 63)];
+    __syncwarp();
+    if (lane + count < on) outq[lane] = carry;
+    on -= count;
+    __syncwarp();
+  };
   float4* base = s_base[warp];
   int2* segs = s_seg[warp];
   const long long n_items = (long long)P.n_tiles * n_cgroups;
@@ -348,20 +365,16 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       qn -= take;
       const unsigned int bal = __ballot_sync(0xffffffffu, keep);
       if (bal) {
-        unsigned long long pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(&P.counters[0], (unsigned long long)__popc(bal));
-        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        if (keep) {
-          const unsigned long long pos = pos0 + __popc(bal & ((1u << lane) - 1u));
-          if (pos < P.cand_capacity) P.cand[pos] = make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)));
-        }
+        if (keep) outq[on + __popc(bal & lt_mask)] = make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)));
+        on += __popc(bal);
+        if (on >= 32) flush(32);
       }
       __syncwarp();
     };
     auto push = [&](int seg, int k, bool pass) {
       const unsigned int b = __ballot_sync(0xffffffffu, pass);
       if (b) {
-        if (pass) queue[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned int)seg << 11) | ((unsigned int)k << 5) | (unsigned int)lane;
+        if (pass) queue[qn + __popc(b & lt_mask)] = ((unsigned int)seg << 11) | ((unsigned int)k << 5) | (unsigned int)lane;
         qn += __popc(b);
       }
     };
@@ -398,6 +411,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
     }
     if (qn > 0) drain(qn);
   }
+  if (on > 0) flush(on);
 }
 
 // ------------------------------------------------------------------------------------------------------
