@@ -114,27 +114,32 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, ~1 ulp: amp
   return r;
 }
 
-__device__ __forceinline__ bool stage_b(const DeviceScene& sc, const float4 p, int cj) {
-  if (!sc.slit_filter) return true;  // non-periodic collimator: decided in fp64 only
+constexpr int kSlitUnknown = 15;  // candidate records carry the slit the FP32 filter saw in 4 bits; 15 = not known
+
+// Returns -1 when the ray misses every slit (band included), else the index of the slit it goes through on both
+// sides, or kSlitUnknown when that is ambiguous / not evaluated.  The exact kernel tries the hinted slit first.
+__device__ __forceinline__ int stage_b(const DeviceScene& sc, const float4 p, int cj) {
+  if (!sc.slit_filter) return kSlitUnknown;  // non-periodic collimator: decided in fp64 only
   const float4* f = sc.slit_forms + 6 * cj;  // six forms of one crystal point are contiguous (96 B)
   const float Xc = form(__ldg(f), p), Yc = form(__ldg(f + 1), p), Wc = form(__ldg(f + 2), p);
   const float Xp = form(__ldg(f + 3), p), Yp = form(__ldg(f + 4), p);
   const float Wp = sc.slit_same_w ? Wc : form(__ldg(f + 5), p);
-  if (fminf(fabsf(Wc), fabsf(Wp)) < 1e-3f) return true;  // grazing ray: let fp64 decide
+  if (fminf(fabsf(Wc), fabsf(Wp)) < 1e-3f) return kSlitUnknown;  // grazing ray: let fp64 decide
   const float ic = rcp_approx(Wc), ip = sc.slit_same_w ? ic : rcp_approx(Wp);
   const float xc = Xc * ic, yc = Yc * ic, xp = Xp * ip, yp = Yp * ip;
   const bool y_ok = yc >= sc.rect_crys.ylo && yc <= sc.rect_crys.yhi && yp >= sc.rect_plasma.ylo && yp <= sc.rect_plasma.yhi;
   // slit index from the crystal side; the polygon of slit k sticks out below k*T by |xlo| < T, so k and k+1 are tried
   const float kf = floorf(xc * sc.slit_inv_period);
-  bool ok = false;
+  int code = -1;
 #pragma unroll
   for (int dk = 0; dk < 2; ++dk) {
     const float k = kf + (float)dk;
     const float a = fmaf(-k, sc.slit_period, xc), b = fmaf(-k, sc.slit_period, xp);
-    ok |= k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
-          b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
+    const bool ok = k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
+                    b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
+    if (ok) code = code < 0 ? min((int)k, kSlitUnknown) : kSlitUnknown;
   }
-  return ok && y_ok;
+  return y_ok ? code : -1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -190,9 +195,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
       __syncwarp();
       bool keep = false;
       unsigned int ent = 0;
+      int slit = -1;
       if (lane < take) {
         ent = queue[qn - take + lane];
-        keep = sc.filter_disabled != 0 || stage_b(sc, s_tile[ent >> 5], ci - lane + (int)(ent & 31));
+        slit = sc.filter_disabled != 0 ? kSlitUnknown : stage_b(sc, s_tile[ent >> 5], ci - lane + (int)(ent & 31));
+        keep = slit >= 0;
       }
       qn -= take;
       const unsigned int b = __ballot_sync(0xffffffffu, keep);
@@ -203,7 +210,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
         if (keep) {
           const unsigned long long pos = base + __popc(b & ((1u << lane) - 1u));
           if (pos < P.cand_capacity)
-            P.cand[pos] = make_uint2((unsigned int)(tile_base + (ent >> 5)), (unsigned int)(ci - lane + (ent & 31)));
+            P.cand[pos] = make_uint2((unsigned int)(tile_base + (ent >> 5)),
+                                     (unsigned int)(ci - lane + (ent & 31)) | ((unsigned int)slit << 28));
         }
       }
       __syncwarp();
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       __syncwarp();
       bool keep = false;
       unsigned int ent = 0;
-      int vloc = 0;
+      int vloc = 0, slit = -1;
       if (lane < take) {
         ent = queue[qn - take + lane];
         const int seg = ent >> 11, k = (ent >> 5) & 63;
@@ -360,12 +368,15 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
         const float kf = (float)k;
         const float4 p = make_float4(fmaf(kf, P.dz[0], b.x), fmaf(kf, P.dz[1], b.y), fmaf(kf, P.dz[2], b.z), 1.f);
         vloc = segs[seg].x + k;
-        keep = sc.filter_disabled != 0 || stage_b(sc, p, cg * 32 + (int)(ent & 31));
+        slit = sc.filter_disabled != 0 ? kSlitUnknown : stage_b(sc, p, cg * 32 + (int)(ent & 31));
+        keep = slit >= 0;
       }
       qn -= take;
       const unsigned int bal = __ballot_sync(0xffffffffu, keep);
       if (bal) {
-        if (keep) outq[on + __popc(bal & lt_mask)] = make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)));
+        if (keep)
+          outq[on + __popc(bal & lt_mask)] =
+              make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)) | ((unsigned int)slit << 28));
         on += __popc(bal);
         if (on >= 32) flush(32);
       }
@@ -472,7 +483,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   if (i < n) {
     const uint2 e = P.cand[i];
     const long long vloc = e.x;
-    const int ci = (int)e.y;
+    const int ci = (int)(e.y & 0x0fffffffu), slit_hint = (int)(e.y >> 28);
     const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
     const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
     // simulation.py:309-321
@@ -485,24 +496,6 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     near_edge |= fabs(h.margin) < kNear;
     bool ok = h.pass;
     if (ok) {  // collimator :344-369, the same slit on both sides
-      ok = false;
-      int k_first = 0, k_lo = 0, k_hi = S - 1;
-      bool try_neighbours = true;
-      if (sc.slit_period_d > 0.0) {
-        // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slit that can contain it
-        const HitResult h0 = aperture_hit(s_ap[0], s_edges, plasma, crystal);
-        if (h0.margin == -1e300) {
-          k_hi = -1;  // parallel to the collimator plane: NaN in the reference
-        } else {
-          const double q = h0.x / sc.slit_period_d;
-          const int k0 = (int)floor(q);
-          k_first = min(max(k0, 0), S - 1);
-          k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
-          // neighbours matter only within 1e-3 periods of a period boundary (polygon skew is 0.02 mm at most)
-          const double fr = q - floor(q);
-          try_neighbours = fr < 0.05 || fr > 0.95;
-        }
-      }
       auto both_sides = [&](int k) {
         const HitResult a = aperture_hit(s_ap[2 * k], s_edges, plasma, crystal);
         near_edge |= fabs(a.margin) < kNear;
@@ -511,14 +504,36 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
         near_edge |= fabs(b.margin) < kNear;
         return b.pass;
       };
-      if (k_hi >= 0) {
+      // the slit the FP32 filter saw is tried first: "any slit passes" is all the reference asks (:408-411)
+      ok = slit_hint < S && slit_hint != kSlitUnknown && both_sides(slit_hint);
+      if (!ok) {
+        int k_first = -1, k_lo = 0, k_hi = S - 1;
+        bool try_neighbours = true;
         if (sc.slit_period_d > 0.0) {
-          ok = both_sides(k_first);
-          if (!ok && try_neighbours)
+          // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slit that can contain it
+          const HitResult h0 = aperture_hit(s_ap[0], s_edges, plasma, crystal);
+          if (h0.margin == -1e300) {
+            k_hi = -1;  // parallel to the collimator plane: NaN in the reference
+          } else {
+            const double q = h0.x / sc.slit_period_d;
+            const int k0 = (int)floor(q);
+            k_first = min(max(k0, 0), S - 1);
+            k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
+            // neighbours matter only near a period boundary (polygon skew is 0.02 mm at most)
+            const double fr = q - floor(q);
+            try_neighbours = fr < 0.05 || fr > 0.95;
+          }
+        }
+        if (k_hi >= 0) {
+          if (k_first >= 0) {
+            ok = k_first != slit_hint && both_sides(k_first);
+            if (!ok && try_neighbours)
+              for (int k = k_lo; k <= k_hi && !ok; ++k)
+                if (k != k_first && k != slit_hint) ok = both_sides(k);
+          } else {
             for (int k = k_lo; k <= k_hi && !ok; ++k)
-              if (k != k_first) ok = both_sides(k);
-        } else {
-          for (int k = k_lo; k <= k_hi && !ok; ++k) ok = both_sides(k);
+              if (k != slit_hint) ok = both_sides(k);
+          }
         }
       }
     }
