@@ -21,6 +21,15 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _device_f64(x, dev):
+    """Contiguous float64 CUDA tensor from a host array or a tensor of any layout (the C ABI takes dense row-major)."""
+    import torch
+
+    if torch.is_tensor(x):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.array(x, dtype=np.float64, order="C", copy=True)).to(dev)
+
+
 class LineTables:
     """FA + PEC tables of (element, ion_state, wavelength, transitions) on the device."""
 
@@ -89,9 +98,9 @@ class LineTables:
         K = len(prof)
         sorted_flag = int(np.all(np.diff(prof[:, 0]) >= 0))
         with torch.cuda.device(dev):
-            prof_d = torch.from_numpy(prof).to(dev)
-            reff_d = reff if torch.is_tensor(reff) else torch.from_numpy(np.ascontiguousarray(reff, dtype=np.float64)).to(dev)
-            w_d = w if torch.is_tensor(w) else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(dev)
+            prof_d = _device_f64(prof, dev)
+            reff_d = _device_f64(reff, dev)
+            w_d = _device_f64(w, dev)
             n = int(reff_d.numel())
             nt = len(self.transitions)
             flux = torch.zeros(nt + 1, dtype=torch.float64, device=dev)
@@ -121,10 +130,10 @@ class LineTables:
         prof[:, 0] = profile_reff
         sorted_flag = int(np.all(np.diff(prof[:, 0]) >= 0))
         with torch.cuda.device(dev):
-            prof_d = torch.from_numpy(prof).to(dev)
-            if reff is not None and not torch.is_tensor(reff):
-                reff = torch.from_numpy(np.ascontiguousarray(reff, dtype=np.float64)).to(dev)
-            w_d = w if torch.is_tensor(w) else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(dev)
+            prof_d = _device_f64(prof, dev)
+            if reff is not None:
+                reff = _device_f64(reff, dev)
+            w_d = _device_f64(w, dev)
             n = int(w_d.numel())
             hist = torch.zeros(K, dtype=torch.float64, device=dev)
             bnd = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -143,8 +152,7 @@ class LineTables:
 
         dev = hist.device
         with torch.cuda.device(dev):
-            prof_d = profiles if torch.is_tensor(profiles) else torch.from_numpy(
-                np.ascontiguousarray(profiles, dtype=np.float64)).to(dev)
+            prof_d = _device_f64(profiles, dev)  # (an np.stack of DataFrame.to_numpy() blocks is not C-ordered)
             n_slices, K = int(prof_d.shape[0]), int(prof_d.shape[1])
             if K != hist.numel():
                 raise ValueError("profiles and histogram disagree on the number of profile rows")

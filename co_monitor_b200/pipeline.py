@@ -56,7 +56,7 @@ class ChannelPipeline:
         import torch
 
         prof = np.ascontiguousarray(profile, dtype=np.float64)
-        self._profile = torch.from_numpy(prof.copy()).to(self.device)
+        self._profile = torch.from_numpy(np.array(prof, dtype=np.float64, order="C", copy=True)).to(self.device)
         self._K = len(prof)
         self._sorted = int(np.all(np.diff(prof[:, 0]) >= 0))
         self._pmax = float(prof[:, 0].max())

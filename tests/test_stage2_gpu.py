@@ -204,3 +204,29 @@ def test_host_buffer_emissivity_call(gold, reff10):
     mine = cols[valid.astype(bool)]
     order = np.argsort(obs[keep][valid.astype(bool), 0], kind="stable")
     np.testing.assert_allclose(mine[order], ref_rows[:, 6:], rtol=RTOL, atol=0)
+
+
+def test_sweep_accepts_any_tensor_layout(reff10):
+    """np.stack of DataFrame.to_numpy() blocks is not C-ordered; device tensors made from it must still be read right."""
+    import torch
+
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from oracle import stage2 as o2
+
+    obs = o2.read_observed_volume("O")
+    reff = reff10[obs[:, 0].astype(np.int64)]
+    keep = ~np.isnan(reff)
+    reff, w = reff[keep], obs[keep, 4]
+    tables = cached_line_tables("O", "Z7", 19.0, ("EXCIT", "RECOM"), None)
+    profs = np.stack([TwoGaussSumProfile(NE_SWEEP, list(TE_SWEEP_LO + (TE_SWEEP_HI - TE_SWEEP_LO) * (s / 19))).profiles_df[
+        ["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy() for s in range(20)])
+    assert not profs.flags["C_CONTIGUOUS"]
+    hist, _ = tables.weight_histogram(profs[0][:, 0], torch.from_numpy(reff).cuda(), torch.from_numpy(w).cuda())
+    a = tables.sweep(profs, hist, 0.02).cpu().numpy()
+    b = tables.sweep(torch.from_numpy(profs).cuda(), hist, 0.02).cpu().numpy()
+    assert np.array_equal(a, b)
+    for s in (0, 7, 19):
+        naive = tables.integrate(profs[s], 0.02, reff, w, per_voxel=False)["flux"]
+        np.testing.assert_allclose(a[s], naive, rtol=1e-11)
+    assert a[0, 2] != a[19, 2]
