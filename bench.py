@@ -298,8 +298,7 @@ def run_ours(args):
 
     # one CUDA graph of the whole step (every launch of the path is stream-ordered, nothing syncs with the host)
     graph = None
-    # N > 1: NCCL collectives inside a captured graph gain ~3 % here and make process-group teardown hang; not used
-    if world == 1 and not args.no_graph:
+    if not args.no_graph and (world == 1 or not args.no_graph_multi_gpu):
         try:
             graph = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=device)
@@ -420,9 +419,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_tests / float(t.item())
 
-    if rank != 0:
+    def teardown():
+        """Every rank leaves the same way: captured graph released first, then a barrier, then the process group."""
+        nonlocal graph, run_step
+        graph = run_step = None
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
 
     # ---- roofline of the dominant kernel (K1a FP32 filter) ----
@@ -489,9 +499,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": base,
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    teardown()
 
 
 def main():
@@ -502,6 +511,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph-multi-gpu", action="store_true",
+                    help="at N > 1 do not capture the step (NCCL all-reduces included) in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
