@@ -444,23 +444,36 @@ def run_ours(args):
     measured_peak = lib.com_measure_fp32_tflops()
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     peak = nominal_fp32_tflops(sm_max)
+    # Hardware-side figure next to the canonical one: lane-instructions actually executed per test, taken from the
+    # committed ncu capture of this kernel on this workload (profiles/r1_ncu_full_summary_k1a_after_queue.txt: warp instructions x
+    # active threads per instruction / 1.62e8 tests, mean of the four channels), against the issue peak
+    # 148 SM x 4 schedulers x 32 lanes x f_max.
+    LANE_INSTR_PER_TEST = 17.0
+    issue_peak = 148 * 4 * 32 * sm_max * 1e6
+    issue_frac = (tests_per_launch / (filter_ms * 1e-3)) * LANE_INSTR_PER_TEST / issue_peak if filter_ms > 0 else None
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if achieved else None, "traffic": None,
+        "frac": achieved / peak if achieved else None,
+        "traffic": 1.04e5,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/ "
+                        "(104 kB: geometry tables only; the lattice kernel reads no voxel data and writes 8 B per candidate via L2)",
         "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
                        f"register-only FMA probe measured {measured_peak:.1f} TFLOP/s on this GPU in this run",
         "measured_fp32_tflops": measured_peak,
-        "kernel": "com::filter_kernel (K1a)", "kernel_ms_per_launch": filter_ms, "exact_kernel_ms_per_launch": exact_ms,
+        "kernel": "com::filter_kernel_lattice (K1a)", "kernel_ms_per_launch": filter_ms, "exact_kernel_ms_per_launch": exact_ms,
         "kernel_share_of_step": (f_ms.value + x_ms.value) / seq_ms if seq_ms > 0 else None,
         "filter_kernel_share_of_step": f_ms.value / seq_ms if seq_ms > 0 else None,
         "sequential_ms_per_step": seq_ms / n_seq,
         "timing_pass": "kernel times and shares come from a separate pass of the same step on one stream without the "
                        "CUDA graph (the headline step overlaps the four channels on four streams)",
         "algorithmic_flop_per_test": FLOP_PER_TEST,
-        "executed_fp32_flop_per_test": 18 + 4,
-        "note": "achieved counts the canonical 247 FLOP/test of SURVEY.md 8(d); K1a's mirrored-detector formulation executes "
-                "9 FFMA + 4 ALU ops per test (about 22 FLOP), so the canonical fraction can exceed 1 - the issue-slot "
-                "utilisation in profiles/ is the hardware figure",
+        "executed_lane_instr_per_test": LANE_INSTR_PER_TEST,
+        "issue_frac": issue_frac,
+        "note": "`frac` uses the canonical 247 FLOP/test of SURVEY.md 8(d) as the contract asks; it exceeds 1 because the kernel does "
+                "not execute that arithmetic: mirroring the detector in the crystal makes the aperture coordinates linear "
+                "forms of the voxel position, advanced along z with 3 FADD per test (DESIGN.md section 4). The hardware "
+                "figure is `issue_frac`: executed lane-instructions per second over the issue peak (ncu: 78-80 % issue-slot "
+                "utilisation while the kernel runs).",
     }
 
     base = None
