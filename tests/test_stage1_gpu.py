@@ -205,3 +205,68 @@ def test_block_cyclic_shards_equal_the_unsharded_grid(sims):
         sub = sim.scene.visibility(lattice=sh, begin=1000, end=31000)
         assert np.array_equal(sub.nrays.cpu().numpy(), nr_full[g[1000:31000]])
     assert seen.all() and total_rays == PASSING_RAYS["C"]
+
+
+@pytest.mark.parametrize("el,spacing,h,l,slits,centre", [
+    ("O", 10, 20, 80, 10, 140000),   # class defaults of Simulation: 1600 crystal points (no golden file exists)
+    ("B", 15, 10, 10, 10, 40000),    # the reference's __main__ settings: 15 mm grid, 100 crystal points
+    ("N", 10, 30, 20, 4, 150000),    # fewer slits
+    ("C", 20, 7, 13, 10, 17000),     # odd crystal sampling: 91 points (padded warp)
+])
+def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre):
+    """Ray-exact agreement with the NumPy/Qhull oracle on slabs of configurations that have no shipped golden file,
+    with the FP32 filter on, and the same slab with the filter off (every ray through fp64)."""
+    import contextlib
+    import io
+
+    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from oracle import geometry_setup as gs
+    from oracle import stage1 as oracle
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        mesh = CuboidMesh(spacing)
+        scene = make_channel(el, slits, h, l, lattice=mesh.lattice)
+        brute = make_channel(el, slits, h, l, lattice=mesh.lattice, filter_eps_mm=1e30)
+    lat = mesh.lattice
+    full = scene.visibility(lattice=lat)
+    nr = full.nrays.cpu().numpy()
+    vis = np.flatnonzero(nr)
+    assert len(vis) > 0
+    # slab around the visible voxel nearest to `centre`
+    c = int(vis[np.argmin(np.abs(vis - centre))])
+    lo = max(0, c - 300)
+    hi = min(lat.n_points, lo + 600)
+    idx = np.arange(lo, hi)
+    osc = oracle.build_scene(el, slits, h, l)
+    ref = oracle.run_chunk(osc, gs.voxel_mesh(gs.load_db(), spacing, flat_indices=idx))
+    assert ref.nrays.sum() > 0
+    assert np.array_equal(nr[lo:hi], ref.nrays)
+    np.testing.assert_allclose(full.weight.cpu().numpy()[lo:hi], ref.weight, rtol=1e-12, atol=1e-300)
+    b = brute.visibility(lattice=lat, begin=lo, end=hi)
+    assert np.array_equal(b.nrays.cpu().numpy(), ref.nrays)
+    assert b.stats["candidates"] == (hi - lo) * h * l
+    scene.close()
+    brute.close()
+
+
+@pytest.mark.parametrize("el", list("BNO"))
+def test_filter_is_conservative_other_channels(sims, el):
+    """Filter on vs off on 20 000 voxels per channel: identical per-voxel ray counts."""
+    import contextlib
+    import io
+
+    import torch
+
+    from co_monitor_b200.geometry.engine import make_channel
+
+    sim = sims(el)
+    lat = sim.mesh.lattice
+    with contextlib.redirect_stdout(io.StringIO()):
+        brute = make_channel(el, 10, 30, 20, lattice=lat, filter_eps_mm=1e30)
+    lo, hi = 125000, 145000
+    a = sim.scene.visibility(lattice=lat, begin=lo, end=hi)
+    b = brute.visibility(lattice=lat, begin=lo, end=hi)
+    assert a.stats["passing_rays"] == b.stats["passing_rays"] > 0
+    assert torch.equal(a.nrays, b.nrays)
+    brute.close()
