@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -290,6 +291,76 @@ __global__ void __launch_bounds__(kK2Threads) weight_histogram_kernel(const K2Pa
   if (blockIdx.x == 0 && threadIdx.x == 0) P.scratch[1] = boundary;
 }
 
+// Fast voxel pass for uint16 millimetre bins (the form large grids keep their Reff in): every voxel is read once,
+// 10 B/voxel, with 16-byte vector loads; no search in the hot loop - the weights are binned by the raw millimetre
+// value in shared memory and the boundary cut and the bin -> profile-row mapping are applied afterwards on the
+// <= 4096-bin histogram (histogram_rows_kernel).  Only voxels with w != 0 count: they are the visible ones
+// (every passing ray adds a strictly positive weight), which is the set the reference takes the maximum over.
+constexpr int kMmBins = 4096;
+
+__device__ __forceinline__ void bin_one(double* s_h, unsigned int b, double w) {
+  if (w != 0.0 && b != 0xFFFFu) atomicAdd(&s_h[min(b, (unsigned int)(kMmBins - 1))], w);
+}
+
+__global__ void __launch_bounds__(kK2Threads) weight_histogram_mm_kernel(const uint16_t* __restrict__ reff_mm,
+                                                                       const double* __restrict__ w, long long n_max,
+                                                                       const unsigned long long* n_device,
+                                                                       double* __restrict__ hist_mm) {
+  __shared__ double s_h[kMmBins];
+  for (int k = threadIdx.x; k < kMmBins; k += kK2Threads) s_h[k] = 0.0;
+  __syncthreads();
+  const long long n = n_device ? (long long)min((unsigned long long)n_max, *n_device) : n_max;
+  const long long n8 = n >> 3;
+  const uint4* r4 = reinterpret_cast<const uint4*>(reff_mm);
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  const long long stride = (long long)gridDim.x * kK2Threads;
+  for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < n8; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool second = j < n8;
+    // all loads of the two 8-voxel groups are issued before any is consumed
+    const uint4 ra = __ldcs(r4 + i);
+    const double2 a0 = __ldcs(w2 + 4 * i), a1 = __ldcs(w2 + 4 * i + 1), a2 = __ldcs(w2 + 4 * i + 2), a3 = __ldcs(w2 + 4 * i + 3);
+    uint4 rb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    double2 b0 = make_double2(0, 0), b1 = b0, b2 = b0, b3 = b0;
+    if (second) {
+      rb = __ldcs(r4 + j);
+      b0 = __ldcs(w2 + 4 * j), b1 = __ldcs(w2 + 4 * j + 1), b2 = __ldcs(w2 + 4 * j + 2), b3 = __ldcs(w2 + 4 * j + 3);
+    }
+    bin_one(s_h, ra.x & 0xFFFFu, a0.x), bin_one(s_h, ra.x >> 16, a0.y);
+    bin_one(s_h, ra.y & 0xFFFFu, a1.x), bin_one(s_h, ra.y >> 16, a1.y);
+    bin_one(s_h, ra.z & 0xFFFFu, a2.x), bin_one(s_h, ra.z >> 16, a2.y);
+    bin_one(s_h, ra.w & 0xFFFFu, a3.x), bin_one(s_h, ra.w >> 16, a3.y);
+    bin_one(s_h, rb.x & 0xFFFFu, b0.x), bin_one(s_h, rb.x >> 16, b0.y);
+    bin_one(s_h, rb.y & 0xFFFFu, b1.x), bin_one(s_h, rb.y >> 16, b1.y);
+    bin_one(s_h, rb.z & 0xFFFFu, b2.x), bin_one(s_h, rb.z >> 16, b2.y);
+    bin_one(s_h, rb.w & 0xFFFFu, b3.x), bin_one(s_h, rb.w >> 16, b3.y);
+  }
+  if (blockIdx.x == 0)  // the < 8 voxels left over
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += kK2Threads) bin_one(s_h, reff_mm[i], w[i]);
+  __syncthreads();
+  for (int k = threadIdx.x; k < kMmBins; k += kK2Threads)
+    if (s_h[k] != 0.0) atomicAdd(&hist_mm[k], s_h[k]);
+}
+
+// Boundary cut and millimetre bin -> profile row on the small histogram (one block).
+__global__ void __launch_bounds__(kK2Threads) histogram_rows_kernel(const K2Params P, const double* __restrict__ hist_mm) {
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = -1;
+  __syncthreads();
+  int m = -1;
+  for (int b = threadIdx.x; b < kMmBins; b += kK2Threads)
+    if (hist_mm[b] != 0.0) m = b;
+  atomicMax(&s_max, m);
+  __syncthreads();
+  const double mapped = P.mapped_max ? *P.mapped_max : (s_max >= 0 ? (double)s_max / 1000.0 : 0.0);
+  const double boundary = fmin(mapped, P.profile_reff_max);
+  for (int b = threadIdx.x; b < kMmBins; b += kK2Threads) {
+    const double h = hist_mm[b], reff = (double)b / 1000.0;
+    if (h != 0.0 && !(reff >= boundary)) atomicAdd(&P.hist_out[profile_row(P, reff)], h);
+  }
+  if (threadIdx.x == 0) P.scratch[0] = mapped, P.scratch[1] = boundary;
+}
+
 struct SweepParams {
   DevTables tab;
   const double* profiles;  // (n_slices, K, 3)
@@ -447,7 +518,8 @@ int com_tables_destroy(ComTables* t) {
 
 size_t com_emissivity_workspace_bytes(int64_t n) {
   long long blocks = std::min<long long>(std::max<long long>(1, (n + com::kK2Threads - 1) / com::kK2Threads), 148 * 8);  // upper bound of any launch below
-  return 256 + align_up(sizeof(double) * (8 + (size_t)blocks * (com::kMaxTransitions + 1)), 256);
+  return 256 + align_up(sizeof(double) * (8 + (size_t)blocks * (com::kMaxTransitions + 1)), 256) +
+         sizeof(double) * com::kMmBins;  // + the millimetre-bin histogram of the fast voxel pass
 }
 
 static int fill_params(com::K2Params& P, const ComTables* tables, const double* profile, int32_t K, int32_t sorted,
@@ -514,7 +586,17 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256 + 64, s));
   COM_CUDA(cudaMemsetAsync(hist_out, 0, sizeof(double) * K, s));
-  if (n > 0) {
+  if (n > 0 && reff_mm && !reff && !reff_index && (reinterpret_cast<uintptr_t>(reff_mm) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    // fast path: one 10 B/voxel pass binned by millimetre, then the cut and row mapping on 4096 bins
+    double* hist_mm = reinterpret_cast<double*>(static_cast<char*>(workspace) + workspace_bytes - sizeof(double) * com::kMmBins);
+    COM_CUDA(cudaMemsetAsync(hist_mm, 0, sizeof(double) * com::kMmBins, s));
+    const int blocks = (int)std::min<long long>((n / 8 + com::kK2Threads - 1) / com::kK2Threads + 1, 148 * 6);
+    com::weight_histogram_mm_kernel<<<blocks, com::kK2Threads, 0, s>>>(
+        reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm);
+    com::histogram_rows_kernel<<<1, com::kK2Threads, 0, s>>>(P, hist_mm);
+    COM_CUDA(cudaGetLastError());
+  } else if (n > 0) {
     const size_t smem = sizeof(double) * K;
     static bool attr_set = false;
     if (!attr_set) {

@@ -230,3 +230,30 @@ def test_sweep_accepts_any_tensor_layout(reff10):
         naive = tables.integrate(profs[s], 0.02, reff, w, per_voxel=False)["flux"]
         np.testing.assert_allclose(a[s], naive, rtol=1e-11)
     assert a[0, 2] != a[19, 2]
+
+
+def test_millimetre_bin_histogram_fast_path():
+    """uint16-millimetre Reff bins (fast 10 B/voxel pass) against the fp64-Reff path and a NumPy histogram:
+    odd length (scalar tail), 0xFFFF = outside the LCFS, zero weights = invisible voxels, values beyond the cut."""
+    import torch
+
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+
+    rng = np.random.default_rng(5)
+    n = 200_003
+    mm = rng.integers(0, 700, n).astype(np.uint16)
+    mm[rng.random(n) < 0.3] = 0xFFFF
+    w = rng.random(n) * 1e-6
+    w[rng.random(n) < 0.8] = 0.0
+    reff = np.where(mm == 0xFFFF, np.nan, mm / 1000.0)
+    prof_reff = np.arange(0, 0.539, 0.001)
+    tables = cached_line_tables("C", "Z5", 33.7, ("EXCIT", "RECOM"), None)
+    mm_d = torch.from_numpy(mm.view(np.int16)).cuda()
+    fast, b_fast = tables.weight_histogram(prof_reff, None, w, reff_mm=mm_d)
+    vis = w != 0  # the fp64 path takes the maximum over every voxel it is given: give it the visible ones, like the pipeline
+    slow, b_slow = tables.weight_histogram(prof_reff, reff[vis], w[vis])
+    assert b_fast == b_slow == 0.538
+    np.testing.assert_allclose(fast.cpu().numpy(), slow.cpu().numpy(), rtol=1e-12, atol=1e-300)
+    keep = vis & (mm != 0xFFFF) & (mm / 1000.0 < b_fast)
+    ref = np.bincount(mm[keep].astype(np.int64), weights=w[keep], minlength=539)[:539]
+    np.testing.assert_allclose(fast.cpu().numpy(), ref, rtol=1e-12, atol=1e-300)
