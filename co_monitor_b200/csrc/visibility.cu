@@ -25,7 +25,7 @@ namespace com {
 constexpr int kTileVoxels = 512;       // voxels per work item, explicit-voxel kernel
 constexpr int kSegmentMax = 64;        // longest run of z-consecutive voxels advanced by forward differences
 constexpr int kMaxWarps = 16;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;
 constexpr int kQueueCap = 32 * kUnroll + 32;
 
 struct VoxelSource {
