@@ -31,16 +31,17 @@ void kernel_timing_read(double*, double*, long long*);
 
 namespace com {
 namespace {
-std::mutex g_arena_mu;
-char* g_arena_dev = nullptr;
-size_t g_arena_dev_cap = 0;
-int g_arena_device = -1;
-char* g_arena_pinned = nullptr;
-size_t g_arena_pinned_cap = 0;
+// One arena per host thread: the *_host entry points may be called concurrently from several threads (one channel
+// per thread), each on its own per-thread CUDA stream.
+thread_local char* g_arena_dev = nullptr;
+thread_local size_t g_arena_dev_cap = 0;
+thread_local int g_arena_device = -1;
+thread_local char* g_arena_pinned = nullptr;
+thread_local size_t g_arena_pinned_cap = 0;
 }  // namespace
 
-void HostArena::lock() { g_arena_mu.lock(); }
-void HostArena::unlock() { g_arena_mu.unlock(); }
+void HostArena::lock() {}
+void HostArena::unlock() {}
 
 void HostArena::release_all() {
   if (g_arena_dev) cudaFree(g_arena_dev);
@@ -356,7 +357,7 @@ static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* la
   void* d_cws = take(align_up(cws_bytes, 256));
   void* d_ws = take(ws_bytes);
 
-  cudaStream_t s = nullptr;  // legacy default stream: ordered with everything else the caller did
+  cudaStream_t s = cudaStreamPerThread;  // concurrent host threads overlap on the device
   std::memcpy(pin, blob.bytes.data(), blob.bytes.size());
   COM_CUDA(cudaMemcpyAsync(d_scene, pin, blob.bytes.size(), cudaMemcpyHostToDevice, s));
   bind_scene(scene.dev, d_scene, blob);

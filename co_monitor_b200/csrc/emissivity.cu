@@ -677,7 +677,7 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
   std::memcpy(pin + b_tab, profile_h, sizeof(double) * 3 * K);
   std::memcpy(pin + b_tab + b_prof, reff_h, sizeof(double) * (size_t)n);
   std::memcpy(pin + b_tab + b_prof + b_n, w_h, sizeof(double) * (size_t)n);
-  cudaStream_t s = nullptr;
+  cudaStream_t s = cudaStreamPerThread;
   COM_CUDA(cudaMemcpyAsync(d, pin, up, cudaMemcpyHostToDevice, s));
   bind_tables(T.dev, d);
   double* d_prof = reinterpret_cast<double*>(d + b_tab);

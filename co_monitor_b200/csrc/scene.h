@@ -64,9 +64,10 @@ int build_host_scene(const ComSceneDesc& d, HostScene& out);
 
 void set_error(const char* fmt, ...);
 
-// Grow-only device block + pinned staging block shared by the synchronous *_host entry points, so that a
-// reference-facing call does not pay cudaMalloc/cudaFree (both synchronise the device) every time.
-// lock() serialises the host entry points; reserve() returns COM_OK or COM_E_*.
+// Grow-only device block + pinned staging block kept per host thread by the synchronous *_host entry points, so that a
+// reference-facing call does not pay cudaMalloc/cudaFree (both synchronise the device) every time.  Each thread
+// works on its own per-thread CUDA stream, so calls from different threads overlap on the device.
+// reserve() returns COM_OK or COM_E_*.
 struct HostArena {
   static void lock();
   static void unlock();

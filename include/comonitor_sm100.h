@@ -200,8 +200,9 @@ int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* latti
                              int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
                              int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h);
 
-/* The *_host calls keep one grow-only device block and one pinned staging block between calls (cudaMalloc and
- * cudaFree synchronise the device); this frees them. */
+/* The *_host calls keep one grow-only device block and one pinned staging block per calling thread between calls
+ * (cudaMalloc and cudaFree synchronise the device) and run on the per-thread CUDA stream: they may be called
+ * concurrently from several host threads (e.g. one channel per thread).  This frees the calling thread's blocks. */
 int com_host_arena_release(void);
 
 /* Compaction of the visible voxels (nrays > 0), ascending flat index: idx_out[i] = vox_begin + position,
