@@ -280,6 +280,18 @@ int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* ou
   return COM_OK;
 }
 
+int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, int32_t ny, double pixel_mm, double x0_mm,
+                                 double y0_mm) {
+  if (!scene || (pix_out && (nx < 1 || ny < 1 || !(pixel_mm > 0)))) {
+    com::set_error("com_scene_set_detector_image: bad arguments");
+    return COM_E_BADARG;
+  }
+  scene->dev.pix_out = pix_out;
+  scene->dev.pix_nx = nx, scene->dev.pix_ny = ny;
+  scene->dev.pix_mm = pixel_mm, scene->dev.pix_x0 = x0_mm, scene->dev.pix_y0 = y0_mm;
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

@@ -45,6 +45,11 @@ struct DeviceScene {
   const double* edges;           // (n_edges_total,3)
   // FP32 filter tables: linear forms in the recentred voxel position p' = p - origin, value = g.p' + h
   const float4* det_forms;       // [3][Cp]: Xs, Ys, W of the mirrored detector; passes iff max(|Xs|,|Ys|) <= |W|
+  // optional detector image (extension, off unless com_scene_set_detector_image was called): weight of every passing
+  // ray accumulated into the pixel its detector hit falls in, pixels of pix_mm in the detector aperture frame (e1, e2)
+  double* pix_out;
+  int pix_nx, pix_ny;
+  double pix_mm, pix_x0, pix_y0;
   const float4* slit_forms;      // [Cp][6]: X', Y', W on the crystal-side slit plane, then on the plasma side
 };
 

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
 struct HitResult {
   bool pass;
   double margin;
-  double x;  // in-plane coordinate along e1 (used to pick the slit)
+  double x, y;  // in-plane coordinates along e1, e2 (x picks the slit; both address the detector image)
 };
 
 // simulation.py:143-173 (+175-207): line through `dst` with direction src - dst against the aperture plane,
@@ -439,7 +439,7 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
                                                   D3 dst) {
   const D3 N = ld3(ap.normal), u = src - dst;
   const double ndotu = dot(N, u);
-  if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0};  // the reference writes NaN -> never inside
+  if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0, 0.0};  // the reference writes NaN -> never inside
   const D3 w = dst - ld3(ap.p1);
   const double si = -(dot(N, w) / ndotu);
   const D3 r = w + si * u;  // X - p1
@@ -447,7 +447,7 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
   double m = 1e300;
   const double* e = edges + 3 * ap.edge_offset;
   for (int k = 0; k < ap.n_edges; ++k) m = fmin(m, e[3 * k] * x + e[3 * k + 1] * y + e[3 * k + 2]);
-  return {m >= 0.0, m, x};
+  return {m >= 0.0, m, x, y};
 }
 
 constexpr int kExactThreads = 256;
@@ -563,6 +563,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
       if (P.hist_out) {
         const int bin = P.reff_bin[P.vox_begin + vloc];
         if (bin < P.n_bins) atomicAdd(&P.hist_out[bin], w);
+      }
+      if (sc.pix_out) {  // h still holds the detector hit
+        const int px = min(max((int)floor((h.x - sc.pix_x0) / sc.pix_mm), 0), sc.pix_nx - 1);
+        const int py = min(max((int)floor((h.y - sc.pix_y0) / sc.pix_mm), 0), sc.pix_ny - 1);
+        atomicAdd(&sc.pix_out[(size_t)py * sc.pix_nx + px], w);
       }
       if (P.rays_out) {
         const unsigned long long pos = atomicAdd(P.rays_count, 1ull);

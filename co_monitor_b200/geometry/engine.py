@@ -140,6 +140,29 @@ class ChannelScene:
         return dict(slit_filter=bool(sf.value), filter_disabled=bool(fd.value), slit_period_mm=period.value,
                     eps_mm=eps.value)
 
+    def enable_detector_image(self, pixel_mm: float = 0.1, nx: int | None = None, ny: int | None = None, device=None):
+        """Extension: accumulate every passing ray's weight into a detector image (see com_scene_set_detector_image).
+
+        Returns the CUDA float64 tensor ``(ny, nx)``; it keeps accumulating over launches until zeroed by the caller.
+        Default extent: the bounding box of the detector polygon in its own frame.
+        """
+        import torch
+
+        det = self.aperture(2 * self.n_slits + 1)
+        v = det.vertices()
+        if nx is None:
+            nx = int(np.ceil(v[:, 0].max() / pixel_mm))
+        if ny is None:
+            ny = int(np.ceil(v[:, 1].max() / pixel_mm))
+        self.detector_image = torch.zeros((ny, nx), dtype=torch.float64, device=torch.device(device or "cuda"))
+        _lib.check(self._lib.com_scene_set_detector_image(self.handle, C.c_void_p(self.detector_image.data_ptr()), nx, ny,
+                                                          float(pixel_mm), 0.0, 0.0), "com_scene_set_detector_image")
+        return self.detector_image
+
+    def disable_detector_image(self):
+        _lib.check(self._lib.com_scene_set_detector_image(self.handle, None, 0, 0, 0.0, 0.0, 0.0), "com_scene_set_detector_image")
+        self.detector_image = None
+
     def aperture(self, index: int) -> _lib.ComAperture:
         ap = _lib.ComAperture()
         _lib.check(self._lib.com_scene_get_aperture(self.handle, index, C.byref(ap)), "com_scene_get_aperture")

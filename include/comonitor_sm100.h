@@ -115,6 +115,14 @@ int com_scene_destroy(ComScene* scene);
 /* number of apertures (2S+2, order: crys_0, plasma_0, crys_1, ..., port, detector) and a host copy of one */
 int com_scene_aperture_count(const ComScene* scene);
 int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* out_h);
+/* Extension (not in the reference; SURVEY.md 8(d) config 3 "per-pixel detector resolution"): while pix_out != NULL every
+ * com_visibility_weights call on this scene also accumulates each passing ray's weight into a detector image,
+ * pix_out[py*nx + px] (DEVICE, nx*ny fp64, never cleared by the library), where (x, y) is the ray's hit on the detector
+ * plane in the detector aperture's frame (origin = first detector vertex, e1 along vertex 1 -> 2), px = floor((x - x0)/
+ * pixel), py = floor((y - y0)/pixel), clamped to the image, so that sum(image) == sum(weights).  NULL switches it off. */
+int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, int32_t ny, double pixel_mm, double x0_mm,
+                                 double y0_mm);
+
 /* what the FP32 filter was built with (any output pointer may be NULL): whether the collimator was found periodic
  * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled,

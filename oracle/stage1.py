@@ -126,6 +126,24 @@ def ray_weights(scene, plasma, crystal, reflected):
     return dist, aoi, fraction * reflect_prof
 
 
+def detector_image(scene, plasma, crystal, reflected, sel, w_ray, nx, ny, pixel_mm):
+    """Extension oracle: 2-D histogram of the detector-plane hit points of the passing rays
+    (simulation.py:387-390 gives the hit), in the frame origin = detector vertex 1, e1 along vertex 1 -> 2,
+    e2 = n x e1, weight-accumulated; hits are clamped to the image."""
+    dv = scene.det_v
+    X = plane_hit(dv[0], dv[1], dv[2], reflected, crystal)[sel]
+    normal = np.cross(dv[1] - dv[0], dv[2] - dv[1])
+    nh = normal / np.linalg.norm(normal)
+    e1 = (dv[1] - dv[0]) / np.linalg.norm(dv[1] - dv[0])
+    e2 = np.cross(nh, e1)
+    x, y = (X - dv[0]) @ e1, (X - dv[0]) @ e2
+    px = np.clip(np.floor(x / pixel_mm).astype(int), 0, nx - 1)
+    py = np.clip(np.floor(y / pixel_mm).astype(int), 0, ny - 1)
+    img = np.zeros((ny, nx))
+    np.add.at(img, (py, px), w_ray[sel])
+    return img
+
+
 def run_chunk(scene, voxels, want_rays=False):
     """Stage 1 on a chunk of voxels.  Returns per-voxel weight, per-voxel passing-ray count and,
     optionally, the (n, C) mask with per-ray distance / AOI."""
@@ -136,6 +154,7 @@ def run_chunk(scene, voxels, want_rays=False):
     out = SimpleNamespace(weight=w_vox, nrays=sel.sum(axis=1).astype(np.int64))
     if want_rays:
         out.mask, out.dist, out.aoi, out.w_ray = sel, dist, aoi, w
+        out.geometry = (plasma, crystal, reflected)
     return out
 
 

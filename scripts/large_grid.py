@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--l", type=int, default=20)
     ap.add_argument("--slits", type=int, default=10)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--image", action="store_true", help="also accumulate the 0.1 mm detector image (config 3 extension)")
     a = ap.parse_args()
     with contextlib.redirect_stdout(io.StringIO()):
         lat = CuboidMesh(a.spacing).lattice
@@ -42,7 +43,10 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             scene = make_channel(el, a.slits, a.h, a.l, lattice=lat)
         best = None
+        img = scene.enable_detector_image(0.1) if a.image else None
         for _ in range(a.repeat):
+            if img is not None:
+                img.zero_()
             sum_w, vis, rays, cand, near, ms_total, chunks = 0.0, 0, 0, 0, 0, 0.0, []
             for lo in range(0, P, a.chunk):
                 hi = min(P, lo + a.chunk)
@@ -69,6 +73,10 @@ def main():
                    "ms": ms_total, "tests_per_s": tests / (ms_total * 1e-3), "visible_voxels": vis, "passing_rays": rays,
                    "fp64_candidates": cand, "near_edge_rays": near, "sum_w": sum_w,
                    "sum_w_times_voxel_volume_mm3": sum_w * a.spacing**3, "chunk_ms": chunks}
+            if img is not None:
+                rec["detector_image"] = {"shape": list(img.shape), "pixel_mm": 0.1, "sum": float(img.sum().item()),
+                                         "max_pixel": float(img.max().item()),
+                                         "lit_pixels": int((img > 0).sum().item())}
             if best is None or rec["ms"] < best["ms"]:
                 best = rec
         print(json.dumps(best))

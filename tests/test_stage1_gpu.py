@@ -270,3 +270,58 @@ def test_filter_is_conservative_other_channels(sims, el):
     assert a.stats["passing_rays"] == b.stats["passing_rays"] > 0
     assert torch.equal(a.nrays, b.nrays)
     brute.close()
+
+
+def test_fused_reff_bin_histogram(sims):
+    """K1b can accumulate the weights straight into a Reff-bin histogram (no per-voxel pass afterwards):
+    hist[bin[v]] += w_ray.  Checked against a bincount of the per-voxel weights; bins >= n_bins are skipped."""
+    import torch
+
+    sim = sims("N")
+    lat = sim.mesh.lattice
+    rng = np.random.default_rng(11)
+    bins = rng.integers(0, 600, lat.n_points).astype(np.uint16)
+    bins[rng.random(lat.n_points) < 0.3] = 0xFFFF
+    bins_d = torch.from_numpy(bins.view(np.int16)).cuda()
+    hist = torch.zeros(540, dtype=torch.float64, device="cuda")
+    lo, hi = 60000, 250000
+    res = sim.scene.visibility(lattice=lat, begin=lo, end=hi, reff_bin=bins_d, hist=hist)
+    w = res.weight.cpu().numpy()
+    b = bins[lo:hi].astype(np.int64)
+    keep = b < 540
+    ref = np.bincount(b[keep], weights=w[keep], minlength=540)
+    np.testing.assert_allclose(hist.cpu().numpy(), ref, rtol=1e-11, atol=1e-300)
+    assert ref.sum() > 0
+
+
+def test_detector_image_extension(sims):
+    """Per-pixel detector image (config 3 extension): weight-conserving, and equal to the oracle's histogram of the
+    detector hit points on a slab (a ray exactly on a pixel boundary may fall on either side: L1 tolerance)."""
+    from oracle import geometry_setup as gs
+    from oracle import stage1 as oracle
+
+    sim = sims("O")
+    lat = sim.mesh.lattice
+    img = sim.scene.enable_detector_image(pixel_mm=0.1)
+    ny, nx = img.shape
+    assert (nx, ny) in ((266, 67), (267, 68), (267, 67), (266, 68))
+    lo, hi = 131000, 132000
+    res = sim.scene.visibility(lattice=lat, begin=lo, end=hi)
+    got = img.cpu().numpy().copy()
+    assert abs(got.sum() / float(res.weight.sum().item()) - 1) < 1e-12
+    osc = oracle.build_scene("O", 10, 30, 20)
+    ref = oracle.run_chunk(osc, gs.voxel_mesh(gs.load_db(), 10, flat_indices=np.arange(lo, hi)), want_rays=True)
+    plasma, crystal, reflected = ref.geometry
+    want = oracle.detector_image(osc, plasma, crystal, reflected, ref.mask, ref.w_ray, nx, ny, 0.1)
+    assert want.sum() > 0
+    assert np.abs(got - want).sum() <= 1e-5 * want.sum()
+    same = np.isclose(got, want, rtol=1e-10, atol=1e-300)
+    assert same.mean() > 0.999
+    # the whole grid: total weight conserved, image confined to the detector
+    img.zero_()
+    full = sim.scene.visibility(lattice=lat)
+    assert abs(float(img.sum().item()) / float(full.weight.sum().item()) - 1) < 1e-12
+    sim.scene.disable_detector_image()
+    again = sim.scene.visibility(lattice=lat, begin=lo, end=hi)
+    assert float(img.sum().item()) == float(img.sum().item())  # untouched after disabling
+    assert again.stats["passing_rays"] == res.stats["passing_rays"]
