@@ -163,6 +163,7 @@ def _declare(lib):
     lib.com_scene_aperture_count.argtypes = [vp]
     lib.com_scene_get_aperture.argtypes = [vp, i32, C.POINTER(ComAperture)]
     lib.com_scene_set_detector_image.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, C.c_double]
+    lib.com_scene_filter_tables_host.argtypes = [C.POINTER(ComSceneDesc), C.POINTER(i32), vp, vp, vp, vp, vp]
     lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), dp, dp]
     lib.com_visibility_workspace_bytes.restype = C.c_size_t
     lib.com_visibility_workspace_bytes.argtypes = [vp, i64, C.c_double]
@@ -200,7 +201,7 @@ EXPORTED_SYMBOLS = [
     "com_abi_version", "com_last_error", "com_error_string",
     "com_aperture_from_slab", "com_aperture_contains",
     "com_scene_create", "com_scene_destroy", "com_scene_aperture_count", "com_scene_get_aperture",
-    "com_scene_filter_info", "com_lattice_local_voxels", "com_scene_set_detector_image",
+    "com_scene_filter_info", "com_lattice_local_voxels", "com_scene_set_detector_image", "com_scene_filter_tables_host",
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
     "com_visible_weights_host", "com_host_arena_release",
     "com_compact_workspace_bytes", "com_compact_visible",

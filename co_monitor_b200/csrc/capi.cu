@@ -292,6 +292,27 @@ int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, i
   return COM_OK;
 }
 
+int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_padded, float* det_forms_out,
+                                 float* slit_forms_out, float* rects_out, float* period_out, int32_t* flags_out) {
+  if (!desc_h || !n_crystal_padded) {
+    com::set_error("com_scene_filter_tables_host: null argument");
+    return COM_E_BADARG;
+  }
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  *n_crystal_padded = hs.dev.n_crystal_padded;
+  if (det_forms_out) std::memcpy(det_forms_out, hs.det_forms.data(), hs.det_forms.size() * sizeof(float));
+  if (slit_forms_out) std::memcpy(slit_forms_out, hs.slit_forms.data(), hs.slit_forms.size() * sizeof(float));
+  if (rects_out) {
+    const com::SlitRect r[2] = {hs.dev.rect_crys, hs.dev.rect_plasma};
+    std::memcpy(rects_out, r, sizeof(r));
+  }
+  if (period_out) *period_out = hs.dev.slit_period;
+  if (flags_out) flags_out[0] = hs.dev.slit_filter, flags_out[1] = hs.dev.slit_same_w, flags_out[2] = hs.dev.filter_disabled;
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

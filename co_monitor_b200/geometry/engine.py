@@ -65,7 +65,7 @@ class ChannelScene:
     def __init__(self, crystal_points, normals, slit_crys, slit_plasma, vector_front_back, port_vertices,
                  port_ov, det_vertices, det_ov, origin, area_pt, refl_max, aoi0, refl_sigma=2.2,
                  voxel_corners=None, filter_eps_mm=DEFAULT_FILTER_EPS_MM, calibrate_apertures=True,
-                 near_edge_mm=0.0):
+                 near_edge_mm=0.0, host_only=False):
         self._lib = _lib.load()
         self._keep = {}
 
@@ -111,7 +111,26 @@ class ChannelScene:
         self.n_crystal = d.n_crystal
         self.n_slits = d.n_slits
         self.handle = C.c_void_p()
-        _lib.check(self._lib.com_scene_create(C.byref(d), C.byref(self.handle)), "com_scene_create")
+        if not host_only:  # host_only: description + host-side analysis only (CPU tests of the filter tables)
+            _lib.check(self._lib.com_scene_create(C.byref(d), C.byref(self.handle)), "com_scene_create")
+
+    def filter_tables(self) -> dict:
+        """The FP32 filter tables as NumPy arrays (host-only call, no GPU needed)."""
+        cp = C.c_int32()
+        _lib.check(self._lib.com_scene_filter_tables_host(C.byref(self.desc), C.byref(cp), None, None, None, None, None),
+                   "com_scene_filter_tables_host")
+        Cp = cp.value
+        det = np.zeros((3, Cp, 4), np.float32)
+        slit = np.zeros((Cp, 6, 4), np.float32)
+        rects = np.zeros(8, np.float32)
+        period = C.c_float()
+        flags = (C.c_int32 * 3)()
+        _lib.check(self._lib.com_scene_filter_tables_host(
+            C.byref(self.desc), C.byref(cp), C.c_void_p(det.ctypes.data), C.c_void_p(slit.ctypes.data),
+            C.c_void_p(rects.ctypes.data), C.byref(period), flags), "com_scene_filter_tables_host")
+        return dict(det_forms=det, slit_forms=slit, rect_crys=rects[:4], rect_plasma=rects[4:], period=period.value,
+                    slit_filter=bool(flags[0]), same_w=bool(flags[1]), disabled=bool(flags[2]),
+                    origin=np.array(list(self.desc.origin)))
 
     # -- lifetime ----------------------------------------------------------------------
     def close(self):

@@ -123,6 +123,15 @@ int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* ou
 int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, int32_t ny, double pixel_mm, double x0_mm,
                                  double y0_mm);
 
+/* Host-only (no CUDA): the FP32 filter tables com_scene_create would upload, for inspection and CPU-side tests.
+ *   det_forms_out  [3][Cp][4] floats: forms Xs, Ys, W of the mirrored detector, value = g.p' + h with p' = p - origin
+ *   slit_forms_out [Cp][6][4] floats: X', Y', W on the crystal-side slit plane, then on the plasma side
+ *   rects_out      8 floats: xlo, xhi, ylo, yhi of the crystal-side and of the plasma-side slit rectangle (band included)
+ *   flags_out      3 ints: collimator periodic (stage B active), both sides share W, filter disabled
+ * Any output pointer may be NULL; *n_crystal_padded (Cp) is always written - call once with NULLs to size the buffers. */
+int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_padded, float* det_forms_out,
+                                 float* slit_forms_out, float* rects_out, float* period_out, int32_t* flags_out);
+
 /* what the FP32 filter was built with (any output pointer may be NULL): whether the collimator was found periodic
  * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled,

@@ -1,0 +1,94 @@
+"""CPU-side check of the FP32 filter (K1a) without a GPU: the filter tables come from the library's host-only entry
+point, stages A and B are emulated in NumPy float32 - direct evaluation of the linear forms and forward differences
+along z as the lattice kernel advances them - and every ray the fp64 oracle accepts must survive both stages."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from co_monitor_b200.geometry.engine import make_channel
+from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+from oracle import geometry_setup as gs
+from oracle import stage1 as oracle
+
+
+def forms(tab, p):
+    """value[c, v] = g[c].p[v] + h[c] in float32 (tab: (C,4), p: (V,3))."""
+    g, h = tab[:, :3].astype(np.float32), tab[:, 3].astype(np.float32)
+    return (g[:, None, 0] * p[None, :, 0] + g[:, None, 1] * p[None, :, 1] + g[:, None, 2] * p[None, :, 2] + h[:, None]).astype(np.float32)
+
+
+def stage_a(t, p):
+    xs, ys, w = (forms(t["det_forms"][i], p) for i in range(3))
+    return np.abs(w) - np.maximum(np.abs(xs), np.abs(ys)) >= 0
+
+
+def stage_b(t, p, n_slits):
+    s = t["slit_forms"]
+    Xc, Yc, Wc, Xp, Yp = (forms(s[:, i], p) for i in range(5))
+    Wp = Wc if t["same_w"] else forms(s[:, 5], p)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xc, yc, xp, yp = Xc / Wc, Yc / Wc, Xp / Wp, Yp / Wp
+    rc, rp = t["rect_crys"], t["rect_plasma"]
+    y_ok = (yc >= rc[2]) & (yc <= rc[3]) & (yp >= rp[2]) & (yp <= rp[3])
+    kf = np.floor(xc / np.float32(t["period"]))
+    ok = np.zeros(xc.shape, bool)
+    for dk in (0, 1):
+        k = kf + dk
+        a, b = xc - k * np.float32(t["period"]), xp - k * np.float32(t["period"])
+        ok |= (k >= 0) & (k < n_slits) & (a >= rc[0]) & (a <= rc[1]) & (b >= rp[0]) & (b <= rp[1])
+    grazing = np.minimum(np.abs(Wc), np.abs(Wp)) < 1e-3
+    return (ok & y_ok) | grazing
+
+
+@pytest.mark.parametrize("el,spacing,h,l,lo", [("C", 10, 30, 20, 131000), ("N", 10, 30, 20, 140000), ("O", 15, 10, 10, 40000)])
+def test_filter_never_rejects_a_ray_the_oracle_accepts(el, spacing, h, l, lo):
+    with contextlib.redirect_stdout(io.StringIO()):
+        mesh = CuboidMesh(spacing)
+        scene = make_channel(el, 10, h, l, lattice=mesh.lattice, host_only=True)
+    t = scene.filter_tables()
+    assert t["slit_filter"] and not t["disabled"]
+    C = h * l
+    idx = np.arange(lo, lo + 400)
+    vox = mesh.points_at(idx)
+    osc = oracle.build_scene(el, 10, h, l)
+    ref = oracle.run_chunk(osc, gs.voxel_mesh(gs.load_db(), spacing, flat_indices=idx), want_rays=True)
+    assert ref.mask.sum() > 20
+    p = (vox - t["origin"]).astype(np.float32)
+    a = stage_a(t, p)[:C].T  # (V, C)
+    b = stage_b(t, p, 10)[:C].T
+    assert not (ref.mask & ~a).any(), "stage A rejected a ray the oracle accepts"
+    assert not (ref.mask & ~b).any(), "stage B rejected a ray the oracle accepts"
+    # the filter is also selective: few rays beyond the accepted ones survive both stages
+    survivors = (a & b).sum()
+    assert ref.mask.sum() <= survivors <= 1.3 * ref.mask.sum() + 50
+    # forward differences along z, as the lattice kernel advances the forms (re-based every <= 64 voxels)
+    nz = mesh.lattice.nz
+    col0 = (lo // nz + 1) * nz  # first full column inside the slab
+    k = np.arange(min(nz, 64))
+    base = (mesh.points_at([col0]) - t["origin"]).astype(np.float32)
+    dz = (mesh.lattice.step[2] * mesh.lattice.rotation[2]).astype(np.float32)
+    margins = []
+    for i in range(3):
+        f0 = forms(t["det_forms"][i], base)[:, 0]
+        d = (t["det_forms"][i][:, :3].astype(np.float32) @ dz).astype(np.float32)
+        acc = np.empty((len(f0), len(k)), np.float32)
+        cur = f0.copy()
+        for j in range(len(k)):
+            acc[:, j] = cur
+            cur = (cur + d).astype(np.float32)
+        margins.append(acc)
+    fd = (np.abs(margins[2]) - np.maximum(np.abs(margins[0]), np.abs(margins[1])) >= 0)[:C].T  # (k, C)
+    sel = ref.mask[col0 - lo: col0 - lo + len(k)]
+    assert not (sel & ~fd).any(), "forward-differenced stage A rejected a ray the oracle accepts"
+
+
+def test_padding_lanes_never_pass():
+    with contextlib.redirect_stdout(io.StringIO()):
+        mesh = CuboidMesh(20)
+        scene = make_channel("C", 10, 7, 13, lattice=mesh.lattice, host_only=True)  # 91 points -> 96 lanes
+    t = scene.filter_tables()
+    assert t["det_forms"].shape[1] == 96
+    p = (mesh.points_at(np.arange(0, mesh.lattice.n_points, 37)) - t["origin"]).astype(np.float32)
+    assert not stage_a(t, p)[91:].any()
