@@ -239,56 +239,42 @@ def run_ours(args):
             pipes[el] = ChannelPipeline(scenes[el], tables, lattice, reff_table, lo, hi, 2.0, device=device)
             pipes[el].set_profile(profile)
     tests_per_step_rank = (hi - lo) * H * L * len(ELEMENTS)
-    mapped = torch.zeros(len(ELEMENTS), dtype=torch.float64, device=device)
     flux = torch.zeros((len(ELEMENTS), 3), dtype=torch.float64, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     main_stream = torch.cuda.current_stream(device)
     streams = {el: torch.cuda.Stream(device=device) for el in ELEMENTS}
     fork_ev = torch.cuda.Event()
-    mid_ev = {el: torch.cuda.Event() for el in ELEMENTS}
     join_ev = {el: torch.cuda.Event() for el in ELEMENTS}
 
     def step_sequential():
         """One stream, channel after channel (used for the per-kernel timing pass)."""
         for el in ELEMENTS:
             pipes[el].launch_geometry()
-        if world > 1:
-            for i, el in enumerate(ELEMENTS):
-                mapped[i:i + 1].copy_(pipes[el].mapped_max)
-            dist.all_reduce(mapped, op=dist.ReduceOp.MAX)
-            for i, el in enumerate(ELEMENTS):
-                pipes[el].mapped_max.copy_(mapped[i:i + 1])
+            if world > 1:
+                dist.all_reduce(pipes[el].hist_mm)
         for i, el in enumerate(ELEMENTS):
             pipes[el].launch_emissivity()
             flux[i].copy_(pipes[el].flux)
-        if world > 1:
-            dist.all_reduce(flux)
 
     def step():
-        """Stage 1 + Stage 2 for the four channels, each channel on its own stream (they are independent); at N > 1
-        the per-rank maximum of the mapped Reff is max-reduced per channel on the channel's stream before Stage 2 and
-        the per-channel fluxes are sum-reduced after the join (small NCCL all-reduces, latency bound)."""
+        """Stage 1 + Stage 2 for the four channels, each channel on its own stream (they are independent).  Stage 2
+        works from the millimetre-bin weight histogram of the rank's voxels; at N > 1 the per-rank histograms
+        (4096 fp64 bins, 32 kB) are summed with one NCCL all-reduce per channel on the channel's stream, after which
+        every rank holds the whole-grid flux - the single exchange of the path."""
         cur = torch.cuda.current_stream(device)
         fork_ev.record(cur)
         for i, el in enumerate(ELEMENTS):
             with torch.cuda.stream(streams[el]):
                 streams[el].wait_event(fork_ev)
                 pipes[el].launch_geometry()
-                if world == 1:
-                    pipes[el].launch_emissivity()
-                    flux[i].copy_(pipes[el].flux)
-                    join_ev[el].record(streams[el])
-                else:
-                    # per-channel exchange on the channel's own stream: no cross-channel join in mid-step
-                    dist.all_reduce(pipes[el].mapped_max, op=dist.ReduceOp.MAX)
-                    pipes[el].launch_emissivity()
-                    flux[i].copy_(pipes[el].flux)
-                    join_ev[el].record(streams[el])
+                if world > 1:
+                    dist.all_reduce(pipes[el].hist_mm)
+                pipes[el].launch_emissivity()
+                flux[i].copy_(pipes[el].flux)
+                join_ev[el].record(streams[el])
         for el in ELEMENTS:
             cur.wait_event(join_ev[el])
-        if world > 1:
-            dist.all_reduce(flux)
 
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)

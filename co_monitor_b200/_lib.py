@@ -113,6 +113,7 @@ class ComStats(C.Structure):
 
 
 COM_MAX_TRANSITIONS = 4
+COM_MM_BINS = 4096
 
 
 class ComPecDesc(C.Structure):
@@ -190,6 +191,8 @@ def _declare(lib):
     lib.com_weight_histogram.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp,
                                          C.c_size_t, vp]
     lib.com_emissivity_sweep.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, vp]
+    lib.com_weight_histogram_mm.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.com_histogram_rows.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, vp]
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
     lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
@@ -208,6 +211,7 @@ EXPORTED_SYMBOLS = [
     "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
+    "com_weight_histogram_mm", "com_histogram_rows",
 ]
 
 

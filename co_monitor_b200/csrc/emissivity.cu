@@ -174,7 +174,8 @@ struct K2Params {
   double* flux_out;          // (n_trans + 1)
   double* per_voxel;         // (n, 4 + 2*n_trans + 1) or null
   unsigned char* valid_out;  // (n) or null
-  double* hist_out;          // (K) or null (histogram kernel)
+  double* hist_out;          // (K) or null (histogram kernels)
+  double* boundary_out;      // null, or where histogram_rows_kernel leaves the Reff cut it applied
   double* scratch;           // [0] max mapped reff, [1] boundary, partials from +8
   unsigned int* done_counter;
 };
@@ -358,7 +359,10 @@ __global__ void __launch_bounds__(kK2Threads) histogram_rows_kernel(const K2Para
     const double h = hist_mm[b], reff = (double)b / 1000.0;
     if (h != 0.0 && !(reff >= boundary)) atomicAdd(&P.hist_out[profile_row(P, reff)], h);
   }
-  if (threadIdx.x == 0) P.scratch[0] = mapped, P.scratch[1] = boundary;
+  if (threadIdx.x == 0) {
+    if (P.scratch) P.scratch[0] = mapped, P.scratch[1] = boundary;
+    if (P.boundary_out) *P.boundary_out = boundary;
+  }
 }
 
 struct SweepParams {
@@ -370,14 +374,17 @@ struct SweepParams {
   double* flux_out;        // (n_slices, n_trans + 1)
 };
 
-// One block per time slice: every thread evaluates profile rows (only those with weight) and the block reduces.
-__global__ void __launch_bounds__(kK2Threads) sweep_kernel(const SweepParams P) {
+// One block per time slice: every thread evaluates profile rows (only those with weight) and the block reduces in a
+// fixed order.  THREADS = 256 for large batches; 1024 for a few slices, where the dependent table look-ups of a row
+// are the critical path and one row per thread is the shortest chain.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams P) {
   const int s = blockIdx.x, nt = P.tab.n_trans;
   const double* prof = P.profiles + (size_t)s * P.K * 3;
   double acc[kMaxTransitions + 1];
 #pragma unroll
   for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
-  for (int k = threadIdx.x; k < P.K; k += kK2Threads) {
+  for (int k = threadIdx.x; k < P.K; k += THREADS) {
     const double h = P.hist[k];
     if (h == 0.0) continue;
     RowEval r;
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(kK2Threads) sweep_kernel(const SweepParams P) 
       if (t < nt) acc[t] += r.emis[t] * h;
     acc[kMaxTransitions] += r.total * h;
   }
-  __shared__ double s_red[kK2Threads / 32][kMaxTransitions + 1];
+  __shared__ double s_red[THREADS / 32][kMaxTransitions + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int t = 0; t <= kMaxTransitions; ++t) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(kK2Threads) sweep_kernel(const SweepParams P) 
   if (threadIdx.x <= nt) {
     const int slot = threadIdx.x == nt ? kMaxTransitions : threadIdx.x;
     double v = 0.0;
-    for (int wq = 0; wq < kK2Threads / 32; ++wq) v += s_red[wq][slot];
+    for (int wq = 0; wq < THREADS / 32; ++wq) v += s_red[wq][slot];
     P.flux_out[(size_t)s * (nt + 1) + threadIdx.x] = v;
   }
 }
@@ -612,6 +619,39 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
   return COM_OK;
 }
 
+int com_weight_histogram_mm(const uint16_t* reff_mm, const double* w, int64_t n, const uint64_t* n_device,
+                            double* hist_mm, com_stream_t stream) {
+  if (!reff_mm || !w || !hist_mm || n < 0 || (reinterpret_cast<uintptr_t>(reff_mm) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
+    com::set_error("com_weight_histogram_mm: null or not 16-byte aligned arguments");
+    return COM_E_BADARG;
+  }
+  if (n == 0) return COM_OK;
+  const int blocks = (int)std::min<long long>((n / 8 + com::kK2Threads - 1) / com::kK2Threads + 1, 148 * 6);
+  com::weight_histogram_mm_kernel<<<blocks, com::kK2Threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
+int com_histogram_rows(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                       const double* hist_mm, const double* mapped_reff_max, double* hist_rows_out,
+                       double* boundary_out, com_stream_t stream) {
+  if (!profile || K < 1 || !hist_mm || !hist_rows_out) {
+    com::set_error("com_histogram_rows: bad arguments");
+    return COM_E_BADARG;
+  }
+  com::K2Params P{};
+  P.profile = profile, P.K = K, P.profile_sorted = profile_sorted, P.profile_reff_max = profile_reff_max;
+  P.mapped_max = mapped_reff_max;
+  P.hist_out = hist_rows_out;
+  P.boundary_out = boundary_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  COM_CUDA(cudaMemsetAsync(hist_rows_out, 0, sizeof(double) * K, s));
+  com::histogram_rows_kernel<<<1, com::kK2Threads, 0, s>>>(P, hist_mm);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
 int com_reff_max(const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, int64_t n,
                  const uint64_t* n_device, double* max_out, com_stream_t stream) {
   if ((!reff && !reff_mm) || n < 0 || !max_out) {
@@ -641,7 +681,10 @@ int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_
   }
   if (n_slices == 0) return COM_OK;
   com::SweepParams P{tables->dev, profiles, hist, K, n_slices, concentration, flux_out};
-  com::sweep_kernel<<<n_slices, com::kK2Threads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  if (n_slices <= 32)
+    com::sweep_kernel<1024><<<n_slices, 1024, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  else
+    com::sweep_kernel<com::kK2Threads><<<n_slices, com::kK2Threads, 0, static_cast<cudaStream_t>(stream)>>>(P);
   COM_CUDA(cudaGetLastError());
   return COM_OK;
 }

@@ -23,10 +23,24 @@ from .geometry.mesh_calculation import Lattice
 LYMAN_ALPHA = {"B": ("Z4", 48.6), "C": ("Z5", 33.7), "N": ("Z6", 24.8), "O": ("Z7", 19.0)}
 
 
+def reff_to_mm(reff_table):
+    """uint16 millimetre bins of a Reff [m] tensor (3-decimal Reff files are exact in this form; NaN -> 0xFFFF)."""
+    import torch
+
+    mm = torch.round(reff_table * 1000.0)
+    mm = torch.where(torch.isnan(mm), torch.full_like(mm, 65535.0), mm.clamp(0, 65534))
+    return mm.to(torch.int32).to(torch.uint16) if hasattr(torch, "uint16") else mm.to(torch.int32).to(torch.int16)
+
+
 class ChannelPipeline:
     def __init__(self, scene: ChannelScene, tables: LineTables, lattice: Lattice, reff_table, begin: int, end: int,
-                 concentration_percent: float = 2.0, device=None):
-        """*reff_table*: CUDA float64 tensor with Reff [m] of every lattice voxel (NaN outside the LCFS)."""
+                 concentration_percent: float = 2.0, device=None, stage2: str = "histogram"):
+        """*reff_table*: CUDA float64 tensor with Reff [m] of every lattice voxel (NaN outside the LCFS).
+
+        *stage2* = "histogram" (default): the flux is formed from the millimetre-bin weight histogram of the dense
+        per-voxel weights (one 10 B/voxel pass, no compaction) - sum_v eps(k_v) w_v == sum_k H[k] eps(k);
+        "per_voxel": compaction + the per-voxel kernel the ``Emissivity`` drop-in uses.
+        """
         import torch
 
         self._lib = _lib.load()
@@ -48,8 +62,17 @@ class ChannelPipeline:
             self.flux = torch.zeros(tables.n_out, dtype=torch.float64, device=dev)
             self.ews_bytes = self._lib.com_emissivity_workspace_bytes(n)
             self.ews = torch.empty(self.ews_bytes, dtype=torch.uint8, device=dev)
+            self.stage2 = stage2
+            if stage2 == "histogram":
+                if begin != 0 or end != reff_table.numel():
+                    reff_table = reff_table[begin:end]
+                self.reff_mm = reff_to_mm(reff_table).contiguous()
+                self.hist_mm = torch.zeros(_lib.COM_MM_BINS, dtype=torch.float64, device=dev)
+                self.hist_rows = None
+                self.boundary = torch.zeros(1, dtype=torch.float64, device=dev)
         self._profile = None
-        self.kernels_per_launch = 2 + 3 + 1 + 1  # filter, exact, 3 x compaction, reff max, emissivity
+        # filter, exact, then either (mm histogram, rows, sweep) or (3 x compaction, reff max, emissivity)
+        self.kernels_per_launch = 2 + (3 if stage2 == "histogram" else 5)
 
     def set_profile(self, profile: np.ndarray):
         """(K,3) [Reff, T_e, n_e] host array -> device."""
@@ -60,6 +83,8 @@ class ChannelPipeline:
         self._K = len(prof)
         self._sorted = int(np.all(np.diff(prof[:, 0]) >= 0))
         self._pmax = float(prof[:, 0].max())
+        if self.stage2 == "histogram":
+            self.hist_rows = torch.zeros(self._K, dtype=torch.float64, device=self.device)
 
     def _stream(self):
         import torch
@@ -67,9 +92,16 @@ class ChannelPipeline:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def launch_geometry(self):
-        """Stage 1, compaction and this rank's maximum mapped Reff (into ``mapped_max``)."""
+        """Stage 1, then either this rank's millimetre-bin weight histogram (``hist_mm``; ranks all-reduce SUM it) or
+        compaction and this rank's maximum mapped Reff (``mapped_max``; ranks all-reduce MAX it)."""
         s = self._stream()
         self.plan.launch()
+        if self.stage2 == "histogram":
+            self.hist_mm.zero_()
+            rc = self._lib.com_weight_histogram_mm(_ptr(self.reff_mm), _ptr(self.plan.weight), self.n, None,
+                                                   _ptr(self.hist_mm), s)
+            _lib.check(rc, "com_weight_histogram_mm")
+            return
         rc = self._lib.com_compact_visible(_ptr(self.plan.nrays), _ptr(self.plan.weight), self.n, self.plan.begin,
                                            _ptr(self.idx), _ptr(self.w_compact), _ptr(self.count), _ptr(self.cws),
                                            self.cws_bytes, s)
@@ -82,6 +114,15 @@ class ChannelPipeline:
         """Stage 2 over the compacted voxels; ``mapped_max`` may have been max-reduced over ranks in between."""
         if self._profile is None:
             raise RuntimeError("set_profile() first")
+        if self.stage2 == "histogram":
+            s = self._stream()
+            rc = self._lib.com_histogram_rows(_ptr(self._profile), self._K, self._sorted, self._pmax, _ptr(self.hist_mm), None,
+                                              _ptr(self.hist_rows), _ptr(self.boundary), s)
+            _lib.check(rc, "com_histogram_rows")
+            rc = self._lib.com_emissivity_sweep(self.tables.handle, _ptr(self._profile), 1, self._K, _ptr(self.hist_rows),
+                                                self.conc, _ptr(self.flux), s)
+            _lib.check(rc, "com_emissivity_sweep")
+            return
         rc = self._lib.com_emissivity_integrate(
             self.tables.handle, _ptr(self._profile), self._K, self._sorted, self._pmax, self.conc,
             _ptr(self.reff_table), None, _ptr(self.idx), _ptr(self.w_compact), self.n, _ptr(self.count),

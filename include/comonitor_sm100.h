@@ -304,6 +304,19 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
                          const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, const double* w,
                          int64_t n, const uint64_t* n_device, const double* mapped_reff_max, double* hist_out,
                          double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream);
+/* The two halves of the uint16 fast path, for pipelines that keep the millimetre histogram (e.g. to all-reduce it
+ * over ranks: per-rank histograms simply add, and the Reff cut is then taken from the global one):
+ *   com_weight_histogram_mm  hist_mm[min(reff_mm[v], COM_MM_BINS-1)] += w[v] for voxels with w != 0 and reff_mm != 0xFFFF;
+ *                            hist_mm DEVICE (COM_MM_BINS) fp64, ACCUMULATED (clear it yourself); 16-byte aligned inputs
+ *   com_histogram_rows       boundary = min(mapped max, profile_reff_max) with mapped max = largest non-empty bin / 1000
+ *                            (or *mapped_reff_max), then hist_rows_out[row(b/1000)] += hist_mm[b] for b/1000 < boundary;
+ *                            hist_rows_out DEVICE (K) overwritten, boundary_out DEVICE (1) or NULL */
+#define COM_MM_BINS 4096
+int com_weight_histogram_mm(const uint16_t* reff_mm, const double* w, int64_t n, const uint64_t* n_device,
+                            double* hist_mm, com_stream_t stream);
+int com_histogram_rows(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                       const double* hist_mm, const double* mapped_reff_max, double* hist_rows_out,
+                       double* boundary_out, com_stream_t stream);
 int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
                          const double* hist, double concentration, double* flux_out, com_stream_t stream);
 

@@ -149,23 +149,34 @@ def test_device_pipeline_matches_reference_flux(gold, reff10):
     for el in "CO":
         ion, wl = LYMAN_ALPHA[el]
         scene = make_channel(el, 10, 30, 20, lattice=lattice)
-        pipe = ChannelPipeline(scene, cached_line_tables(el, ion, wl, ("EXCIT", "RECOM"), None), lattice, reff, 0,
-                               lattice.n_points, 2.0)
-        pipe.set_profile(prof)
-        flux = pipe.launch().cpu().numpy()
-        np.testing.assert_allclose(flux, gold[f"main_{el}_flux"], rtol=1e-11)
-        # sharded: two half-ranges with the max mapped Reff exchanged in between (what N = 2 ranks do over NCCL)
-        halves = [ChannelPipeline(scene, pipe.tables, lattice, reff, a, b, 2.0) for a, b in ((0, 135000), (135000, 270000))]
-        for h in halves:
-            h.set_profile(prof)
-            h.launch_geometry()
-        m = torch.maximum(halves[0].mapped_max, halves[1].mapped_max)
-        total = np.zeros(3)
-        for h in halves:
-            h.mapped_max.copy_(m)
-            h.launch_emissivity()
-            total += h.flux.cpu().numpy()
-        np.testing.assert_allclose(total, flux, rtol=1e-12)
+        tables = cached_line_tables(el, ion, wl, ("EXCIT", "RECOM"), None)
+        for mode in ("histogram", "per_voxel"):
+            pipe = ChannelPipeline(scene, tables, lattice, reff, 0, lattice.n_points, 2.0, stage2=mode)
+            pipe.set_profile(prof)
+            flux = pipe.launch().cpu().numpy()
+            np.testing.assert_allclose(flux, gold[f"main_{el}_flux"], rtol=1e-11)
+            if mode == "histogram":
+                assert float(pipe.boundary.item()) == float(gold[f"main_{el}_reff_boundary"][0])
+            # sharded: two half-ranges with the exchange in between (what N = 2 ranks do over NCCL)
+            halves = [ChannelPipeline(scene, tables, lattice, reff, a, b, 2.0, stage2=mode)
+                      for a, b in ((0, 135000), (135000, 270000))]
+            for h in halves:
+                h.set_profile(prof)
+                h.launch_geometry()
+            if mode == "histogram":  # all-reduce(SUM) of the millimetre histograms: every rank then holds the whole flux
+                total_hist = halves[0].hist_mm + halves[1].hist_mm
+                for h in halves:
+                    h.hist_mm.copy_(total_hist)
+                    h.launch_emissivity()
+                    np.testing.assert_allclose(h.flux.cpu().numpy(), flux, rtol=1e-12)
+            else:  # all-reduce(MAX) of the mapped Reff, then all-reduce(SUM) of the partial fluxes
+                m = torch.maximum(halves[0].mapped_max, halves[1].mapped_max)
+                total = np.zeros(3)
+                for h in halves:
+                    h.mapped_max.copy_(m)
+                    h.launch_emissivity()
+                    total += h.flux.cpu().numpy()
+                np.testing.assert_allclose(total, flux, rtol=1e-12)
         scene.close()
 
 
