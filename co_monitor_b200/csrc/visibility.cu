@@ -676,8 +676,10 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
                       long long rays_capacity, unsigned long long* rays_count_out, const uint16_t* reff_bin,
                       double* hist_out, int n_bins, ComStats* stats_out, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream) {
-  if (!scene || (!lattice_h && !vox_xyz) || vox_end < vox_begin || !w_out || !stats_out || !workspace ||
-      (rays_out && !rays_count_out) || (hist_out && !reff_bin)) {
+  // an empty range has nothing to write: the output pointers may then be null (empty device tensors are)
+  const bool empty = vox_end == vox_begin;
+  if (!scene || (!lattice_h && !vox_xyz && !empty) || vox_end < vox_begin || (!w_out && !empty) || !stats_out ||
+      !workspace || (rays_out && !rays_count_out) || (hist_out && !reff_bin)) {
     set_error("com_visibility_weights: bad arguments");
     return COM_E_BADARG;
   }
@@ -747,8 +749,8 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   }
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
   COM_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(ComStats), stream));
-  COM_CUDA(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)n_vox, stream));
-  if (nrays_out) COM_CUDA(cudaMemsetAsync(nrays_out, 0, sizeof(unsigned int) * (size_t)n_vox, stream));
+  if (n_vox) COM_CUDA(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)n_vox, stream));
+  if (nrays_out && n_vox) COM_CUDA(cudaMemsetAsync(nrays_out, 0, sizeof(unsigned int) * (size_t)n_vox, stream));
   if (rays_count_out) COM_CUDA(cudaMemsetAsync(rays_count_out, 0, sizeof(unsigned long long), stream));
   if (n_vox == 0) return COM_OK;
 

@@ -325,3 +325,52 @@ def test_detector_image_extension(sims):
     again = sim.scene.visibility(lattice=lat, begin=lo, end=hi)
     assert float(img.sum().item()) == float(img.sum().item())  # untouched after disabling
     assert again.stats["passing_rays"] == res.stats["passing_rays"]
+
+
+def test_edge_cases_empty_range_overflow_and_bad_arguments(sims):
+    """Empty voxel range, candidate-list overflow (reported, then recovered by re-running with the measured count),
+    and argument validation through the C ABI."""
+    import ctypes as C
+
+    import torch
+
+    from co_monitor_b200 import _lib
+
+    sim = sims("C")
+    lat = sim.mesh.lattice
+    lib = _lib.load()
+    # empty range: nothing to do, statistics all zero
+    res = sim.scene.visibility(lattice=lat, begin=1234, end=1234)
+    assert res.weight.numel() == 0 and res.stats["passing_rays"] == 0 and res.stats["tests"] == 0
+    # a candidate list that is far too small: the first launch overflows, the wrapper re-runs with the measured count
+    lo, hi = 120000, 150000
+    want = sim.scene.visibility(lattice=lat, begin=lo, end=hi)
+    tiny = sim.scene.visibility(lattice=lat, begin=lo, end=hi, candidate_fraction=1e-9)
+    assert torch.equal(tiny.nrays, want.nrays) and not tiny.stats["overflow"]
+    # ... and the raw entry point reports the overflow instead of hiding it
+    from co_monitor_b200.geometry.engine import lattice_struct
+
+    n = hi - lo
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    nr = torch.empty(n, dtype=torch.int32, device="cuda")
+    st = torch.zeros(8, dtype=torch.int64, device="cuda")
+    ws = torch.empty(256 + 8 * 100, dtype=torch.uint8, device="cuda")  # room for 100 candidates only
+    ls = lattice_struct(lat)
+    rc = lib.com_visibility_weights(sim.scene.handle, C.byref(ls), None, lo, hi, C.c_void_p(w.data_ptr()),
+                                    C.c_void_p(nr.data_ptr()), None, 0, None, None, None, 0, C.c_void_p(st.data_ptr()),
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    stats = dict(zip([f[0] for f in _lib.ComStats._fields_], st.cpu().tolist()))
+    assert stats["overflow"] == 1 and stats["candidates"] > stats["candidate_capacity"] == 100
+    # argument validation
+    assert lib.com_visibility_weights(None, C.byref(ls), None, 0, 10, C.c_void_p(w.data_ptr()), None, None, 0, None, None,
+                                      None, 0, C.c_void_p(st.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), None) == _lib.COM_E_BADARG
+    assert lib.com_visibility_weights(sim.scene.handle, C.byref(ls), None, 0, lat.n_points + 1, C.c_void_p(w.data_ptr()),
+                                      None, None, 0, None, None, None, 0, C.c_void_p(st.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), None) == _lib.COM_E_BADARG
+    assert b"outside the lattice" in lib.com_last_error()
+    with pytest.raises(ValueError):
+        sim.scene.visibility(lattice=lat, voxels=torch.zeros((3, 3), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        sim.scene.visibility(voxels=torch.zeros((3, 3), dtype=torch.float32, device="cuda"))
