@@ -193,6 +193,8 @@ def _declare(lib):
     lib.com_emissivity_sweep.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, vp]
     lib.com_weight_histogram_mm.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.com_histogram_rows.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, vp]
+    lib.com_reff_resample.argtypes = [C.POINTER(ComLattice), i64, i64, vp, i64, i64, i64, vp, vp, vp]
+    lib.com_reff_quadratic.argtypes = [C.POINTER(ComLattice), i64, i64, dp, C.c_double, vp, vp, vp]
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
     lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
@@ -211,7 +213,7 @@ EXPORTED_SYMBOLS = [
     "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
-    "com_weight_histogram_mm", "com_histogram_rows",
+    "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
 ]
 
 

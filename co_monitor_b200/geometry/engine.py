@@ -267,9 +267,10 @@ class ChannelScene:
         return VisibilityResult(begin=begin, end=end, weight=w, nrays=nr, stats=stats, rays=rays)
 
     def plan(self, lattice: Lattice, begin: int = 0, end: int | None = None, candidate_fraction: float = 0.0,
-             device=None) -> "VisibilityPlan":
+             device=None, **kwargs) -> "VisibilityPlan":
         """Pre-allocated, sync-free launcher for repeated Stage-1 runs over the same voxel range."""
-        return VisibilityPlan(self, lattice, begin, lattice.n_points if end is None else end, candidate_fraction, device)
+        return VisibilityPlan(self, lattice, begin, lattice.n_points if end is None else end, candidate_fraction, device,
+                              **kwargs)
 
     def compact(self, result: VisibilityResult):
         """Visible voxels of *result*: (flat indices int64, weights float64), device tensors, ascending."""
@@ -295,19 +296,38 @@ class ChannelScene:
 class VisibilityPlan:
     """Device buffers + arguments of one ``com_visibility_weights`` call, reusable without host syncs."""
 
-    def __init__(self, scene: ChannelScene, lattice: Lattice, begin: int, end: int, candidate_fraction: float, device):
+    def __init__(self, scene: ChannelScene, lattice: Lattice, begin: int, end: int, candidate_fraction: float, device,
+                 reff_bin=None, hist=None, capacity: int | None = None):
+        """*reff_bin* (uint16 CUDA tensor over the whole lattice/shard) and *hist* (float64 CUDA tensor): the exact
+        kernel also accumulates every passing ray's weight into ``hist[reff_bin[voxel]]`` (bins >= len(hist) skipped).
+        *capacity*: size the buffers for ranges of up to that many voxels (``rebind`` then moves the range)."""
         import torch
 
         self.scene, self.begin, self.end = scene, begin, end
         self.device = torch.device(device if device is not None else "cuda")
-        n = end - begin
+        n = max(end - begin, capacity or 0)
+        self.capacity = n
         self._lat = lattice_struct(lattice)
+        self.reff_bin, self.hist = reff_bin, hist
+        if (reff_bin is None) != (hist is None):
+            raise ValueError("reff_bin and hist go together")
         with torch.cuda.device(self.device):
             self.weight = torch.empty(n, dtype=torch.float64, device=self.device)
             self.nrays = torch.empty(n, dtype=torch.int32, device=self.device)
             self.stats_t = torch.zeros(8, dtype=torch.int64, device=self.device)
             self.ws_bytes = scene._lib.com_visibility_workspace_bytes(scene.handle, n, candidate_fraction)
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self._stats = self.stats_t
+
+    def rebind(self, begin: int, end: int, stats=None) -> "VisibilityPlan":
+        """Move the plan to the voxels [begin, end) (at most ``capacity`` of them); the outputs are then
+        ``weight[:end-begin]`` / ``nrays[:end-begin]``.  *stats*: another 8 x int64 CUDA tensor to leave the statistics in."""
+        if not 0 <= end - begin <= self.capacity:
+            raise ValueError(f"range of {end - begin} voxels, plan capacity {self.capacity}")
+        self.begin, self.end = begin, end
+        if stats is not None:
+            self._stats = stats
+        return self
 
     def launch(self, stream=None) -> None:
         import torch
@@ -317,12 +337,15 @@ class VisibilityPlan:
         s = self.scene
         rc = s._lib.com_visibility_weights(
             s.handle, C.byref(self._lat), None, self.begin, self.end, C.c_void_p(self.weight.data_ptr()),
-            C.c_void_p(self.nrays.data_ptr()), None, 0, None, None, None, 0, C.c_void_p(self.stats_t.data_ptr()),
+            C.c_void_p(self.nrays.data_ptr()), None, 0, None,
+            C.c_void_p(self.reff_bin.data_ptr()) if self.reff_bin is not None else None,
+            C.c_void_p(self.hist.data_ptr()) if self.hist is not None else None,
+            int(self.hist.numel()) if self.hist is not None else 0, C.c_void_p(self._stats.data_ptr()),
             C.c_void_p(self.ws.data_ptr()), self.ws_bytes, C.c_void_p(stream))
         _lib.check(rc, "com_visibility_weights")
 
     def stats(self) -> dict:
-        out = dict(zip([f[0] for f in _lib.ComStats._fields_], self.stats_t.cpu().tolist()))
+        out = dict(zip([f[0] for f in _lib.ComStats._fields_], self._stats.cpu().tolist()))
         out.pop("reserved", None)
         return out
 

@@ -13,6 +13,9 @@ This module provides the replacements the north-star allows:
                         is NaN (outside the LCFS), exactly how the reference treats NaN rows (reader.py:176).
   * ``QuadraticReff``   an analytic flux-surface model fitted to a shipped grid (Reff^2 as a quadratic form of
                         position: nested elliptic cylinders), evaluable for 1e8-1e9 voxel lattices without a file.
+Both also run on the device (``resample_reff_device``, ``QuadraticReff.on_device``: csrc/reff.cu through
+``com_reff_resample`` / ``com_reff_quadratic``) and then produce the uint16 millimetre bins Stage 2 reads for any
+(sharded) range of a 1e8-1e9 voxel lattice; the NumPy forms here are what those kernels are tested against.
 """
 from __future__ import annotations
 
@@ -44,13 +47,62 @@ def _quiet_mesh(spacing) -> CuboidMesh:
         return CuboidMesh(spacing)
 
 
-def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None = None, decimals: int | None = 3) -> np.ndarray:
-    """Reff [m] on every voxel of *target_lattice* (any lattice spanning the standard cuboid), flat index order."""
+def source_volume(source_spacing: int = 15, root: Path | None = None):
+    """A shipped Reff grid as a ``(ny, nx, nz)`` array (z fastest: the reshape of the file's row order) and its lattice."""
     src = load_reff(source_spacing, root)
-    ls, lt = _quiet_mesh(source_spacing).lattice, target_lattice
+    ls = _quiet_mesh(source_spacing).lattice
     if len(src) != ls.n_points:
         raise ValueError(f"{reff_path(source_spacing, root)} has {len(src)} rows, lattice has {ls.n_points}")
-    vol = src["Reff [m]"].to_numpy(dtype=float).reshape(ls.ny, ls.nx, ls.nz)  # (iy, ix, iz), z fastest
+    return src["Reff [m]"].to_numpy(dtype=float).reshape(ls.ny, ls.nx, ls.nz), ls
+
+
+def _device_outputs(lattice, begin, end, want_reff, device):
+    import torch
+
+    if not torch.cuda.is_available():
+        from .. import _lib
+
+        raise _lib.ComonitorError(_lib.COM_E_CUDA, "Reff provider", "no CUDA device: the accelerated path has no CPU fallback")
+    device = torch.device(device if device is not None else "cuda")
+    end = lattice.n_points if end is None else end
+    if not 0 <= begin <= end <= lattice.n_points:
+        raise ValueError(f"voxel range [{begin},{end}) outside [0,{lattice.n_points})")
+    with torch.cuda.device(device):
+        mm = torch.empty(end - begin, dtype=torch.uint16, device=device)
+        reff = torch.empty(end - begin, dtype=torch.float64, device=device) if want_reff else None
+        stream = torch.cuda.current_stream().cuda_stream
+    return device, end, mm, reff, stream
+
+
+def resample_reff_device(target_lattice, source_spacing: int = 15, begin: int = 0, end: int | None = None,
+                         want_reff: bool = False, device=None, root: Path | None = None, source=None):
+    """``interpolate_reff`` on the GPU for the voxels [begin, end) of *target_lattice* (shard-local indices when the
+    lattice is a shard): ``(reff_mm uint16, reff float64 | None)`` CUDA tensors.  *source*: a ``(vol, lattice)`` pair
+    to resample instead of a shipped file."""
+    import ctypes as C
+
+    import torch
+
+    from .. import _lib
+    from .engine import lattice_struct
+
+    device, end, mm, reff, stream = _device_outputs(target_lattice, begin, end, want_reff, device)
+    vol, ls = source if source is not None else source_volume(source_spacing, root)
+    src = torch.from_numpy(np.array(vol, dtype=np.float64, order="C", copy=True)).to(device)
+    lat = lattice_struct(target_lattice)
+    with torch.cuda.device(device):
+        rc = _lib.load().com_reff_resample(C.byref(lat), begin, end, C.c_void_p(src.data_ptr()), ls.nx, ls.ny, ls.nz,
+                                           C.c_void_p(mm.data_ptr()), C.c_void_p(reff.data_ptr()) if want_reff else None,
+                                           C.c_void_p(stream))
+    _lib.check(rc, "com_reff_resample")
+    src.record_stream(torch.cuda.current_stream(device))
+    return mm, reff
+
+
+def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None = None, decimals: int | None = 3) -> np.ndarray:
+    """Reff [m] on every voxel of *target_lattice* (any lattice spanning the standard cuboid), flat index order."""
+    vol, ls = source_volume(source_spacing, root)
+    lt = target_lattice
 
     def axis(n_t, n_s):
         f = np.arange(n_t) * ((n_s - 1) / (n_t - 1))
@@ -70,6 +122,34 @@ def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None
                 out += np.where(nanv, 0.0, v) * w
     out[bad] = np.nan
     out = out.ravel()
+    return np.round(out, decimals=decimals) if decimals is not None else out
+
+
+def interpolate_reff_at(target_lattice, flat, source_spacing: int = 15, root: Path | None = None,
+                        decimals: int | None = 3, source=None) -> np.ndarray:
+    """``interpolate_reff`` for selected flat indices only (shard-local when the lattice is a shard): the same
+    operations per voxel, so the values are bit-identical; usable on slabs of lattices too large to resample whole."""
+    vol, ls = source if source is not None else source_volume(source_spacing, root)
+    lt = target_lattice
+    ix, iy, iz = lt.unravel(np.asarray(flat, dtype=np.int64))
+
+    def axis(n_t, n_s, i):
+        f = np.arange(n_t) * ((n_s - 1) / (n_t - 1))
+        i0 = np.minimum(np.floor(f).astype(int), n_s - 2)
+        return i0[i], (f - i0)[i]
+
+    (y0, fy), (x0, fx), (z0, fz) = axis(lt.ny, ls.ny, iy), axis(lt.nx, ls.nx, ix), axis(lt.nz, ls.nz, iz)
+    out = np.zeros(len(ix))
+    bad = np.zeros(len(ix), dtype=bool)
+    for dy, wy in ((0, 1 - fy), (1, fy)):
+        for dx, wx in ((0, 1 - fx), (1, fx)):
+            for dz, wz in ((0, 1 - fz), (1, fz)):
+                w = wy * wx * wz
+                v = vol[y0 + dy, x0 + dx, z0 + dz]
+                nanv = np.isnan(v)
+                bad |= nanv & (w > 0)
+                out += np.where(nanv, 0.0, v) * w
+    out[bad] = np.nan
     return np.round(out, decimals=decimals) if decimals is not None else out
 
 
@@ -120,3 +200,22 @@ class QuadraticReff:
              + c[6] * x + c[7] * y + c[8] * z + c[9])
         r = np.sqrt(np.maximum(q, 0.0))
         return np.where(r <= self.reff_max, r, np.nan)
+
+    def on_device(self, lattice, begin: int = 0, end: int | None = None, want_reff: bool = False, device=None):
+        """The model on the voxels [begin, end) of *lattice*, evaluated on the GPU from the lattice closed form:
+        ``(reff_mm uint16, reff float64 rounded to 3 decimals | None)`` CUDA tensors."""
+        import ctypes as C
+
+        from .. import _lib
+        from .engine import lattice_struct
+
+        device, end, mm, reff, stream = _device_outputs(lattice, begin, end, want_reff, device)
+        import torch
+
+        coef = (C.c_double * 10)(*[float(c) for c in self.coef])
+        lat = lattice_struct(lattice)
+        with torch.cuda.device(device):
+            rc = _lib.load().com_reff_quadratic(C.byref(lat), begin, end, coef, self.reff_max, C.c_void_p(mm.data_ptr()),
+                                                C.c_void_p(reff.data_ptr()) if want_reff else None, C.c_void_p(stream))
+        _lib.check(rc, "com_reff_quadratic")
+        return mm, reff

@@ -320,6 +320,23 @@ int com_histogram_rows(const double* profile, int32_t K, int32_t profile_sorted,
 int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
                          const double* hist, double concentration, double* flux_out, com_stream_t stream);
 
+/* ---- Reff provider ------------------------------------------------------------
+ * Replaces the VMEC web-service step (co_monitor/geometry/reff_VMEC.py:85-136) and its 3-decimal file
+ * (reff_VMEC.py:138-176) for lattices that have no shipped file: Reff of the voxels [vox_begin, vox_end) of the
+ * (sharded) target lattice, as uint16 millimetre bins reff_mm_out[v - vox_begin] = rint(Reff * 1000), 0xFFFF outside
+ * the last closed flux surface, and optionally (reff_out, nullable) as the 3-decimal doubles the file would hold.
+ *   com_reff_resample   trilinear resampling of a coarser grid src_reff (DEVICE fp64, (src_ny, src_nx, src_nz) row-major
+ *                       = the reference's flat order; NaN outside the LCFS) spanning the same cuboid; a stencil that
+ *                       touches NaN with non-zero weight gives NaN.  Bit-identical to
+ *                       co_monitor_b200.geometry.reff.interpolate_reff.
+ *   com_reff_quadratic  analytic nested flux surfaces: Reff^2 = c0 x^2 + c1 y^2 + c2 z^2 + c3 xy + c4 xz + c5 yz +
+ *                       c6 x + c7 y + c8 z + c9 (position in metres; coef_h HOST, 10 doubles), NaN beyond reff_max. */
+int com_reff_resample(const ComLattice* target_h, int64_t vox_begin, int64_t vox_end, const double* src_reff,
+                      int64_t src_nx, int64_t src_ny, int64_t src_nz, uint16_t* reff_mm_out, double* reff_out,
+                      com_stream_t stream);
+int com_reff_quadratic(const ComLattice* target_h, int64_t vox_begin, int64_t vox_end, const double* coef_h,
+                       double reff_max, uint16_t* reff_mm_out, double* reff_out, com_stream_t stream);
+
 /* Measurement aid (not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
  * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the
  * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 exact kernel

@@ -180,6 +180,61 @@ def test_device_pipeline_matches_reference_flux(gold, reff10):
         scene.close()
 
 
+def test_volume_pipeline_on_the_fly_histogram_matches_reference_flux(gold):
+    """The whole-volume pipeline of scripts/volume_flux.py (config 5) at the 10 mm grid: Reff bins from the device
+    resampling kernel, Stage 1 in chunks adding every passing ray to the millimetre histogram on the fly, one histogram
+    per shard summed as the all-reduce would, Stage 2 from the histogram - against the reference's flux."""
+    import contextlib
+    import io
+
+    import torch
+
+    from co_monitor_b200 import _lib
+    from co_monitor_b200.emissivity.engine import _ptr, cached_line_tables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.geometry.reff import resample_reff_device
+    from co_monitor_b200.pipeline import LYMAN_ALPHA
+
+    lib = _lib.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        full = CuboidMesh(10).lattice
+    prof = np.ascontiguousarray(TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy())
+    prof_t = torch.from_numpy(prof).cuda()
+    K = len(prof)
+    for el in "BN":
+        ion, wl = LYMAN_ALPHA[el]
+        scene = make_channel(el, 10, 30, 20, lattice=full)
+        tables = cached_line_tables(el, ion, wl, ("EXCIT", "RECOM"), None)
+        for world in (1, 3):
+            total = torch.zeros(_lib.COM_MM_BINS, dtype=torch.float64, device="cuda")
+            rays = 0
+            for rank in range(world):
+                lat = full.shard(world, rank, cols_per_block=8)
+                reff_mm, _ = resample_reff_device(lat, 15)
+                hist = torch.zeros(_lib.COM_MM_BINS, dtype=torch.float64, device="cuda")
+                chunk = 40_000  # several launches per shard, the last one ragged
+                plan = scene.plan(lat, 0, chunk, reff_bin=reff_mm, hist=hist)
+                for lo in range(0, lat.n_points, chunk):
+                    plan.rebind(lo, min(lat.n_points, lo + chunk)).launch()
+                    st = plan.stats()
+                    assert not st["overflow"]
+                    rays += st["passing_rays"]
+                total += hist
+            assert rays == int(gold[f"stage1_{el}_passing_rays"][0]) if f"stage1_{el}_passing_rays" in gold else rays > 0
+            rows = torch.zeros(K, dtype=torch.float64, device="cuda")
+            bnd = torch.zeros(1, dtype=torch.float64, device="cuda")
+            flux = torch.zeros(3, dtype=torch.float64, device="cuda")
+            _lib.check(lib.com_histogram_rows(_ptr(prof_t), K, 1, float(prof[:, 0].max()), _ptr(total), None, _ptr(rows),
+                                              _ptr(bnd), None), "com_histogram_rows")
+            _lib.check(lib.com_emissivity_sweep(tables.handle, _ptr(prof_t), 1, K, _ptr(rows), 0.02, _ptr(flux), None),
+                       "com_emissivity_sweep")
+            np.testing.assert_allclose(flux.cpu().numpy(), gold[f"main_{el}_flux"], rtol=1e-11)
+            assert float(bnd.item()) == float(gold[f"main_{el}_reff_boundary"][0])
+        scene.close()
+
+
 def test_host_buffer_emissivity_call(gold, reff10):
     """com_emissivity_integrate_host (host in, host out) against the reference's C-channel result."""
     import ctypes as C
