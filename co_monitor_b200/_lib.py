@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcomonitor_sm100.so")
 
-COM_OK, COM_E_BADARG, COM_E_CUDA, COM_E_NOMEM, COM_E_OVERFLOW, COM_E_GEOMETRY, COM_E_EMPTY = 0, -1, -2, -3, -4, -5, -6
+COM_OK, COM_E_BADARG, COM_E_CUDA, COM_E_NOMEM, COM_E_OVERFLOW, COM_E_GEOMETRY, COM_E_EMPTY, COM_E_IO = 0, -1, -2, -3, -4, -5, -6, -7
 COM_MAX_EDGES = 32
 
 
@@ -195,6 +195,8 @@ def _declare(lib):
     lib.com_histogram_rows.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, vp]
     lib.com_reff_resample.argtypes = [C.POINTER(ComLattice), i64, i64, vp, i64, i64, i64, vp, vp, vp]
     lib.com_reff_quadratic.argtypes = [C.POINTER(ComLattice), i64, i64, dp, C.c_double, vp, vp, vp]
+    lib.com_write_stage1_csv.argtypes = [C.c_char_p, vp, dp, dp, dp, dp, i64, i32, i32]
+    lib.com_format_float_repr.argtypes = [C.c_double, C.c_char_p, i32]
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
     lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
@@ -214,6 +216,7 @@ EXPORTED_SYMBOLS = [
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
+    "com_write_stage1_csv", "com_format_float_repr",
 ]
 
 

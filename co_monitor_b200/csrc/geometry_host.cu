@@ -371,6 +371,7 @@ const char* com_error_string(int code) {
     case COM_E_OVERFLOW: return "candidate list overflow";
     case COM_E_GEOMETRY: return "degenerate geometry";
     case COM_E_EMPTY: return "Not enough points to perform calculations!";
+    case COM_E_IO: return "result file could not be opened or written";
     default: return "unknown error";
   }
 }

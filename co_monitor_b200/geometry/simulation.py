@@ -19,6 +19,11 @@ Differences a caller can see (all deliberate):
     (``...-slit_<S>0.dat`` == the shipped ``slit_100`` files for S = 10), into
     ``<cwd>/input_files/geometry/observed_plasma_volume/<element>/`` where Stage 2 looks for it
     (the reference writes to a stale package-relative ``_Input_files`` path, simulation.py:619-625).
+    The bytes are the ones pandas/dask produce, written by the native writer (stage1_io.py);
+    ``save_to_file(partitions=k)`` writes k dask-style partitions, ``save_to_file(binary=True)``
+    the 16-byte-per-row side format for 1e8-row results.
+  * Fine grids (1 mm: 2.7e8 voxels, 0.65 mm: 9.8e8) run as several launches of ``stage1_chunk``
+    voxels; nothing per-voxel survives a launch except the visible voxels' indices and weights.
 """
 from __future__ import annotations
 
@@ -68,6 +73,7 @@ class Simulation:
         calibrate_apertures=True,
         output_dir=None,
         verbose=True,
+        stage1_chunk=1 << 26,
     ):
         self._say = print if verbose else (lambda *a, **k: None)
         self._say(f"\nInitializing element {element}.")
@@ -97,8 +103,7 @@ class Simulation:
             filter_eps_mm=filter_eps_mm, calibrate_apertures=calibrate_apertures,
         )
         self._say("\n--- Calculating photon transmission ---")
-        self._result = self.scene.visibility(lattice=self.mesh.lattice, device=device)
-        self.stats = self._result.stats
+        self._visible_idx, self._visible_w, self.stats = self._run_stage1(int(stage1_chunk))
         self._say("--- Photon transmission calculation finished ---")
         if self.stats["passing_rays"] == 0:
             # simulation.py:451-456
@@ -163,11 +168,30 @@ class Simulation:
         return area
 
     # ---- results ---------------------------------------------------------------------------------------
+    def _run_stage1(self, chunk: int):
+        """K1a/K1b + compaction over the lattice in launches of at most *chunk* voxels: the visible voxels'
+        ascending flat indices and weights (host arrays) and the summed statistics."""
+        lattice = self.mesh.lattice
+        total = lattice.n_points
+        idx_parts, w_parts, stats = [], [], None
+        for lo in range(0, total, max(1, chunk)):
+            res = self.scene.visibility(lattice=lattice, begin=lo, end=min(total, lo + chunk), device=self._device)
+            idx_d, w_d = self.scene.compact(res)
+            idx_parts.append(idx_d.cpu().numpy())
+            w_parts.append(w_d.cpu().numpy())
+            if stats is None:
+                stats = dict(res.stats)
+            else:
+                for key, value in res.stats.items():
+                    stats[key] = max(stats[key], value) if key in ("candidate_capacity", "overflow") else stats[key] + value
+            del res, idx_d, w_d
+        if len(idx_parts) == 1:
+            return idx_parts[0], w_parts[0], stats
+        return np.concatenate(idx_parts), np.concatenate(w_parts), stats
+
     def calculate_radiation_fraction(self) -> ComputedFrame:
         """Visible voxels with their summed weight (simulation.py:538-594), ordered by voxel index."""
-        idx_d, w_d = self.scene.compact(self._result)
-        idx = idx_d.cpu().numpy()
-        w = w_d.cpu().numpy()
+        idx, w = self._visible_idx, self._visible_w
         pts = self.mesh.points_at(idx)
         return ComputedFrame(
             {
@@ -226,10 +250,21 @@ class Simulation:
                 f"height_{self.crystal_height_step}-length_{self.crystal_length_step}-slit_{self.slits_number}0.dat")
         return root / name
 
-    def save_to_file(self):
-        """``;``-separated CSV with header, no index (simulation.py:616-630)."""
+    def save_to_file(self, partitions: int = 1, binary: bool = False):
+        """``;``-separated CSV with header, no index (simulation.py:616-630): byte for byte what
+        ``ddf.to_csv(sep=";", header=True, index=False)`` writes.  *partitions* > 1: dask-style numbered parts
+        (``...slit_<S>0.dat``, ``...slit_<S>1.dat``, ...); *binary*: the index + weight side format (``.bin``)."""
+        from . import stage1_io
+
         path = self.output_path()
-        path.parent.mkdir(parents=True, exist_ok=True)
-        pd.DataFrame(self.ddf).to_csv(path, sep=";", header=True, index=False)
+        if binary:
+            path = stage1_io.write_binary(path.with_suffix(".bin"), self.mesh.lattice, self.ddf["idx_sel_plas_points"],
+                                          self.ddf["total_intensity_fraction"])
+        else:
+            name = str(path) if partitions <= 1 else str(path)[: -len("0.dat")] + "*.dat"
+            d = self.ddf
+            files = stage1_io.write_csv(name, d["idx_sel_plas_points"], d["plasma_x"], d["plasma_y"], d["plasma_z"],
+                                        d["total_intensity_fraction"], partitions=partitions)
+            path = files[0]
         self._say("\nFile successfully saved!")
         return path

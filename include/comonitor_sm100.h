@@ -45,6 +45,7 @@ extern "C" {
 #define COM_E_GEOMETRY (-5) /* degenerate aperture (collinear plane points, empty section) */
 #define COM_E_EMPTY (-6)    /* no ray passed: the reference's "Not enough points to perform
                                calculations!" (simulation.py:451-456)                      */
+#define COM_E_IO (-7)       /* a result file could not be opened or written                */
 
 typedef void* com_stream_t; /* cudaStream_t */
 
@@ -336,6 +337,16 @@ int com_reff_resample(const ComLattice* target_h, int64_t vox_begin, int64_t vox
                       com_stream_t stream);
 int com_reff_quadratic(const ComLattice* target_h, int64_t vox_begin, int64_t vox_end, const double* coef_h,
                        double reff_max, uint16_t* reff_mm_out, double* reff_out, com_stream_t stream);
+
+/* ---- Stage-1 result file -------------------------------------------------------
+ * The reference writes its result with to_csv(sep=";", header=True, index=False) (simulation.py:616-630):
+ *   idx_sel_plas_points;plasma_x;plasma_y;plasma_z;total_intensity_fraction
+ * integers in decimal, floats in Python's shortest round-trip repr.  com_write_stage1_csv writes the same bytes from
+ * HOST arrays (n rows), formatting on n_threads host threads (0: all cores); 1e7-1e8 rows in seconds.
+ * com_format_float_repr formats one value (returns its length; out needs >= 32 bytes) - the rule the writer uses. */
+int com_write_stage1_csv(const char* path, const int64_t* idx, const double* x, const double* y, const double* z,
+                         const double* w, int64_t n, int32_t write_header, int32_t n_threads);
+int com_format_float_repr(double value, char* out, int32_t out_bytes);
 
 /* Measurement aid (not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
  * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the

@@ -374,3 +374,30 @@ def test_edge_cases_empty_range_overflow_and_bad_arguments(sims):
         sim.scene.visibility(lattice=lat, voxels=torch.zeros((3, 3), dtype=torch.float64, device="cuda"))
     with pytest.raises(ValueError):
         sim.scene.visibility(voxels=torch.zeros((3, 3), dtype=torch.float32, device="cuda"))
+
+
+def test_chunked_launches_and_result_files(sims, tmp_path):
+    """Simulation over several launches gives the same frame; the files it writes: text = pandas' bytes (and so the
+    format of the shipped files), dask-style partitions, and the binary side format - all read back to the frame."""
+    from co_monitor_b200.geometry import stage1_io
+    from co_monitor_b200.geometry.simulation import Simulation
+
+    whole = sims("O")
+    chunked = Simulation("O", slits_number=10, distance_between_points=10, crystal_height_step=30, crystal_length_step=20,
+                         plot=False, verbose=False, stage1_chunk=47_123, output_dir=tmp_path)  # 6 ragged launches
+    a, b = pd.DataFrame(whole.ddf), pd.DataFrame(chunked.ddf)
+    assert a.idx_sel_plas_points.equals(b.idx_sel_plas_points)
+    np.testing.assert_allclose(b.total_intensity_fraction, a.total_intensity_fraction, rtol=1e-13)
+    for key in ("tests", "passing_rays", "visible_voxels", "near_edge_rays"):
+        assert chunked.stats[key] == whole.stats[key]
+    path = chunked.save_to_file()
+    assert path.name == "O_plasma_coordinates-10_mm_spacing-height_30-length_20-slit_100.dat"
+    want = tmp_path / "pandas.csv"
+    b.to_csv(want, sep=";", header=True, index=False)
+    assert path.read_bytes() == want.read_bytes()
+    pd.testing.assert_frame_equal(stage1_io.read(path), b)
+    first = chunked.save_to_file(partitions=4)
+    assert first.name.endswith("slit_100.dat") and (tmp_path / first.name.replace("slit_100", "slit_103")).exists()
+    pd.testing.assert_frame_equal(stage1_io.read(str(first).replace("slit_100", "slit_10*")), b)
+    binary = chunked.save_to_file(binary=True)
+    pd.testing.assert_frame_equal(stage1_io.read(binary, mesh=chunked.mesh), b)
