@@ -351,9 +351,29 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       const float4 p0 = base[seg];
       const int len = segs[seg].y;
       float xs = form(gx, p0), ys = form(gy, p0), w = form(gw, p0);
+      // Hierarchical cull.  xs - w and xs + w are linear along the run, and a ray passes the X test iff they differ in
+      // sign (|xs| <= |w|).  If they agree in sign at both ends of a run - |xs| > |w| at both ends, with xs of the same
+      // sign - they agree everywhere in between, so no voxel of the run passes; likewise for Y.  First the whole
+      // segment, then every group of kUnroll voxels; only the groups that survive are evaluated per voxel.  A passing
+      // ray has a margin >= the band (0.4 in these units), the end values are good to 0.02: a run holding one is kept.
+      auto culled = [&](float xa, float ya, float wa, float xb, float yb, float wb) {
+        return (fabsf(xa) > fabsf(wa) && fabsf(xb) > fabsf(wb) && xa * xb > 0.f) ||
+               (fabsf(ya) > fabsf(wa) && fabsf(yb) > fabsf(wb) && ya * yb > 0.f);
+      };
+      if (sc.filter_disabled == 0) {
+        const float n1 = (float)(len - 1);
+        if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(n1, dxs, xs), fmaf(n1, dys, ys), fmaf(n1, dws, w)))) continue;
+      }
       int k = 0;
 #pragma unroll 1
       for (; k + kUnroll <= len; k += kUnroll) {
+        if (sc.filter_disabled == 0) {
+          constexpr float kLast = (float)(kUnroll - 1), kStep = (float)kUnroll;
+          if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(kLast, dxs, xs), fmaf(kLast, dys, ys), fmaf(kLast, dws, w)))) {
+            xs = fmaf(kStep, dxs, xs), ys = fmaf(kStep, dys, ys), w = fmaf(kStep, dws, w);
+            continue;
+          }
+        }
         float t[kUnroll];
 #pragma unroll
         for (int i = 0; i < kUnroll; ++i) {

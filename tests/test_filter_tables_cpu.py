@@ -82,6 +82,26 @@ def test_filter_never_rejects_a_ray_the_oracle_accepts(el, spacing, h, l, lo):
     fd = (np.abs(margins[2]) - np.maximum(np.abs(margins[0]), np.abs(margins[1])) >= 0)[:C].T  # (k, C)
     sel = ref.mask[col0 - lo: col0 - lo + len(k)]
     assert not (sel & ~fd).any(), "forward-differenced stage A rejected a ray the oracle accepts"
+    # hierarchical cull of the lattice kernel: a run (whole segment, then groups of 8 voxels) is skipped for a crystal
+    # point when |Xs| > |W| at both ends with Xs of one sign (or the same for Ys); end values by fmaf like the kernel
+    X, Y, W = margins
+
+    def culled(a, b):
+        xa, ya, wa = X[:, a], Y[:, a], W[:, a]
+        n = np.float32(b - a)
+        d = [(t["det_forms"][i][:, :3].astype(np.float32) @ dz).astype(np.float32) for i in range(3)]
+        xb, yb, wb = (xa + n * d[0]).astype(np.float32), (ya + n * d[1]).astype(np.float32), (wa + n * d[2]).astype(np.float32)
+        return ((np.abs(xa) > np.abs(wa)) & (np.abs(xb) > np.abs(wb)) & (xa * xb > 0)) | \
+               ((np.abs(ya) > np.abs(wa)) & (np.abs(yb) > np.abs(wb)) & (ya * yb > 0))
+
+    runs = [(0, len(k) - 1)] + [(a, a + 7) for a in range(0, len(k) - 7, 8)]
+    skipped = 0
+    for a, b in runs:
+        c = culled(a, b)[:C]  # (C,)
+        assert not (sel[a:b + 1] & c[None, :]).any(), f"run [{a},{b}] culled although the oracle accepts a ray in it"
+        assert not (fd[a:b + 1] & c[None, :]).any(), "a culled run holds a voxel that passes stage A"
+        skipped += int(c.sum())
+    assert skipped > 0.3 * C * len(runs)  # even in a column inside the visible region a good part of the pairs go
 
 
 def test_padding_lanes_never_pass():
