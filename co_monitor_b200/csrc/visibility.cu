@@ -338,12 +338,10 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       }
       __syncwarp();
     };
-    auto push = [&](int seg, int k, bool pass) {
+    auto push = [&](int seg, int k, bool pass) {  // branch-free: a predicated store and two popcounts
       const unsigned int b = __ballot_sync(0xffffffffu, pass);
-      if (b) {
-        if (pass) queue[qn + __popc(b & lt_mask)] = ((unsigned int)seg << 11) | ((unsigned int)k << 5) | (unsigned int)lane;
-        qn += __popc(b);
-      }
+      if (pass) queue[qn + __popc(b & lt_mask)] = ((unsigned int)seg << 11) | ((unsigned int)k << 5) | (unsigned int)lane;
+      qn += __popc(b);
     };
 
 #pragma unroll 1
@@ -389,6 +387,10 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
           while (qn >= 32) drain(32);
         }
       }
+      if (k < len && sc.filter_disabled == 0) {  // the ragged tail is one more run
+        const float n1 = (float)(len - 1 - k);
+        if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(n1, dxs, xs), fmaf(n1, dys, ys), fmaf(n1, dws, w)))) continue;
+      }
       for (; k < len; ++k) {
         const float t = fabsf(w) - fmaxf(fabsf(xs), fabsf(ys));
         xs += dxs, ys += dys, w += dws;
@@ -411,8 +413,8 @@ struct HitResult {
 
 // simulation.py:143-173 (+175-207): line through `dst` with direction src - dst against the aperture plane,
 // then the polygon test that replaces Delaunay.find_simplex (geometry_host.cu / apertures.py).
-__device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const double* __restrict__ edges, D3 src,
-                                                  D3 dst) {
+__device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const double* __restrict__ edges,
+                                                  const float* __restrict__ edges_f, float tau, D3 src, D3 dst) {
   const D3 N = ld3(ap.normal), u = src - dst;
   const double ndotu = dot(N, u);
   if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0, 0.0};  // the reference writes NaN -> never inside
@@ -420,6 +422,16 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
   const double si = -(dot(N, w) / ndotu);
   const D3 r = w + si * u;  // X - p1
   const double x = dot(r, ld3(ap.e1)), y = dot(r, ld3(ap.e2));
+  // The hit point is fp64 with the reference's arithmetic; only its distance to the polygon edges is first taken
+  // in FP32 (unit edge normals, |x|,|y| < 1e3 mm: good to ~1e-4 mm).  A point further than tau (>= 2e-3 mm) from
+  // every edge line is decided; anything closer is decided by the fp64 margins below.
+  {
+    const float xf = (float)x, yf = (float)y;
+    const float* ef = edges_f + 3 * ap.edge_offset;
+    float mf = 3.0e38f;
+    for (int k = 0; k < ap.n_edges; ++k) mf = fminf(mf, fmaf(ef[3 * k], xf, fmaf(ef[3 * k + 1], yf, ef[3 * k + 2])));
+    if (fabsf(mf) > tau) return {mf > 0.f, (double)mf, x, y};
+  }
   double m = 1e300;
   const double* e = edges + 3 * ap.edge_offset;
   for (int k = 0; k < ap.n_edges; ++k) m = fmin(m, e[3 * k] * x + e[3 * k + 1] * y + e[3 * k + 2]);
@@ -443,18 +455,25 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   // apertures + edge pool -> shared memory (a few kB)
   DevAperture* s_ap = reinterpret_cast<DevAperture*>(s_raw);
   double* s_edges = reinterpret_cast<double*>(s_raw + sizeof(DevAperture) * sc.n_apertures);
+  float* s_edges_f = reinterpret_cast<float*>(s_edges + 3 * sc.n_edges_total);
   {
     const double* src = reinterpret_cast<const double*>(sc.apertures);
     double* dst = reinterpret_cast<double*>(s_ap);
     const int n_ap_d = (int)(sizeof(DevAperture) / sizeof(double)) * sc.n_apertures;
     for (int i = threadIdx.x; i < n_ap_d; i += kExactThreads) dst[i] = src[i];
-    for (int i = threadIdx.x; i < 3 * sc.n_edges_total; i += kExactThreads) s_edges[i] = sc.edges[i];
+    for (int i = threadIdx.x; i < 3 * sc.n_edges_total; i += kExactThreads) {
+      const double v = sc.edges[i];
+      s_edges[i] = v;
+      s_edges_f[i] = (float)v;
+    }
   }
   __syncthreads();
 
   const int S = sc.n_slits;
   unsigned int n_pass = 0, n_edge = 0, n_vis = 0;
   const double kNear = sc.near_edge_mm;
+  // FP32 edge distances decide beyond this; twice the near-edge radius so that the near-edge count stays exact
+  const float tau = fmaxf(2.0e-3f, 2.f * (float)sc.near_edge_mm);
   const unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x;
   if (i < n) {
     const uint2 e = P.cand[i];
@@ -468,15 +487,15 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     const D3 reflected = c + r, plasma = c - d, crystal = p + d;
 
     bool near_edge = false;
-    HitResult h = aperture_hit(s_ap[2 * S], s_edges, plasma, crystal);  // port :372-384
+    HitResult h = aperture_hit(s_ap[2 * S], s_edges, s_edges_f, tau, plasma, crystal);  // port :372-384
     near_edge |= fabs(h.margin) < kNear;
     bool ok = h.pass;
     if (ok) {  // collimator :344-369, the same slit on both sides
       auto both_sides = [&](int k) {
-        const HitResult a = aperture_hit(s_ap[2 * k], s_edges, plasma, crystal);
+        const HitResult a = aperture_hit(s_ap[2 * k], s_edges, s_edges_f, tau, plasma, crystal);
         near_edge |= fabs(a.margin) < kNear;
         if (!a.pass) return false;
-        const HitResult b = aperture_hit(s_ap[2 * k + 1], s_edges, plasma, crystal);
+        const HitResult b = aperture_hit(s_ap[2 * k + 1], s_edges, s_edges_f, tau, plasma, crystal);
         near_edge |= fabs(b.margin) < kNear;
         return b.pass;
       };
@@ -487,7 +506,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
         bool try_neighbours = true;
         if (sc.slit_period_d > 0.0) {
           // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slit that can contain it
-          const HitResult h0 = aperture_hit(s_ap[0], s_edges, plasma, crystal);
+          const HitResult h0 = aperture_hit(s_ap[0], s_edges, s_edges_f, tau, plasma, crystal);
           if (h0.margin == -1e300) {
             k_hi = -1;  // parallel to the collimator plane: NaN in the reference
           } else {
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
       }
     }
     if (ok) {
-      h = aperture_hit(s_ap[2 * S + 1], s_edges, reflected, crystal);  // detector :387-400
+      h = aperture_hit(s_ap[2 * S + 1], s_edges, s_edges_f, tau, reflected, crystal);  // detector :387-400
       near_edge |= fabs(h.margin) < kNear;
       ok = h.pass;
     }
@@ -758,7 +777,7 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     // one thread per candidate slot; blocks beyond the actual count exit at once
     const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
     const unsigned int blocks = (unsigned int)std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, 0x7fffffffull);
-    const size_t smem = sizeof(DevAperture) * P.sc.n_apertures + sizeof(double) * 3 * P.sc.n_edges_total;
+    const size_t smem = sizeof(DevAperture) * P.sc.n_apertures + (sizeof(double) + sizeof(float)) * 3 * P.sc.n_edges_total;
     exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
   }
   COM_CUDA(cudaGetLastError());
