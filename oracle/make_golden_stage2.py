@@ -12,7 +12,8 @@ reference expects (``input_files/...`` relative to the CWD, SURVEY.md section 8(
 and stores what it produces as tests/golden/stage2_reference.npz (per-voxel columns keyed by
 ``idx_sel_plas_points``, the flux totals, the profile / FA / PEC tables at sampled points).
 
-    python oracle/make_golden_stage2.py
+    python oracle/make_golden_stage2.py                 # tests/golden/stage2_reference.npz
+    python oracle/make_golden_stage2.py --transitions   # tests/golden/stage2_transitions_reference.npz
 """
 from __future__ import annotations
 
@@ -66,12 +67,12 @@ def scratch_cwd() -> str:
     return tmp
 
 
-def run_emissivity(element, profiles, time="Test", concentration=2):
+def run_emissivity(element, profiles, time="Test", concentration=2, transitions=("EXCIT", "RECOM")):
     from co_monitor.emissivity.reader import Emissivity
 
     ion, wl = LINES[element]
     with contextlib.redirect_stdout(io.StringIO()):
-        em = Emissivity(element, ion, wl, concentration, ["EXCIT", "RECOM"], "Reff_coordinates-10_mm", profiles, time)
+        em = Emissivity(element, ion, wl, concentration, list(transitions), "Reff_coordinates-10_mm", profiles, time)
     df = em.df_prof_frac_ab_pec.sort_values("idx_sel_plas_points", kind="stable")
     return em, df
 
@@ -89,6 +90,44 @@ def pack(out, tag, em, df, stride=1):
     out[f"{tag}_colsum"] = arr.sum(axis=0)
     out[f"{tag}_total_str"] = np.array([em.total_emissivity])
     out[f"{tag}_reff_boundary"] = np.array([em.reff_boundary])
+
+
+OUT_TRANSITIONS = os.path.join(ROOT, "tests", "golden", "stage2_transitions_reference.npz")
+#: other transition lists the reference accepts: single transitions, a different order, and the charge-exchange block
+#: of the ADAS files, which reader.py:355-369 treats like EXCIT (its FA column logic only knows "RECOM" / else)
+TRANSITION_CASES = [("C", ("EXCIT",)), ("C", ("RECOM",)), ("C", ("EXCIT", "RECOM", "CHEXC")), ("O", ("RECOM", "EXCIT")),
+                    ("N", ("CHEXC",))]
+
+
+def main_transitions():
+    from co_monitor.emissivity.kinetic_profiles import TwoGaussSumProfile
+
+    tmp = scratch_cwd()
+    old = os.getcwd()
+    os.chdir(tmp)
+    out = {}
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            prof = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df
+        for el, trs in TRANSITION_CASES:
+            em, df = run_emissivity(el, prof, transitions=trs)
+            tag = f"{el}_{'_'.join(trs)}"
+            arr = df.to_numpy(dtype=float)
+            w = df["total_intensity_fraction"]
+            out[f"{tag}_columns"] = np.array(list(df.columns))
+            out[f"{tag}_nrows"] = np.array([len(arr)])
+            out[f"{tag}_rows"] = arr[::9]
+            out[f"{tag}_colsum"] = arr.sum(axis=0)
+            names = ["Emissivity_RECOM" if "RECOM" in t else f"Emissivity_{t}" for t in trs] + ["Emissivity_TOTAL"]
+            out[f"{tag}_flux"] = np.array([(df[n] * w).sum() for n in names])
+            out[f"{tag}_total_str"] = np.array([em.total_emissivity])
+            out[f"{tag}_reff_boundary"] = np.array([em.reff_boundary])
+            print(tag, len(df), em.total_emissivity)
+    finally:
+        os.chdir(old)
+        shutil.rmtree(tmp, ignore_errors=True)
+    np.savez_compressed(OUT_TRANSITIONS, **out)
+    print("wrote", OUT_TRANSITIONS, f"{os.path.getsize(OUT_TRANSITIONS)/1e6:.2f} MB", len(out), "arrays")
 
 
 def main():
@@ -158,4 +197,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--transitions" in sys.argv:
+        main_transitions()
+    else:
+        main()

@@ -119,6 +119,31 @@ def test_oracle_parity_random_reff_and_unsorted_profile(tmp_path):
         assert out["boundary"] == ref.reff_boundary
 
 
+@pytest.mark.parametrize("el,transitions", [("C", ("EXCIT",)), ("C", ("RECOM",)), ("C", ("EXCIT", "RECOM", "CHEXC")),
+                                            ("O", ("RECOM", "EXCIT")), ("N", ("CHEXC",))])
+def test_reference_parity_other_transition_lists(golden_dir, tmp_path, el, transitions):
+    """The drop-in with single transitions, a swapped order and the charge-exchange block - columns, rows, flux and the
+    total string of the unmodified reference (tests/golden/stage2_transitions_reference.npz)."""
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.emissivity.reader import Emissivity
+
+    gold = np.load(os.path.join(golden_dir, "stage2_transitions_reference.npz"))
+    tag = f"{el}_{'_'.join(transitions)}"
+    ion, wl = LINES[el]
+    em = Emissivity(el, ion, wl, 2, list(transitions), "Reff_coordinates-10_mm", TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df,
+                    output_dir=tmp_path, verbose=False)
+    df = em.df_prof_frac_ab_pec
+    assert list(df.columns) == list(gold[f"{tag}_columns"])
+    rows = df.sort_values("idx_sel_plas_points", kind="stable").to_numpy(dtype=float)
+    assert len(rows) == int(gold[f"{tag}_nrows"][0])
+    np.testing.assert_allclose(rows[::9], gold[f"{tag}_rows"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(rows.sum(axis=0), gold[f"{tag}_colsum"], rtol=1e-11)
+    flux = np.array([em.flux[t] for t in transitions] + [em.flux["TOTAL"]])
+    np.testing.assert_allclose(flux, gold[f"{tag}_flux"], rtol=RTOL)
+    assert em.total_emissivity == str(gold[f"{tag}_total_str"][0])
+    assert em.reff_boundary == float(gold[f"{tag}_reff_boundary"][0])
+
+
 def test_find_nearest_reference_unit_test():
     from co_monitor_b200.emissivity.reader import Emissivity
 
