@@ -461,9 +461,9 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if achieved else None,
-        "traffic": 1.04e5,
+        "traffic": 1.19e5,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/ "
-                        "(104 kB: geometry tables only; the lattice kernel reads no voxel data and writes 8 B per candidate via L2)",
+                        "(119 kB: geometry tables only; the lattice kernel reads no voxel data and writes 8 B per candidate via L2)",
         "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
                        f"register-only FMA probe measured {measured_peak:.1f} TFLOP/s on this GPU in this run",
         "measured_fp32_tflops": measured_peak,
@@ -482,6 +482,47 @@ def run_ours(args):
                 "figure is `issue_frac`: executed lane-instructions per second over the issue peak (ncu: 70-75 % issue-slot "
                 "utilisation while the kernel runs).",
     }
+
+    # ---- second roofline: the Stage-2 voxel pass (HBM bound; SURVEY.md 8(d): 10 B per voxel per channel) ----
+    # At the benchmark's 270 000 voxels per channel that pass is launch-latency bound, so it is measured here on a
+    # synthetic array of 5e8 voxels (5 GB, far beyond L2; a 0.65 mm grid has 9.8e8 per channel): uint16 Reff
+    # millimetres, fp64 weights of which ~89 % are zero like a real Stage-1 output.
+    roofline_stage2 = None
+    if not args.no_stage2_roofline:
+        n2 = 500_000_000
+        gen = torch.Generator(device=device).manual_seed(0)
+        r2 = torch.randint(0, 600, (n2,), dtype=torch.int32, device=device, generator=gen).to(torch.int16)
+        w2 = torch.rand(n2, dtype=torch.float64, device=device, generator=gen)
+        w2[torch.rand(n2, device=device, generator=gen) < 0.89] = 0.0
+        h2 = torch.zeros(_lib.COM_MM_BINS, dtype=torch.float64, device=device)
+        cur = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        times = []
+        for _ in range(7):
+            h2.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.com_weight_histogram_mm(C.c_void_p(r2.data_ptr()), C.c_void_p(w2.data_ptr()), n2, None,
+                                                   C.c_void_p(h2.data_ptr()), cur), "com_weight_histogram_mm")
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms2 = float(np.median(times[2:]))
+        want = torch.bincount(r2.to(torch.int64), weights=w2, minlength=_lib.COM_MM_BINS)[: _lib.COM_MM_BINS]
+        err2 = float(((h2 - want).abs().max() / want.abs().max()).item())
+        del r2, w2
+        hbm_peak, src = 6650.0, "fallback of B200_PROFILING.md"
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
+                hbm_peak, src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except (OSError, KeyError, ValueError):
+            pass
+        gbs = 10.0 * n2 / (ms2 * 1e-3) / 1e9
+        roofline_stage2 = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                           "traffic": None, "peak_source": src, "kernel": "com::weight_histogram_mm_kernel",
+                           "kernel_ms_per_launch": ms2, "voxels_per_launch": n2, "algorithmic_bytes_per_voxel": 10,
+                           "max_rel_err_vs_bincount": err2,
+                           "note": "the Stage-2 voxel pass on a synthetic 5e8-voxel channel (inputs larger than L2); in the "
+                                   "timed step above the same kernel runs on 270 000 voxels and is latency bound"}
 
     base = None
     if world == 1 and not args.no_cpu_baseline:
@@ -518,6 +559,7 @@ def run_ours(args):
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_stage2": roofline_stage2,
         "cpu_baseline": base,
     }
     print(json.dumps(out), flush=True)
@@ -531,6 +573,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage2-roofline", action="store_true", help="skip the HBM roofline leg of the Stage-2 voxel pass")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-graph-multi-gpu", action="store_true",
                     help="at N > 1 do not capture the step (NCCL all-reduces included) in a CUDA graph")
