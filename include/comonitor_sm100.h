@@ -71,7 +71,8 @@ typedef struct ComAperture {
  * verts[0..2].  verts is (n,3) row-major, 3 <= n <= 16. */
 int com_aperture_from_slab(const double* verts_h, int32_t n, const double* offset_h, ComAperture* out_h);
 
-/* Host-only helper (no CUDA): 1 if the point (global mm) passes the aperture test in fp64, else 0. */
+/* Host-only helper (no CUDA): 1 if the point (global mm) passes the aperture test in fp64, else 0.
+ * Replaces Simulation.check_in_hull for one point (simulation.py:234-271). */
 int com_aperture_contains(const ComAperture* ap_h, const double* point_h);
 
 /* The beam line of one spectroscopic channel, at the level of the reference's own arrays. */
@@ -111,9 +112,13 @@ typedef struct ComSceneDesc {
 
 typedef struct ComScene ComScene; /* opaque: device-resident tables of one channel */
 
+/* Uploads what Simulation.__init__ collects before the ray work starts (simulation.py:77-141: _init_collimator,
+ * _init_dispersive_element, _init_port, _init_detector) plus the slabs of make_spatial_object (:209-232) reduced to
+ * apertures; com_scene_destroy frees it. */
 int com_scene_create(const ComSceneDesc* desc_h, ComScene** out);
 int com_scene_destroy(ComScene* scene);
-/* number of apertures (2S+2, order: crys_0, plasma_0, crys_1, ..., port, detector) and a host copy of one */
+/* number of apertures (2S+2, order: crys_0, plasma_0, crys_1, ..., port, detector - the order of the 22 in-hull
+ * tests of check_ray_transmission, simulation.py:344-400) and a host copy of one */
 int com_scene_aperture_count(const ComScene* scene);
 int com_scene_get_aperture(const ComScene* scene, int32_t index, ComAperture* out_h);
 /* Extension (not in the reference; SURVEY.md 8(d) config 3 "per-pixel detector resolution"): while pix_out != NULL every
@@ -125,6 +130,7 @@ int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, i
                                  double y0_mm);
 
 /* Host-only (no CUDA): the FP32 filter tables com_scene_create would upload, for inspection and CPU-side tests.
+ * (No counterpart in the reference: the filter is a conservative pre-selection in front of simulation.py:327-432.)
  *   det_forms_out  [3][Cp][4] floats: forms Xs, Ys, W of the mirrored detector, value = g.p' + h with p' = p - origin
  *   slit_forms_out [Cp][6][4] floats: X', Y', W on the crystal-side slit plane, then on the plasma side
  *   rects_out      8 floats: xlo, xhi, ylo, yhi of the crystal-side and of the plasma-side slit rectangle (band included)
@@ -133,7 +139,8 @@ int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, i
 int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_padded, float* det_forms_out,
                                  float* slit_forms_out, float* rects_out, float* period_out, int32_t* flags_out);
 
-/* what the FP32 filter was built with (any output pointer may be NULL): whether the collimator was found periodic
+/* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
+ * are tested one by one, simulation.py:344-369): whether the collimator was found periodic
  * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled,
                           double* slit_period_mm, double* eps_mm);
@@ -182,11 +189,15 @@ typedef struct ComRayRecord {
   double weight;     /* contribution to total_intensity_fraction */
 } ComRayRecord;
 
-/* Bytes of scratch needed by com_visibility_weights for n voxels against this scene.
+/* Bytes of scratch needed by com_visibility_weights for n voxels against this scene (the candidate list: rays the FP32
+ * filter could not reject; the reference materialises all P x C rays instead, simulation.py:316-321).
  * candidate_fraction <= 0 selects the default (2 % of the rays, at least 1 Mi entries). */
 size_t com_visibility_workspace_bytes(const ComScene* scene, int64_t n_voxels, double candidate_fraction);
 
-/* Stage 1 on the voxels [vox_begin, vox_end).
+/* Stage 1 on the voxels [vox_begin, vox_end).  Replaces, per (voxel, crystal point) ray, calculate_radiation_reflection
+ * (simulation.py:273-325), find_intersection_points / line_plane_intersection (:143-207), check_in_hull (:234-271),
+ * check_ray_transmission (:327-432), calculate_indices (:434-481), calculate_distances (:483-504), calculate_angles
+ * (:506-536) and the per-ray weight and per-voxel sum of calculate_radiation_fraction (:538-577).
  *   lattice_h != NULL : voxel coordinates come from the implicit lattice (flat indices are lattice indices);
  *   vox_xyz   != NULL : (n_total,3) fp64 DEVICE array in global mm, indexed by the same flat index.
  * Outputs are indexed by (flat - vox_begin):
@@ -204,7 +215,8 @@ int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, c
                            const uint16_t* reff_bin, double* hist_out, int32_t n_bins, ComStats* stats_out,
                            void* workspace, size_t workspace_bytes, com_stream_t stream);
 
-/* Host-buffer variant (the reference-facing call): host in, host out, device work inside; synchronous.
+/* Host-buffer variant (the reference-facing call: everything Simulation.__init__ does after its _init_* methods,
+ * simulation.py:50-72): host in, host out, device work inside; synchronous.
  * vox_xyz_h may be NULL when lattice_h is given.  rays_out_h may be NULL.  Returns COM_E_EMPTY when no
  * ray passes (outputs are still valid: all zero). */
 int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
@@ -218,12 +230,13 @@ int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* latti
                              int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
                              int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h);
 
-/* The *_host calls keep one grow-only device block and one pinned staging block per calling thread between calls
+/* (No counterpart in the reference.)  The *_host calls keep one grow-only device block and one pinned staging block per calling thread between calls
  * (cudaMalloc and cudaFree synchronise the device) and run on the per-thread CUDA stream: they may be called
  * concurrently from several host threads (e.g. one channel per thread).  This frees the calling thread's blocks. */
 int com_host_arena_release(void);
 
-/* Compaction of the visible voxels (nrays > 0), ascending flat index: idx_out[i] = vox_begin + position,
+/* Compaction of the visible voxels (nrays > 0) - the group-by of calculate_radiation_fraction (simulation.py:564-577) -
+ * ascending flat index: idx_out[i] = vox_begin + position,
  * w_compact[i] = w[position].  *count_out (device u64).  idx_out / w_compact need room for n entries. */
 int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
                         double* w_compact, uint64_t* count_out, void* workspace, size_t workspace_bytes,
@@ -257,12 +270,18 @@ typedef struct ComTablesDesc {
 
 typedef struct ComTables ComTables; /* opaque: device-resident Stage-2 tables of one line */
 
+/* Uploads the tables Emissivity.__init__ builds before its per-voxel loops: FractionalAbundance.df_interpolated_frac_ab
+ * (fractional_abundance.py:59-91; reader.py:245-261) and, per transition, the ADAS block of PEC (pec.py:122-151) with
+ * its two linspace grids (pec.py:169-174) instead of the dense 2000 x 2000 table of _get_pec_data (reader.py:83-97). */
 int com_tables_create(const ComTablesDesc* desc_h, ComTables** out);
 int com_tables_destroy(ComTables* tables);
 
+/* scratch of com_emissivity_integrate / com_weight_histogram for n voxels (block partials of the flux sums that
+ * calculate_total_emissivity takes with DataFrame.sum(), reader.py:380-401) */
 size_t com_emissivity_workspace_bytes(int64_t n);
 
-/* Per-voxel pass == Emissivity.read_ne_te ... calculate_total_emissivity for n voxels.
+/* Per-voxel pass == Emissivity.read_ne_te (reader.py:199-243), find_closest_temp_idx / assign_temp_accodring_to_indexes
+ * (:282-314), read_pec (:316-341), calculate_intensity (:343-378), calculate_total_emissivity (:380-401) for n voxels.
  *   profile        DEVICE (K,3) row-major [Reff, T_e, n_e] (the reference's profiles_df column order)
  *   profile_sorted 1 when the Reff column is non-decreasing (binary search); 0 = literal linear argmin
  *   reff / reff_mm Reff in metres (NaN = outside the LCFS), or as uint16 millimetres (0xFFFF = NaN); exactly one
@@ -285,17 +304,21 @@ int com_emissivity_integrate(const ComTables* tables, const double* profile, int
                              double* per_voxel_out, uint8_t* valid_out, void* workspace, size_t workspace_bytes,
                              com_stream_t stream);
 
-/* Maximum finite Reff of the addressed voxels into max_out (DEVICE, 1 double); 0 when there is none. */
+/* Maximum finite Reff of the addressed voxels into max_out (DEVICE, 1 double); 0 when there is none: the
+ * "Max reff from mapped vmec" of read_ne_te (reader.py:210-212). */
 int com_reff_max(const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, int64_t n,
                  const uint64_t* n_device, double* max_out, com_stream_t stream);
 
-/* Host-buffer variant (the reference-facing call): everything host, synchronous. */
+/* Host-buffer variant (the reference-facing call: what Emissivity.__init__ does after get_plas_coords_with_rad_frac,
+ * reader.py:68-79): everything host, synchronous. */
 int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
                                   double concentration, const double* reff_h, const double* w_h, int64_t n,
                                   double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
                                   double* boundary_out_h);
 
-/* Factorised form for profile sweeps and very large grids: the flux only depends on the voxels through
+/* Factorised form for profile sweeps (the loop over time slices of co_monitor/emissivity/main.py:39-60, one Emissivity
+ * per slice) and very large grids: every quantity of reader.py:199-378 depends on the voxel only through its nearest
+ * profile row, so the flux (reader.py:380-401) depends on the voxels only through
  * H[k] = sum of w over the voxels whose nearest profile row is k.
  *   com_weight_histogram  one pass over the voxels (10 B/voxel with uint16 Reff), hist_out DEVICE (K) overwritten,
  *                         boundary_out DEVICE (1) or NULL
@@ -305,7 +328,8 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
                          const double* reff, const uint16_t* reff_mm, const int64_t* reff_index, const double* w,
                          int64_t n, const uint64_t* n_device, const double* mapped_reff_max, double* hist_out,
                          double* boundary_out, void* workspace, size_t workspace_bytes, com_stream_t stream);
-/* The two halves of the uint16 fast path, for pipelines that keep the millimetre histogram (e.g. to all-reduce it
+/* The two halves of the uint16 fast path (same reference lines as com_weight_histogram: the Reff cut of read_ne_te,
+ * reader.py:210-217 and 240-242, and its nearest-row lookup, :220-238), for pipelines that keep the millimetre histogram (e.g. to all-reduce it
  * over ranks: per-rank histograms simply add, and the Reff cut is then taken from the global one):
  *   com_weight_histogram_mm  hist_mm[min(reff_mm[v], COM_MM_BINS-1)] += w[v] for voxels with w != 0 and reff_mm != 0xFFFF;
  *                            hist_mm DEVICE (COM_MM_BINS) fp64, ACCUMULATED (clear it yourself); 16-byte aligned inputs
@@ -348,7 +372,7 @@ int com_write_stage1_csv(const char* path, const int64_t* idx, const double* x, 
                          const double* w, int64_t n, int32_t write_header, int32_t n_threads);
 int com_format_float_repr(double value, char* out, int32_t out_bytes);
 
-/* Measurement aid (not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
+/* Measurement aid (no counterpart in the reference; not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
  * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the
  * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 exact kernel
  * and the number of calls since the last enable. */
@@ -359,6 +383,8 @@ int com_kernel_timing_read(double* filter_ms, double* exact_ms, int64_t* launche
  * the denominator bench.py reports next to the nominal 148 x 128 x 2 x f_max.  < 0 on error. */
 double com_measure_fp32_tflops(void);
 
+/* Error text of the last failure on the calling thread / of a status code.  The reference raises Python exceptions and
+ * calls sys.exit("Not enough points to perform calculations!") (simulation.py:451-456): COM_E_EMPTY carries that text. */
 const char* com_last_error(void);
 const char* com_error_string(int code);
 int com_abi_version(void);
