@@ -122,6 +122,8 @@ class ComPecDesc(C.Structure):
         ("n_te", C.c_int32),
         ("n_grid", C.c_int32),
         ("use_fully_stripped", C.c_int32),
+        ("interpolation", C.c_int32),
+        ("reserved", C.c_int32),
         ("ne_nodes", C.POINTER(C.c_double)),
         ("te_nodes", C.POINTER(C.c_double)),
         ("table", C.POINTER(C.c_double)),

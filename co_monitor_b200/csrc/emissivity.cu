@@ -34,7 +34,7 @@ namespace com {
 constexpr int kMaxTransitions = 4;
 
 struct DevPec {
-  int n_ne, n_te, n_grid, use_stripped;
+  int n_ne, n_te, n_grid, use_stripped, loglog;
   const double* ne_nodes;
   const double* te_nodes;
   const double* table;  // (n_ne, n_te) row-major
@@ -132,6 +132,31 @@ __device__ __forceinline__ double pec_bilinear(const DevPec& p, double x, double
   return sp;
 }
 
+// Extension (COM_PEC_LOGLOG, not what the reference computes): bilinear interpolation of log PEC in (log ne, log Te)
+// through the ADAS nodes at the row's own (ne, Te), arguments clamped to the node range.  A cell with a non-positive
+// PEC value falls back to the linear form.
+__device__ __forceinline__ double pec_loglog(const DevPec& p, double ne, double te) {
+  const double x = fmin(fmax(ne, p.ne_nodes[0]), p.ne_nodes[p.n_ne - 1]);
+  const double y = fmin(fmax(te, p.te_nodes[0]), p.te_nodes[p.n_te - 1]);
+  auto cell = [](const double* nodes, int n, double q) {
+    int lo = 0, hi = n;  // upper_bound
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (nodes[mid] <= q) lo = mid + 1; else hi = mid;
+    }
+    return min(max(lo - 1, 0), n - 2);
+  };
+  const int i = cell(p.ne_nodes, p.n_ne, x), j = cell(p.te_nodes, p.n_te, y);
+  const double* c = p.table + (size_t)i * p.n_te + j;
+  const double c00 = c[0], c01 = c[1], c10 = c[p.n_te], c11 = c[p.n_te + 1];
+  if (!(c00 > 0.0 && c01 > 0.0 && c10 > 0.0 && c11 > 0.0 && p.ne_nodes[i] > 0.0 && p.te_nodes[j] > 0.0))
+    return pec_bilinear(p, x, y);
+  const double lx0 = log(p.ne_nodes[i]), lx1 = log(p.ne_nodes[i + 1]), ly0 = log(p.te_nodes[j]), ly1 = log(p.te_nodes[j + 1]);
+  const double u = (log(x) - lx0) / (lx1 - lx0), v = (log(y) - ly0) / (ly1 - ly0);
+  const double L = (1.0 - u) * (1.0 - v) * log(c00) + (1.0 - u) * v * log(c01) + u * (1.0 - v) * log(c10) + u * v * log(c11);
+  return exp(L);
+}
+
 struct RowEval {
   double fa_ion, fa_last;
   double pec[kMaxTransitions];
@@ -148,9 +173,13 @@ __device__ __forceinline__ void eval_row(const DevTables& T, double ne, double t
   const double ne2 = __dmul_rn(ne, ne);
   for (int t = 0; t < T.n_trans; ++t) {
     const DevPec& p = T.pec[t];
-    const int ie = nearest_first_sorted<1>(p.ne_grid, p.n_grid, ne);
-    const int it = nearest_first_sorted<1>(p.te_grid, p.n_grid, te);
-    r.pec[t] = pec_bilinear(p, p.ne_grid[ie], p.te_grid[it]);
+    if (p.loglog) {
+      r.pec[t] = pec_loglog(p, ne, te);
+    } else {
+      const int ie = nearest_first_sorted<1>(p.ne_grid, p.n_grid, ne);
+      const int it = nearest_first_sorted<1>(p.te_grid, p.n_grid, te);
+      r.pec[t] = pec_bilinear(p, p.ne_grid[ie], p.te_grid[it]);
+    }
     const double fa = p.use_stripped ? r.fa_last : r.fa_ion;
     r.emis[t] = __dmul_rn(__dmul_rn(__dmul_rn(fa, r.pec[t]), ne2), conc);
     r.total = t == 0 ? r.emis[0] : __dadd_rn(r.total, r.emis[t]);
@@ -472,7 +501,11 @@ static int build_tables_blob(const ComTablesDesc* d, std::vector<double>& blob, 
       com::set_error("Stage-2 tables: PEC block %d incomplete or not sorted", t);
       return COM_E_BADARG;
     }
-    dev.pec[t] = com::DevPec{p.n_ne, p.n_te, p.n_grid, p.use_fully_stripped, push(p.ne_nodes, p.n_ne),
+    if (p.interpolation != COM_PEC_REFERENCE && p.interpolation != COM_PEC_LOGLOG) {
+      com::set_error("Stage-2 tables: PEC block %d asks for unknown interpolation %d", t, p.interpolation);
+      return COM_E_BADARG;
+    }
+    dev.pec[t] = com::DevPec{p.n_ne, p.n_te, p.n_grid, p.use_fully_stripped, p.interpolation, push(p.ne_nodes, p.n_ne),
                              push(p.te_nodes, p.n_te), push(p.table, (size_t)p.n_ne * p.n_te),
                              push(p.ne_grid, p.n_grid), push(p.te_grid, p.n_grid)};
   }

@@ -33,7 +33,14 @@ def _device_f64(x, dev):
 class LineTables:
     """FA + PEC tables of (element, ion_state, wavelength, transitions) on the device."""
 
-    def __init__(self, element, ion_state, wavelength, transitions, input_root=None, interp_step=2000):
+    def __init__(self, element, ion_state, wavelength, transitions, input_root=None, interp_step=2000,
+                 pec_interpolation: str = "reference"):
+        """*pec_interpolation*: "reference" = what the reference does (linear interp2d on a 2000 x 2000 linspace table read
+        at the nearest node, pec.py:153-187 + reader.py:316-341); "loglog" = bilinear in log-log space through the ADAS
+        nodes at the row's own (ne, Te) - an extension, off by default, not comparable with reference output."""
+        if pec_interpolation not in ("reference", "loglog"):
+            raise ValueError("pec_interpolation must be 'reference' or 'loglog'")
+        self.pec_interpolation = pec_interpolation
         self._lib = _lib.load()
         self.element, self.ion_state, self.wavelength = element, ion_state, wavelength
         self.transitions = list(transitions)
@@ -60,6 +67,7 @@ class LineTables:
             p = d.pec[t]
             p.n_ne, p.n_te, p.n_grid = pec.ne_nodes_nr, pec.te_nodes_nr, pec.interp_step
             p.use_fully_stripped = 1 if "RECOM" in tr else 0  # reader.py:355: `if "RECOM" in pec`
+            p.interpolation = 1 if pec_interpolation == "loglog" else 0
             p.ne_nodes, p.te_nodes = hold(pec.ne_nodes), hold(pec.te_nodes)
             p.table = hold(pec.pec_data_array)
             p.ne_grid, p.te_grid = hold(pec.ne_grid), hold(pec.te_grid)
@@ -164,5 +172,7 @@ class LineTables:
 
 
 @lru_cache(maxsize=16)
-def cached_line_tables(element, ion_state, wavelength, transitions: tuple, input_root=None) -> LineTables:
-    return LineTables(element, ion_state, wavelength, list(transitions), input_root=input_root)
+def cached_line_tables(element, ion_state, wavelength, transitions: tuple, input_root=None,
+                       pec_interpolation: str = "reference") -> LineTables:
+    return LineTables(element, ion_state, wavelength, list(transitions), input_root=input_root,
+                      pec_interpolation=pec_interpolation)

@@ -18,6 +18,9 @@ Things kept exactly as the reference does them, because results depend on them:
 Deviations: the fractional-abundance file is found under both ``.txt`` and ``.dat``; a
 missing ``Reff_coordinates-<s>_mm`` file is synthesised by trilinear up-sampling of a shipped grid;
 ``pec_data`` (the 2 x 96 MB dense PEC arrays) is built only when somebody reads it.
+Extension, off by default: ``pec_interpolation="loglog"`` evaluates the PEC by bilinear interpolation in log-log space
+through the ADAS nodes at each row's own (ne, Te) instead of the reference's nearest node of a linearly interpolated
+2000 x 2000 table (pec.py:153-187); results then differ from the reference's by design.
 """
 from __future__ import annotations
 
@@ -53,6 +56,7 @@ class Emissivity:
         device=None,
         save=True,
         verbose=True,
+        pec_interpolation="reference",
     ):
         self._say = print if verbose else (lambda *a, **k: None)
         self._input_root = stage2_input_root(input_root)
@@ -75,7 +79,8 @@ class Emissivity:
         self.plas_coords_with_rad_frac = self.get_plas_coords_with_rad_frac(plot=False)
         self.df_sel_frac_ab = self.get_frac_ab()
 
-        self._tables = cached_line_tables(element, ion_state, wavelength, tuple(transitions), str(self._input_root))
+        self._tables = cached_line_tables(element, ion_state, wavelength, tuple(transitions), str(self._input_root),
+                                          pec_interpolation)
         self._run_device_pass()
         self.total_emissivity = self.calculate_total_emissivity()
         if save:

@@ -351,14 +351,17 @@ class VisibilityPlan:
 
 
 def make_channel(element: str, slits_number: int = 10, crystal_height_step: int = 20, crystal_length_step: int = 80,
-                 lattice: Lattice | None = None, **scene_kwargs) -> ChannelScene:
-    """Channel scene from the reference's setup classes (what ``Simulation.__init__`` collects, :77-141)."""
+                 lattice: Lattice | None = None, closing_side: str = "top closing side", **scene_kwargs) -> ChannelScene:
+    """Channel scene from the reference's setup classes (what ``Simulation.__init__`` collects, :77-141).
+
+    *closing_side*: the reference always simulates "top closing side" (simulation.py:91); the geometry database also
+    holds "bottom closing side" (collimator.py:57-68), selectable here."""
     from .collimator import Collimator
     from .detector import Detector
     from .dispersive_element import DispersiveElement
     from .port import Port
 
-    col = Collimator(element, "top closing side", slits_number)
+    col = Collimator(element, closing_side, slits_number)
     _, crys, plas = col.read_colim_coord()
     de = DispersiveElement(element, crystal_height_step, crystal_length_step)
     port, det = Port(), Detector(element)

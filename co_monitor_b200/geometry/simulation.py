@@ -74,6 +74,7 @@ class Simulation:
         output_dir=None,
         verbose=True,
         stage1_chunk=1 << 26,
+        closing_side="top closing side",
     ):
         self._say = print if verbose else (lambda *a, **k: None)
         self._say(f"\nInitializing element {element}.")
@@ -85,6 +86,7 @@ class Simulation:
         self.plot = plot
         self._device = device
         self._output_dir = output_dir
+        self.closing_side = closing_side  # the reference hard-codes the top one (simulation.py:91)
         self._rays = None
         self._selected = None
 
@@ -131,7 +133,7 @@ class Simulation:
         return self.mesh.outer_cube_mesh
 
     def _init_collimator(self):
-        self.collim = Collimator(self.element, "top closing side", self.slits_number)
+        self.collim = Collimator(self.element, self.closing_side, self.slits_number)
         self.collim_vector_front_back = self.collim.vector_front_back
         (
             self.collimator_spatial,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define COM_ABI_VERSION 1
+#define COM_ABI_VERSION 2
 
 #define COM_OK 0
 #define COM_E_BADARG (-1)   /* null pointer, bad size, inconsistent description            */
@@ -247,11 +247,18 @@ size_t com_compact_workspace_bytes(int64_t n);
  * Stage 2: line-emissivity integration (reader.py:199-401).
  * All tables are fp64 host arrays copied to the device by com_tables_create. */
 #define COM_MAX_TRANSITIONS 4
+#define COM_PEC_REFERENCE 0
+#define COM_PEC_LOGLOG 1
 
 typedef struct ComPecDesc {
   int32_t n_ne, n_te;        /* ADAS block size (24 x 24; B: 8 x 11), pec.py:122-151                           */
   int32_t n_grid;            /* interp_step = 2000, pec.py:169-174                                            */
   int32_t use_fully_stripped;/* 1 for RECOM (multiplies the last FA column), 0 otherwise (reader.py:355-369)  */
+  int32_t interpolation;     /* COM_PEC_REFERENCE (0): linear interp2d on the n_grid x n_grid linspace table, read at the
+                                nearest grid node (pec.py:153-187, reader.py:316-341) - the parity path.
+                                COM_PEC_LOGLOG (1), extension off by default: bilinear in (log ne, log Te) of log PEC
+                                through the ADAS nodes at the row's own (ne, Te), clamped to the node range            */
+  int32_t reserved;
   const double* ne_nodes;    /* (n_ne)                                                                        */
   const double* te_nodes;    /* (n_te)                                                                        */
   const double* table;       /* (n_ne, n_te) row-major PEC values                                             */

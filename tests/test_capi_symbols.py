@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "binding list and header disagree"
-    assert lib.com_abi_version() == 1
+    assert lib.com_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(lib):

@@ -207,13 +207,14 @@ def test_block_cyclic_shards_equal_the_unsharded_grid(sims):
     assert seen.all() and total_rays == PASSING_RAYS["C"]
 
 
-@pytest.mark.parametrize("el,spacing,h,l,slits,centre", [
-    ("O", 10, 20, 80, 10, 140000),   # class defaults of Simulation: 1600 crystal points (no golden file exists)
-    ("B", 15, 10, 10, 10, 40000),    # the reference's __main__ settings: 15 mm grid, 100 crystal points
-    ("N", 10, 30, 20, 4, 150000),    # fewer slits
-    ("C", 20, 7, 13, 10, 17000),     # odd crystal sampling: 91 points (padded warp)
+@pytest.mark.parametrize("el,spacing,h,l,slits,centre,side", [
+    ("O", 10, 20, 80, 10, 140000, "top closing side"),   # class defaults of Simulation: 1600 crystal points (no golden file)
+    ("B", 15, 10, 10, 10, 40000, "top closing side"),    # the reference's __main__ settings: 15 mm grid, 100 crystal points
+    ("N", 10, 30, 20, 4, 150000, "top closing side"),    # fewer slits
+    ("C", 20, 7, 13, 10, 17000, "top closing side"),     # odd crystal sampling: 91 points (padded warp)
+    ("C", 10, 30, 20, 10, 135000, "bottom closing side"),  # the collimator position the reference never selects
 ])
-def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre):
+def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre, side):
     """Ray-exact agreement with the NumPy/Qhull oracle on slabs of configurations that have no shipped golden file,
     with the FP32 filter on, and the same slab with the filter off (every ray through fp64)."""
     import contextlib
@@ -226,8 +227,8 @@ def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre):
 
     with contextlib.redirect_stdout(io.StringIO()):
         mesh = CuboidMesh(spacing)
-        scene = make_channel(el, slits, h, l, lattice=mesh.lattice)
-        brute = make_channel(el, slits, h, l, lattice=mesh.lattice, filter_eps_mm=1e30)
+        scene = make_channel(el, slits, h, l, lattice=mesh.lattice, closing_side=side)
+        brute = make_channel(el, slits, h, l, lattice=mesh.lattice, filter_eps_mm=1e30, closing_side=side)
     lat = mesh.lattice
     full = scene.visibility(lattice=lat)
     nr = full.nrays.cpu().numpy()
@@ -238,7 +239,7 @@ def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre):
     lo = max(0, c - 300)
     hi = min(lat.n_points, lo + 600)
     idx = np.arange(lo, hi)
-    osc = oracle.build_scene(el, slits, h, l)
+    osc = oracle.build_scene(el, slits, h, l, side=side)
     ref = oracle.run_chunk(osc, gs.voxel_mesh(gs.load_db(), spacing, flat_indices=idx))
     assert ref.nrays.sum() > 0
     assert np.array_equal(nr[lo:hi], ref.nrays)

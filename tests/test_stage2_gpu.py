@@ -348,3 +348,44 @@ def test_millimetre_bin_histogram_fast_path():
     keep = vis & (mm != 0xFFFF) & (mm / 1000.0 < b_fast)
     ref = np.bincount(mm[keep].astype(np.int64), weights=w[keep], minlength=539)[:539]
     np.testing.assert_allclose(fast.cpu().numpy(), ref, rtol=1e-12, atol=1e-300)
+
+
+def test_loglog_pec_extension(tmp_path):
+    """``pec_interpolation="loglog"`` (off by default, not reference behaviour): the kernel against its NumPy statement,
+    through the sweep entry point (flux and per-row arithmetic) and through the Emissivity drop-in."""
+    import torch
+
+    from co_monitor_b200.emissivity.engine import LineTables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.emissivity.pec import loglog_on_nodes
+    from co_monitor_b200.emissivity.reader import Emissivity
+
+    prof_df = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df
+    prof = prof_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy()
+    tables = LineTables("C", "Z5", 33.7, ["EXCIT", "RECOM"], pec_interpolation="loglog")
+    K = len(prof)
+    rng = np.random.default_rng(3)
+    hist = rng.uniform(0, 1e-6, K)
+    flux = tables.sweep(prof[None], torch.from_numpy(hist).cuda(), 0.02).cpu().numpy()[0]
+    te, ne = prof[:, 1], prof[:, 2]
+    fa = tables.fa.df_interpolated_frac_ab
+    j = np.abs(fa.iloc[:, 0].to_numpy()[None, :] - te[:, None]).argmin(axis=1)
+    fa_ion, fa_last = fa["Z5"].to_numpy()[j], fa.iloc[:, -1].to_numpy()[j]
+    want = []
+    for pec, f in zip(tables.pecs, (fa_ion, fa_last)):
+        val = loglog_on_nodes(pec.ne_nodes, pec.te_nodes, pec.pec_data_array, ne, te)
+        want.append(float((f * val * ne**2 * 0.02 * hist).sum()))
+    np.testing.assert_allclose(flux[:2], want, rtol=1e-12)
+    np.testing.assert_allclose(flux[2], want[0] + want[1], rtol=1e-12)
+    # the reference interpolation reads the nearest node of a linear table: same order of magnitude, not the same number
+    ref_tables = LineTables("C", "Z5", 33.7, ["EXCIT", "RECOM"])
+    ref_flux = ref_tables.sweep(prof[None], torch.from_numpy(hist).cuda(), 0.02).cpu().numpy()[0]
+    assert 0.5 < flux[2] / ref_flux[2] < 2.0 and flux[2] != ref_flux[2]
+    em = Emissivity("C", "Z5", 33.7, 2, ["EXCIT", "RECOM"], "Reff_coordinates-10_mm", prof_df, output_dir=tmp_path,
+                    verbose=False, pec_interpolation="loglog")
+    df = em.df_prof_frac_ab_pec
+    np.testing.assert_allclose(df["pec_EXCIT"].to_numpy(),
+                               loglog_on_nodes(tables.pecs[0].ne_nodes, tables.pecs[0].te_nodes, tables.pecs[0].pec_data_array,
+                                               df["n_e [m-3]"].to_numpy(), df["T_e [eV]"].to_numpy()), rtol=1e-12)
+    with pytest.raises(ValueError):
+        LineTables("C", "Z5", 33.7, ["EXCIT"], pec_interpolation="cubic")
