@@ -79,11 +79,23 @@ def calibrate_to_qhull(ap: _lib.ComAperture, vertices: np.ndarray, orientation_v
     return out
 
 
+_APERTURE_CACHE: dict = {}
+
+
 def build_apertures(slit_crys, slit_plasma, vector_front_back, port_vertices, port_ov, det_vertices, det_ov,
                     calibrate: bool = True):
-    """ctypes array of the 2S+2 apertures in the library's order plus the per-edge calibration shifts."""
+    """ctypes array of the 2S+2 apertures in the library's order plus the per-edge calibration shifts.
+
+    The calibration against SciPy costs about a second per channel; the result only depends on the vertex arrays, so it
+    is kept per process (a second ``Simulation`` of the same channel, or the four shards of a sweep, reuse it)."""
     S = len(slit_crys)
+    key = (bool(calibrate),) + tuple(np.ascontiguousarray(a, dtype=float).tobytes() for a in
+                                     (slit_crys, slit_plasma, vector_front_back, port_vertices, port_ov, det_vertices, det_ov))
+    hit = _APERTURE_CACHE.get(key)
     arr = (_lib.ComAperture * (2 * S + 2))()
+    if hit is not None:
+        C.memmove(arr, hit[0], len(hit[0]))
+        return arr, [s.copy() for s in hit[1]]
     shifts = []
     specs = []
     for k in range(S):
@@ -96,4 +108,6 @@ def build_apertures(slit_crys, slit_plasma, vector_front_back, port_vertices, po
         ap = aperture_polygon(verts, ov)
         shifts.append(calibrate_to_qhull(ap, verts, ov) if calibrate else np.zeros(ap.n_edges))
         C.memmove(C.byref(arr[i]), C.byref(ap), C.sizeof(ap))
+    if len(_APERTURE_CACHE) < 64:
+        _APERTURE_CACHE[key] = (bytes(arr), [np.array(s, dtype=float) for s in shifts])
     return arr, shifts

@@ -167,8 +167,21 @@ class CuboidMesh:
             shift=MESH_SHIFT.copy(),
         )
 
-    def points_at(self, flat_indices) -> np.ndarray:
-        """fp64 coordinates of the voxels with the given flat indices, shape (n, 3)."""
+    def points_at(self, flat_indices, threads: int | None = None) -> np.ndarray:
+        """fp64 coordinates of the voxels with the given flat indices, shape (n, 3).
+
+        Long index lists (the 1e7-1e8 visible voxels of a fine grid) are evaluated in blocks on a thread pool; every
+        row goes through the same NumPy operations, so the values do not depend on the blocking
+        (tests/test_host_setup.py)."""
+        flat_indices = np.asarray(flat_indices, dtype=np.int64)
+        block = 1 << 18
+        if flat_indices.ndim == 1 and len(flat_indices) > 2 * block and threads != 1:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+
+            parts = [flat_indices[i:i + block] for i in range(0, len(flat_indices), block)]
+            with ThreadPoolExecutor(threads or min(16, os.cpu_count() or 1)) as pool:
+                return np.concatenate(list(pool.map(lambda p: self.points_at(p, threads=1), parts)))
         lat = self.lattice
         ix, iy, iz = lat.unravel(flat_indices)
         raw = np.vstack(

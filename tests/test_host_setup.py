@@ -96,6 +96,14 @@ def test_mesh_bit_exact(gold, capsys):
     assert "Number of points in the considered volume: 270000 points." in capsys.readouterr().out
     lat = CuboidMesh(10).lattice
     assert (lat.nx, lat.ny, lat.nz) == (135, 80, 25)
+    # long index lists are evaluated in blocks on a thread pool: same values as in one piece, and as the reference
+    # mesh rows they address
+    fine = CuboidMesh(2)
+    idx = np.sort(np.random.default_rng(0).choice(fine.lattice.n_points, 700_000, replace=False))
+    assert np.array_equal(fine.points_at(idx), fine.points_at(idx, threads=1))
+    m10 = CuboidMesh(10)
+    every = np.arange(m10.lattice.n_points)
+    assert len(every) < 2 * (1 << 18) or np.array_equal(m10.points_at(every), m10.points_at(every, threads=1))
 
 
 def test_mesh_rejects_coarse_spacing():
