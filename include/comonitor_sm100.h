@@ -95,7 +95,7 @@ typedef struct ComSceneDesc {
   double refl_max;               /* max reflectivity                                                  */
   double aoi0;                   /* nominal angle of incidence, degrees                               */
   double refl_sigma;             /* 2.2                                                               */
-  double filter_eps_mm;          /* FP32 filter band; <=0 selects the default (2e-3 mm);
+  double filter_eps_mm;          /* FP32 filter band; <=0 selects the default (5e-3 mm);
                                     >= 1e30 disables the filter: every ray is evaluated in fp64       */
   const ComAperture* apertures_override; /* NULL, or 2S+2 apertures (crys_0, plasma_0, ..., port, detector)
                                     to use instead of the exact hull sections computed from the vertex lists.
