@@ -105,11 +105,11 @@ class ComStats(C.Structure):
         ("visible_voxels", C.c_uint64),
         ("candidate_capacity", C.c_uint64),
         ("overflow", C.c_uint64),
-        ("reserved", C.c_uint64),
+        ("certain_candidates", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
-        return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
+        return {name: int(getattr(self, name)) for name, _ in self._fields_ }
 
 
 COM_MAX_TRANSITIONS = 4
@@ -197,6 +197,7 @@ def _declare(lib):
     lib.com_histogram_rows.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, vp]
     lib.com_reff_resample.argtypes = [C.POINTER(ComLattice), i64, i64, vp, i64, i64, i64, vp, vp, vp]
     lib.com_reff_quadratic.argtypes = [C.POINTER(ComLattice), i64, i64, dp, C.c_double, vp, vp, vp]
+    lib.com_scene_filter_certain_host.argtypes = [C.POINTER(ComSceneDesc), vp]
     lib.com_write_stage1_csv.argtypes = [C.c_char_p, vp, dp, dp, dp, dp, i64, i32, i32]
     lib.com_format_float_repr.argtypes = [C.c_double, C.c_char_p, i32]
     lib.com_measure_fp32_tflops.restype = C.c_double
@@ -218,7 +219,7 @@ EXPORTED_SYMBOLS = [
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
-    "com_write_stage1_csv", "com_format_float_repr",
+    "com_write_stage1_csv", "com_format_float_repr", "com_scene_filter_certain_host",
 ]
 
 

@@ -313,6 +313,20 @@ int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_
   return COM_OK;
 }
 
+int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9) {
+  if (!desc_h || !out9) {
+    com::set_error("com_scene_filter_certain_host: null argument");
+    return COM_E_BADARG;
+  }
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  const com::SlitRect r[2] = {hs.dev.inner_crys, hs.dev.inner_plasma};
+  std::memcpy(out9, r, sizeof(r));
+  out9[8] = hs.dev.certain_mm;
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

@@ -296,6 +296,44 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   rect_of(p0, eps, xlo, xhi, ylo, yhi);
   dv.rect_plasma = SlitRect{(float)xlo, (float)xhi, (float)ylo, (float)yhi};
 
+  // Inner rectangles: the bounding rectangle shrunk until its four corners (hence, by convexity, all of it) are at
+  // least `safe` inside every edge of the polygon.  FP32 evaluation of the in-plane coordinates is good to ~1e-4 mm
+  //  and the slit polygons agree with slit 0's to 1e-4 mm (checked above): 2e-2 mm is ample.
+  const double safe = std::max(2e-2, 2.0 * dv.near_edge_mm);
+  dv.certain_mm = (float)safe;
+  auto inner_of = [&](const ComAperture& ap, double& ixlo, double& ixhi, double& iylo, double& iyhi) {
+    rect_of(ap, -safe, ixlo, ixhi, iylo, iyhi);
+    for (int it = 0; it < 4000 && ixlo < ixhi && iylo < iyhi; ++it) {
+      bool inside = true;
+      const double cx[4] = {ixlo, ixhi, ixhi, ixlo}, cy[4] = {iylo, iylo, iyhi, iyhi};
+      for (int k = 0; k < ap.n_edges && inside; ++k)
+        for (int c = 0; c < 4 && inside; ++c)
+          inside = ap.edge[k][0] * cx[c] + ap.edge[k][1] * cy[c] + ap.edge[k][2] >= safe;
+      if (inside) return true;
+      ixlo += 5e-3, ixhi -= 5e-3, iylo += 5e-3, iyhi -= 5e-3;
+    }
+    ixlo = 1.0, ixhi = -1.0, iylo = 1.0, iyhi = -1.0;  // no inner rectangle: shortcut off
+    return false;
+  };
+  {
+    double a = 1, b = -1, c2 = 1, d2 = -1;
+    // every slit must share slit 0's inner rectangle: take it from slit 0 and verify it on the others
+    bool okc = periodic && inner_of(c0, a, b, c2, d2);
+    dv.inner_crys = SlitRect{(float)a, (float)b, (float)c2, (float)d2};
+    bool okp = periodic && inner_of(p0, a, b, c2, d2);
+    dv.inner_plasma = SlitRect{(float)a, (float)b, (float)c2, (float)d2};
+    for (int k = 1; k < S && okc && okp; ++k)
+      for (int side = 0; side < 2; ++side) {
+        const ComAperture& ak = hs.apertures[2 * k + side];
+        const SlitRect& r = side ? dv.inner_plasma : dv.inner_crys;
+        const double cx[4] = {r.xlo, r.xhi, r.xhi, r.xlo}, cy[4] = {r.ylo, r.ylo, r.yhi, r.yhi};
+        for (int e = 0; e < ak.n_edges; ++e)
+          for (int c = 0; c < 4; ++c)
+            if (!(ak.edge[e][0] * cx[c] + ak.edge[e][1] * cy[c] + ak.edge[e][2] >= 0.5 * safe)) okc = false;
+      }
+    if (!okc || !okp) dv.inner_crys = dv.inner_plasma = SlitRect{1.f, -1.f, 1.f, -1.f};
+  }
+
   const int Cp = dv.n_crystal_padded;
   hs.det_forms.assign((size_t)4 * 3 * Cp, 0.f);
   hs.slit_forms.assign((size_t)4 * 6 * Cp, 0.f);

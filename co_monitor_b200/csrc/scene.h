@@ -35,6 +35,11 @@ struct DeviceScene {
   float slit_period;     // slit pitch along e1 (2 |vector_top_bottom|)
   float slit_inv_period;
   SlitRect rect_crys, rect_plasma;
+  // "certain pass" regions of the FP32 filter: rectangles inside the slit polygons whose every point is at least
+  // certain_mm inside.  A ray the filter finds in them on both sides of one slit skips the fp64 slit tests of the
+  // exact kernel (it could not fail them); xlo > xhi switches the shortcut off.
+  SlitRect inner_crys, inner_plasma;
+  float certain_mm;
   double slit_period_d;  // 0 when the collimator is not periodic (exact kernel then tries every slit)
   double origin[3];
   double area_pt, refl_max, aoi0, refl_sigma;

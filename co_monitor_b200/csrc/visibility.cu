@@ -80,6 +80,9 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, ~1 ulp: amp
 }
 
 constexpr int kSlitUnknown = 15;  // candidate records carry the slit the FP32 filter saw in 4 bits; 15 = not known
+constexpr int kSlitCertain = 0x100;  // stage_b: the ray is inside the inner rectangle of that slit on both sides
+constexpr unsigned int kCandCertain = 1u << 27;  // candidate record: the slit tests cannot fail (the exact kernel skips them)
+constexpr unsigned int kCandCrystalMask = kCandCertain - 1u;
 
 // Returns -1 when the ray misses every slit (band included), else the index of the slit it goes through on both
 // sides, or kSlitUnknown when that is ambiguous / not evaluated.  The exact kernel tries the hinted slit first.
@@ -96,15 +99,22 @@ __device__ __forceinline__ int stage_b(const DeviceScene& sc, const float4 p, in
   // slit index from the crystal side; the polygon of slit k sticks out below k*T by |xlo| < T, so k and k+1 are tried
   const float kf = floorf(xc * sc.slit_inv_period);
   int code = -1;
+  bool inner = false;
 #pragma unroll
   for (int dk = 0; dk < 2; ++dk) {
     const float k = kf + (float)dk;
     const float a = fmaf(-k, sc.slit_period, xc), b = fmaf(-k, sc.slit_period, xp);
     const bool ok = k >= 0.f && k < (float)sc.n_slits && a >= sc.rect_crys.xlo && a <= sc.rect_crys.xhi &&
                     b >= sc.rect_plasma.xlo && b <= sc.rect_plasma.xhi;
-    if (ok) code = code < 0 ? min((int)k, kSlitUnknown) : kSlitUnknown;
+    if (ok) {
+      inner = code < 0 && a >= sc.inner_crys.xlo && a <= sc.inner_crys.xhi && b >= sc.inner_plasma.xlo && b <= sc.inner_plasma.xhi;
+      code = code < 0 ? min((int)k, kSlitUnknown) : kSlitUnknown;
+    }
   }
-  return y_ok ? code : -1;
+  if (!y_ok) return -1;
+  inner = inner && code != kSlitUnknown && yc >= sc.inner_crys.ylo && yc <= sc.inner_crys.yhi &&
+          yp >= sc.inner_plasma.ylo && yp <= sc.inner_plasma.yhi;
+  return inner ? (code | kSlitCertain) : code;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -165,6 +175,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
         ent = queue[qn - take + lane];
         slit = sc.filter_disabled != 0 ? kSlitUnknown : stage_b(sc, s_tile[ent >> 5], ci - lane + (int)(ent & 31));
         keep = slit >= 0;
+        slit &= 0xF;
       }
       qn -= take;
       const unsigned int b = __ballot_sync(0xffffffffu, keep);
@@ -258,12 +269,30 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   const unsigned int lt_mask = (1u << lane) - 1u;
   int on = 0;  // warp-uniform number of pending survivors
   // append `count` (<= 32) pending survivors to the global candidate list: one atomic, one coalesced store
+  // certain candidates grow from the front of the list, the others from its back: the exact kernel then runs warps of
+  // one kind (a warp with a single uncertain lane would execute the tests the certain lanes skip anyway)
   auto flush = [&](int count) {
     __syncwarp();
-    unsigned long long pos0 = 0;
-    if (lane == 0) pos0 = atomicAdd(&P.counters[0], (unsigned long long)count);
-    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-    if (lane < count && pos0 + lane < P.cand_capacity) P.cand[pos0 + lane] = outq[lane];
+    const uint2 mine = outq[min(lane, 63)];
+    const bool is_c = lane < count && (mine.y & kCandCertain) != 0u;
+    const unsigned int bc = __ballot_sync(0xffffffffu, is_c);
+    const int nc = __popc(bc), nu = count - nc;
+    unsigned long long posc = 0, posu = 0;
+    if (lane == 0) {
+      if (nc) posc = atomicAdd(&P.counters[0], (unsigned long long)nc);
+      if (nu) posu = atomicAdd(&P.counters[2], (unsigned long long)nu);
+    }
+    posc = __shfl_sync(0xffffffffu, posc, 0);
+    posu = __shfl_sync(0xffffffffu, posu, 0);
+    if (lane < count) {
+      if (is_c) {
+        const unsigned long long pos = posc + __popc(bc & lt_mask);
+        if (pos < P.cand_capacity) P.cand[pos] = mine;
+      } else {
+        const unsigned long long pos = posu + (lane - __popc(bc & lt_mask));
+        if (pos < P.cand_capacity) P.cand[P.cand_capacity - 1ull - pos] = mine;
+      }
+    }
     const uint2 carry = outq[min(lane + count, 63)];
     __syncwarp();
     if (lane + count < on) outq[lane] = carry;
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
     int qn = 0;
     auto drain = [&](int take) {
       __syncwarp();
-      bool keep = false;
+      bool keep = false, certain = false;
       unsigned int ent = 0;
       int vloc = 0, slit = -1;
       if (lane < take) {
@@ -324,15 +353,19 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
         const float kf = (float)k;
         const float4 p = make_float4(fmaf(kf, P.dz[0], b.x), fmaf(kf, P.dz[1], b.y), fmaf(kf, P.dz[2], b.z), 1.f);
         vloc = segs[seg].x + k;
-        slit = sc.filter_disabled != 0 ? kSlitUnknown : stage_b(sc, p, cg * 32 + (int)(ent & 31));
+        const int cj = cg * 32 + (int)(ent & 31);
+        slit = sc.filter_disabled != 0 ? kSlitUnknown : stage_b(sc, p, cj);
         keep = slit >= 0;
+        certain = keep && (slit & kSlitCertain) != 0;  // well inside its slit on both sides
+        slit &= 0xF;
       }
       qn -= take;
       const unsigned int bal = __ballot_sync(0xffffffffu, keep);
       if (bal) {
         if (keep)
           outq[on + __popc(bal & lt_mask)] =
-              make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)) | ((unsigned int)slit << 28));
+              make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)) | (certain ? kCandCertain : 0u) |
+                                                 ((unsigned int)slit << 28));
         on += __popc(bal);
         if (on >= 32) flush(32);
       }
@@ -443,10 +476,13 @@ constexpr int kExactThreads = 256;
 __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_constant__ K1Params P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const DeviceScene& sc = P.sc;
-  const unsigned long long n = min(P.counters[0], P.cand_capacity);
+  // front region (certain first, or everything from the explicit-voxel kernel) and back region (uncertain)
+  const unsigned long long n_front = min(P.counters[0], P.cand_capacity);
+  const unsigned long long n_back = min(P.counters[2], P.cand_capacity - n_front);
+  const unsigned long long n = n_front + n_back;
   if ((unsigned long long)blockIdx.x * kExactThreads >= n) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      P.stats->candidates = P.counters[0];
+      P.stats->candidates = P.counters[0] + P.counters[2];
       P.stats->candidate_capacity = P.cand_capacity;
       P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
     }
@@ -476,9 +512,10 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const float tau = fmaxf(2.0e-3f, 2.f * (float)sc.near_edge_mm);
   const unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x;
   if (i < n) {
-    const uint2 e = P.cand[i];
+    const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
     const long long vloc = e.x;
-    const int ci = (int)(e.y & 0x0fffffffu), slit_hint = (int)(e.y >> 28);
+    const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
+    const bool certain = (e.y & kCandCertain) != 0u;  // K1a found the ray >= certain_mm inside one slit on both sides
     const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
     const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
     // simulation.py:309-321
@@ -490,7 +527,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     HitResult h = aperture_hit(s_ap[2 * S], s_edges, s_edges_f, tau, plasma, crystal);  // port :372-384
     near_edge |= fabs(h.margin) < kNear;
     bool ok = h.pass;
-    if (ok) {  // collimator :344-369, the same slit on both sides
+    if (ok && !certain) {  // collimator :344-369, the same slit on both sides
       auto both_sides = [&](int k) {
         const HitResult a = aperture_hit(s_ap[2 * k], s_edges, s_edges_f, tau, plasma, crystal);
         near_edge |= fabs(a.margin) < kNear;
@@ -592,8 +629,9 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->near_edge_rays, (unsigned long long)s_acc[1]);
     if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[2]);
     if (blockIdx.x == 0) {
-      const unsigned long long total = P.counters[0];
+      const unsigned long long total = P.counters[0] + P.counters[2];
       P.stats->candidates = total;
+      P.stats->certain_candidates = (P.sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
       P.stats->candidate_capacity = P.cand_capacity;
       P.stats->overflow = total > P.cand_capacity ? 1 : 0;
       P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;

@@ -128,7 +128,11 @@ class ChannelScene:
         _lib.check(self._lib.com_scene_filter_tables_host(
             C.byref(self.desc), C.byref(cp), C.c_void_p(det.ctypes.data), C.c_void_p(slit.ctypes.data),
             C.c_void_p(rects.ctypes.data), C.byref(period), flags), "com_scene_filter_tables_host")
+        cert = np.zeros(9, np.float32)
+        _lib.check(self._lib.com_scene_filter_certain_host(C.byref(self.desc), C.c_void_p(cert.ctypes.data)),
+                   "com_scene_filter_certain_host")
         return dict(det_forms=det, slit_forms=slit, rect_crys=rects[:4], rect_plasma=rects[4:], period=period.value,
+                    inner_crys=cert[:4], inner_plasma=cert[4:8], certain_mm=float(cert[8]),
                     slit_filter=bool(flags[0]), same_w=bool(flags[1]), disabled=bool(flags[2]),
                     origin=np.array(list(self.desc.origin)))
 
@@ -247,7 +251,6 @@ class ChannelScene:
                     C.c_void_p(stats_t.data_ptr()), C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream))
                 _lib.check(rc, "com_visibility_weights")
                 stats = dict(zip([f[0] for f in _lib.ComStats._fields_], stats_t.cpu().tolist()))
-                stats.pop("reserved", None)
                 if not stats["overflow"]:
                     break
                 if hist is not None:
@@ -346,7 +349,6 @@ class VisibilityPlan:
 
     def stats(self) -> dict:
         out = dict(zip([f[0] for f in _lib.ComStats._fields_], self._stats.cpu().tolist()))
-        out.pop("reserved", None)
         return out
 
 

@@ -139,6 +139,13 @@ int com_scene_set_detector_image(ComScene* scene, double* pix_out, int32_t nx, i
 int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_padded, float* det_forms_out,
                                  float* slit_forms_out, float* rects_out, float* period_out, int32_t* flags_out);
 
+/* Host-only (no CUDA): the "certain pass" regions of the filter.  out9 = xlo, xhi, ylo, yhi of the inner rectangle of
+ * the crystal-side slit polygon, the same for the plasma side (every point of them is >= out9[8] mm inside the
+ * polygon; xlo > xhi: shortcut off), then that distance, max(2e-2, 2 near_edge_mm).  A candidate the FP32 filter finds
+ * inside both rectangles of one slit skips the two fp64 slit tests of the exact kernel - they could not fail
+ * (check_ray_transmission, simulation.py:344-369, would find it in that slit); port and detector are still tested. */
+int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9);
+
 /* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
  * are tested one by one, simulation.py:344-369): whether the collimator was found periodic
  * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
@@ -177,7 +184,8 @@ typedef struct ComStats {
   uint64_t visible_voxels;  /* voxels with >= 1 passing ray                                          */
   uint64_t candidate_capacity; /* capacity the launch ran with                                       */
   uint64_t overflow;        /* != 0: candidates > capacity, results incomplete (COM_E_OVERFLOW)      */
-  uint64_t reserved;
+  uint64_t certain_candidates; /* candidates the filter found >= 2e-2 mm inside one slit on both sides: the exact
+                                  kernel skips the slit tests for them (lattice kernel only)               */
 } ComStats;
 
 /* One passing ray (optional output): what the reference keeps per selected ray

@@ -24,6 +24,29 @@ def stage_a(t, p):
     return np.abs(w) - np.maximum(np.abs(xs), np.abs(ys)) >= 0
 
 
+def certain(t, p, n_slits):
+    """The filter's "certain pass" flag (float32, as stage B of the lattice kernel computes it): inside the inner
+    rectangle of exactly one slit on both sides."""
+    s = t["slit_forms"]
+    Xc, Yc, Wc, Xp, Yp = (forms(s[:, i], p) for i in range(5))
+    Wp = Wc if t["same_w"] else forms(s[:, 5], p)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xc, yc, xp, yp = Xc / Wc, Yc / Wc, Xp / Wp, Yp / Wp
+    rc, rp, ic, ip = t["rect_crys"], t["rect_plasma"], t["inner_crys"], t["inner_plasma"]
+    T = np.float32(t["period"])
+    kf = np.floor(xc / T)
+    hits = np.zeros(xc.shape, np.int32)
+    inner = np.zeros(xc.shape, bool)
+    for dk in (0, 1):
+        k = kf + dk
+        a, b = xc - k * T, xp - k * T
+        ok = (k >= 0) & (k < n_slits) & (a >= rc[0]) & (a <= rc[1]) & (b >= rp[0]) & (b <= rp[1])
+        inner |= ok & (hits == 0) & (a >= ic[0]) & (a <= ic[1]) & (b >= ip[0]) & (b <= ip[1])
+        hits += ok
+    inner &= (hits == 1) & (yc >= ic[2]) & (yc <= ic[3]) & (yp >= ip[2]) & (yp <= ip[3])
+    return inner & ~(np.minimum(np.abs(Wc), np.abs(Wp)) < 1e-3)
+
+
 def stage_b(t, p, n_slits):
     s = t["slit_forms"]
     Xc, Yc, Wc, Xp, Yp = (forms(s[:, i], p) for i in range(5))
@@ -60,6 +83,12 @@ def test_filter_never_rejects_a_ray_the_oracle_accepts(el, spacing, h, l, lo):
     b = stage_b(t, p, 10)[:C].T
     assert not (ref.mask & ~a).any(), "stage A rejected a ray the oracle accepts"
     assert not (ref.mask & ~b).any(), "stage B rejected a ray the oracle accepts"
+    # "certain" candidates skip the fp64 slit tests of the exact kernel: the oracle must find every one of them going
+    # through the collimator (port and detector are still tested), and most candidates should be certain
+    cert = certain(t, p, 10)[:C].T & a & b
+    through, port, det = oracle.transmission(osc, *ref.geometry, parts=True)
+    assert not (cert & ~through).any(), "a ray flagged certain fails the collimator in the oracle"
+    assert cert.sum() > 0.5 * (a & b).sum()
     # the filter is also selective: few rays beyond the accepted ones survive both stages
     survivors = (a & b).sum()
     assert ref.mask.sum() <= survivors <= 1.3 * ref.mask.sum() + 50
