@@ -456,10 +456,10 @@ def run_ours(args):
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     peak = nominal_fp32_tflops(sm_max)
     # Hardware-side figure next to the canonical one: lane-instructions actually executed per test, taken from the
-    # committed ncu capture of this kernel on this workload (profiles/r1b_ncu_full_summary_k1.txt: warp instructions x
+    # committed ncu capture of this kernel on this workload (profiles/r1c_ncu_full_summary_k1.txt: warp instructions x
     # active threads per instruction / 1.62e8 tests, mean of the four channels), against the issue peak
     # 148 SM x 4 schedulers x 32 lanes x f_max.
-    LANE_INSTR_PER_TEST = 10.5
+    LANE_INSTR_PER_TEST = 11.3
     issue_peak = 148 * 4 * 32 * sm_max * 1e6
     issue_frac = (tests_per_launch / (filter_ms * 1e-3)) * LANE_INSTR_PER_TEST / issue_peak if filter_ms > 0 else None
     roofline = {
