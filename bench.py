@@ -227,7 +227,8 @@ def run_ours(args):
     full_lattice = refined_lattice(world)
     P = full_lattice.n_points
     # block-cyclic shard of the z-columns: the visible voxels are spatially clustered, contiguous ranges would not balance
-    lattice = full_lattice.shard(world, rank, cols_per_block=8)
+    cols_per_block = int(os.environ.get("COM_BENCH_COLS_PER_BLOCK", "8"))
+    lattice = full_lattice.shard(world, rank, cols_per_block=cols_per_block)
     lo, hi = 0, lattice.n_points
     # Reff of every lattice voxel: the shipped 15 mm VMEC grid resampled onto the lattice (no VMEC service here),
     # re-ordered to this shard's local voxel order
@@ -539,7 +540,7 @@ def run_ours(args):
         "config": {
             "workload": f"configs[1]: B/C/N/O, Stage 1 (visibility + weight) then Stage 2 (EXCIT + RECOM emissivity -> flux), "
                         f"10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} ({P} voxels, {hi - lo} per GPU, "
-                        f"block-cyclic shards of 8 z-columns) "
+                        f"block-cyclic shards of {cols_per_block} z-columns) "
                         f"x {H}x{L} crystal points x {SLITS} slits, Reff = shipped 15 mm VMEC grid resampled",
             "tests_per_step": tests_per_step_rank * world,
             "l2": "256 MB buffer written between timed steps (L2 flushed, untimed)",
