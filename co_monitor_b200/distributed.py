@@ -1,10 +1,12 @@
-"""Multi-GPU plumbing: voxel-range sharding and the single reduce of the path.
+"""Multi-GPU plumbing: sharding helpers and the single reduce of the path.
 
-Stage 1 is independent per voxel and Stage 2 is a sum over voxels, so the path shards by contiguous ranges of
-the flat voxel index (z-fastest lattice order keeps every shard a slab of whole y-planes) with *no* data-path
-collective.  The only exchange is one all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests) of a
-packed fp64 buffer - per-channel flux, Reff-bin weight histograms, weight sums - and of the int64 counters.
-Per-voxel weight arrays stay sharded on their ranks.
+Stage 1 is independent per voxel and Stage 2 is a sum over voxels, so the path shards by voxels with *no* data-path
+collective in Stage 1.  The production shards are block-cyclic over the lattice's z-columns (``Lattice.shard``,
+``ComLattice.shard_*``: the visible voxels are spatially clustered, contiguous ranges do not balance);
+``shard_range`` is the contiguous split, used for explicit voxel arrays and in tests.  The only exchange is one
+all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests) of a packed fp64 buffer - the Reff-millimetre
+weight histograms from which every rank then evaluates Stage 2, weight sums - and of the int64 counters.  Per-voxel
+weight arrays stay sharded on their ranks.  tests/test_distributed_gloo.py runs both forms on two CPU ranks.
 """
 from __future__ import annotations
 

@@ -71,3 +71,97 @@ def test_two_rank_reduce_equals_unsharded(tmp_path):
         assert list(r["counters"]) == [int(n.sum()), int((n > 0).sum()), hi - lo]
     assert np.array_equal(np.concatenate((r0["shard_w"], r1["shard_w"])), w)  # per-voxel data stays sharded
     assert n.sum() > 100
+
+
+# ---- the production exchange: block-cyclic shards, one all-reduce of the Reff-millimetre histogram, Stage 2 from it ----
+SPACING, H, L = 20, 12, 10  # 67 x 40 x 12 = 32 160 voxels x 120 crystal points: seconds for the CPU oracle
+NE_MAIN = [7e13, 0, 0.37, 9.8e12, 0.5, 0.11]
+TE_MAIN = [1870, 0, 0.155, 210, 0.38, 0.07]
+WINDOW = (14000, 20000)  # local voxel range per rank that holds visible voxels
+
+
+def _shard_weights(rank, world):
+    """Oracle Stage 1 on a window of this rank's block-cyclic shard: global indices, weights."""
+    import contextlib
+    import io
+
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from oracle import geometry_setup as gs
+    from oracle import stage1 as o1
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        full = CuboidMesh(SPACING).lattice
+    lat = full.shard(world, rank, cols_per_block=8)
+    lo, hi = (WINDOW[0] // world, WINDOW[1] // world)
+    glob = lat.local_to_global(np.arange(lo, min(hi, lat.n_points)))
+    scene = o1.build_scene("C", 10, H, L)
+    res = o1.run_chunk(scene, gs.voxel_mesh(gs.load_db(), SPACING, flat_indices=glob))
+    return full, glob, res.weight
+
+
+def _mm_histogram(glob, w, reff_all, bins=4096):
+    mm = np.rint(reff_all[glob] * 1000.0)
+    keep = np.isfinite(mm) & (w != 0)
+    return np.bincount(mm[keep].astype(np.int64), weights=w[keep], minlength=bins)[:bins]
+
+
+def _flux_from_histogram(hist):
+    """Stage 2 from the millimetre histogram with the oracle's own per-voxel arithmetic: one pseudo-voxel per
+    non-empty bin, Reff = bin / 1000, weight = H[bin] (what com_histogram_rows + com_emissivity_sweep compute)."""
+    from oracle import stage2 as o2
+
+    bins = np.flatnonzero(hist)
+    observed = np.column_stack((np.arange(len(bins)), np.zeros((len(bins), 3)), hist[bins]))
+    res = o2.emissivity("C", "Z5", 33.7, 2, ["EXCIT", "RECOM"], o2.two_gauss_profile(NE_MAIN, TE_MAIN), observed, bins / 1000.0)
+    return np.array([res.flux["EXCIT"], res.flux["RECOM"], res.flux["TOTAL"]]), res.reff_boundary
+
+
+def _reff20():
+    from co_monitor_b200.geometry.reff import load_reff
+
+    return load_reff(SPACING)["Reff [m]"].to_numpy(dtype=float)
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, glob, w = _shard_weights(rank, world)
+    res = PackedResults()
+    res.add("hist_mm", _mm_histogram(glob, w, _reff20()))
+    res.count("visible_voxels", int((w != 0).sum()))
+    res.all_reduce()  # the single exchange of the path
+    flux, boundary = _flux_from_histogram(res.floats["hist_mm"])  # every rank evaluates Stage 2 from the global histogram
+    np.savez(os.path.join(out_dir, f"x{rank}.npz"), flux=flux, boundary=boundary, glob=glob, w=w,
+             visible=res.counters["visible_voxels"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_cyclic_shards_and_histogram_exchange(tmp_path):
+    """Two ranks, block-cyclic shards of the z-columns, one all-reduce of the 4096-bin histogram, Stage 2 from the reduced
+    histogram on every rank == the per-voxel Stage-2 oracle on the union of the shards (the multi-GPU path of bench.py and
+    scripts/volume_flux.py, with the CPU oracle standing in for the kernels)."""
+    import torch.multiprocessing as mp
+
+    from oracle import stage2 as o2
+
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(tmp_path / f"x{r}.npz") for r in (0, 1))
+    glob = np.concatenate((r0["glob"], r1["glob"]))
+    w = np.concatenate((r0["w"], r1["w"]))
+    assert len(np.unique(glob)) == len(glob)  # the shards do not overlap
+    vis = w != 0
+    assert vis.sum() > 50 and int(r0["visible"]) == int(r1["visible"]) == int(vis.sum())
+    # reference: per-voxel Stage 2 on the union (rows ordered by voxel index, as a Stage-1 file would hold them)
+    order = np.argsort(glob[vis])
+    observed = np.column_stack((glob[vis][order], np.zeros((vis.sum(), 3)), w[vis][order]))
+    ref = o2.emissivity("C", "Z5", 33.7, 2, ["EXCIT", "RECOM"], o2.two_gauss_profile(NE_MAIN, TE_MAIN), observed, _reff20())
+    want = np.array([ref.flux["EXCIT"], ref.flux["RECOM"], ref.flux["TOTAL"]])
+    assert want[2] > 0
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["flux"], want, rtol=1e-12)
+        assert float(r["boundary"]) == ref.reff_boundary
