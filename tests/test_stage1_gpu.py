@@ -213,6 +213,8 @@ def test_block_cyclic_shards_equal_the_unsharded_grid(sims):
     ("N", 10, 30, 20, 4, 150000, "top closing side"),    # fewer slits
     ("C", 20, 7, 13, 10, 17000, "top closing side"),     # odd crystal sampling: 91 points (padded warp)
     ("C", 10, 30, 20, 10, 135000, "bottom closing side"),  # the collimator position the reference never selects
+    ("C", 10, 30, 20, 1, 135000, "top closing side"),    # a single slit: no period to exploit
+    ("O", 10, 30, 20, 18, 145000, "top closing side"),   # more slits than the 4-bit slit hint of a candidate can name
 ])
 def test_other_configurations_against_oracle(el, spacing, h, l, slits, centre, side):
     """Ray-exact agreement with the NumPy/Qhull oracle on slabs of configurations that have no shipped golden file,
