@@ -1,18 +1,20 @@
 // Stage 1 on sm_100a: visibility + geometric weight of every (voxel, crystal point) ray.
 //
-//   K1a  filter_kernel   FP32, all P*C rays.  One warp = 32 crystal points (their detector-cone faces live
-//                        in registers), looping over a tile of voxels broadcast from shared memory.  A ray
-//                        survives stage A when the voxel lies inside the crystal point's mirrored-detector
-//                        cone (3 FFMA per cone face, nothing else); survivors are compacted through a per-warp
-//                        shared-memory queue (ballot + popc) and, 32 at a time, pushed through the periodic
-//                        collimator (both sides) and the port polygon (stage B).  Every comparison carries a
-//                        band eps, so the filter can only over-accept.  Survivors go to a global candidate list.
-//   K1b  exact_kernel    fp64, candidates only (~0.5 % of the rays).  Restates the reference arithmetic ray by
-//                        ray (simulation.py:143-173, 273-325, 344-428, 483-536, 564-577): per-slit plane hits,
-//                        exact polygon tests, distance, AOI with round(deg, 2), weight; accumulates per voxel.
+//   K1a  filter_kernel_lattice / filter_kernel   FP32, all P*C rays.  One warp = 32 crystal points, each lane holding
+//        the three linear forms (Xs, Ys, W) of its point's mirrored detector: a ray can only reach the detector when
+//        max(|Xs|, |Ys|) <= |W| (stage A; band eps folded into the forms).  The lattice kernel walks z-runs of the
+//        implicit lattice with forward differences (3 FADD per ray) and skips whole runs from the linearity of the
+//        forms; the explicit-voxel kernel evaluates the forms on tiles of voxels staged in shared memory.  Survivors
+//        are compacted through a per-warp shared-memory queue (ballot + popc) and, 32 at a time, tested against the
+//        periodic collimator on both sides (stage B: bounding rectangles grown by eps, so the filter can only
+//        over-accept).  What is left goes to a global candidate list, flagged "certain" when it lies well inside one
+//        slit on both sides.
+//   K1b  exact_kernel   fp64, candidates only (~0.5 % of the rays).  Restates the reference arithmetic ray by ray
+//        (simulation.py:143-173, 273-325, 344-428, 483-536, 564-577): plane hits, polygon tests for port, slit (skipped
+//        for "certain" candidates) and detector, distance, AOI with round(deg, 2), weight; accumulates per voxel.
 //
-// The visibility mask is therefore decided in fp64 for every ray the reference could accept; the FP32 pass
-// only discards rays that miss an aperture by more than eps.
+// The visibility mask is therefore decided in fp64 for every ray the reference could accept; the FP32 pass only
+// discards rays that miss an aperture by more than eps, and only vouches for rays that clear the slit edges by 2e-2 mm.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -48,7 +50,7 @@ struct K1Params {
   float dz[3];       // lattice kernel: recentred position step between z-consecutive voxels (FP32)
   uint2* cand;       // (voxel_local, crystal) pairs
   unsigned long long cand_capacity;
-  unsigned long long* counters;  // [0] candidates, [1] next work item
+  unsigned long long* counters;  // [0] candidates (lattice kernel: the certain ones), [1] next work item, [2] uncertain candidates
   double* w_out;
   unsigned int* nrays_out;
   ComRayRecord* rays_out;
