@@ -16,8 +16,12 @@
 //                              reduction of the flux partials; the last block to finish adds the partials in block
 //                              order, so the result does not depend on scheduling.
 //   K2h weight_histogram_kernel  voxel pass for large grids / profile sweeps: w_v accumulated per profile row
-//                              (10 B/voxel of HBM traffic with uint16 Reff bins) - the only per-voxel work a sweep needs
+//                              - the only per-voxel work a sweep needs
+//       weight_histogram_mm_kernel + histogram_rows_kernel  the same in two halves for uint16 millimetre Reff (10 B/voxel
+//                              of HBM traffic): weights binned by millimetre in shared memory, then the Reff cut and the
+//                              millimetre -> profile-row mapping on the 4096-bin histogram (which ranks can all-reduce)
 //   K2s sweep_kernel           flux[s][t] = sum_k H[k] * eps_t(s, k) for a batch of profile time slices
+//   Extension (off by default): log-log bilinear PEC interpolation, pec_loglog.
 #include <cuda_runtime.h>
 
 #include <algorithm>
