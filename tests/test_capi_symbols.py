@@ -128,3 +128,11 @@ def test_compute_fails_loudly_without_a_gpu(lib):
         make_channel("C", 10, 5, 5)
     assert exc.value.code == _lib.COM_E_CUDA
     assert lib.com_measure_fp32_tflops() < 0
+
+
+def test_driver_build_entry_point():
+    """__graft_entry__.build() - what the driver runs on CPU each round - compiles (or finds) the library and passes its
+    own checks."""
+    import __graft_entry__ as entry
+
+    entry.build()
