@@ -523,7 +523,11 @@ def run_ours(args):
             pass
         gbs = 10.0 * n2 / (ms2 * 1e-3) / 1e9
         roofline_stage2 = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                           "traffic": None, "peak_source": src, "kernel": "com::weight_histogram_mm_kernel",
+                           "traffic": 5.0044e9,
+                           "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full "
+                                           "capture profiles/r1c_ncu_full_summary_hist_mm.txt (5.000 GB read = the algorithmic "
+                                           "10 B x 5e8 voxels, 4.4 MB written)",
+                           "peak_source": src, "kernel": "com::weight_histogram_mm_kernel",
                            "kernel_ms_per_launch": ms2, "launch_ms": [round(t, 4) for t in times],
                            "voxels_per_launch": n2, "algorithmic_bytes_per_voxel": 10,
                            "max_rel_err_vs_bincount": err2,
