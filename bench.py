@@ -387,11 +387,12 @@ def run_ours(args):
                                           C.byref(cnt), C.byref(st))
         _lib.check(rc, "com_visible_weights_host")
         m = cnt.value
-        reff_v = reff_np[idx_np[el][:m]]  # host-side join with the Reff table, as reader.py:161-197 does
-        rc = lib.com_emissivity_integrate_host(C.byref(pipes[el].tables.desc), _lib.as_double_ptr(prof_np), len(prof_np),
-                                               0.02, _lib.as_double_ptr(reff_v), _lib.as_double_ptr(w_np[el]), m,
-                                               _lib.as_double_ptr(flux_e2e[i]), None, None, None)
-        _lib.check(rc, "com_emissivity_integrate_host")
+        # the join with the Reff table (reader.py:161-197) happens inside the call, on the visible voxels' indices
+        rc = lib.com_emissivity_integrate_indexed_host(
+            C.byref(pipes[el].tables.desc), _lib.as_double_ptr(prof_np), len(prof_np), 0.02, _lib.as_double_ptr(reff_np),
+            len(reff_np), C.c_void_p(idx_np[el].ctypes.data), _lib.as_double_ptr(w_np[el]), m,
+            _lib.as_double_ptr(flux_e2e[i]), None, None, None)
+        _lib.check(rc, "com_emissivity_integrate_indexed_host")
         if count_bytes:
             k = scenes[el]._keep
             up = sum(k[x].nbytes for x in ("xyz", "nrm", "sc", "sp", "pv", "dv"))
@@ -563,8 +564,8 @@ def run_ours(args):
                 "ms_per_step": 1e3 * e2e_s / args.steps, "ms_per_step_median": 1e3 * float(np.median(e2e_times)),
                 "ms_per_step_max": 1e3 * float(np.max(e2e_times)),
                 "call": "per channel, four channels from four host threads: com_visible_weights_host (geometry up, K1a/K1b + "
-                        "compaction, visible voxels' indices and weights down) then com_emissivity_integrate_host (tables, "
-                        "profile, Reff and weights up, flux down)"},
+                        "compaction, visible voxels' indices and weights down) then com_emissivity_integrate_indexed_host (tables, "
+                        "profile, Reff of the visible voxels and weights up, flux down)"},
         "gpu_launches": int(args.steps * len(ELEMENTS) * pipes[ELEMENTS[0]].kernels_per_launch),
         "wall_s_timed_region": wall,
         "clocks": clocks,

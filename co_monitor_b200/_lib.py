@@ -190,6 +190,8 @@ def _declare(lib):
                                              vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.com_reff_max.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.com_emissivity_integrate_host.argtypes = [C.POINTER(ComTablesDesc), dp, i32, C.c_double, dp, dp, i64, dp, vp, vp, dp]
+    lib.com_emissivity_integrate_indexed_host.argtypes = [C.POINTER(ComTablesDesc), dp, i32, C.c_double, dp, i64, vp, dp, i64,
+                                                          dp, vp, vp, dp]
     lib.com_weight_histogram.argtypes = [vp, i32, i32, C.c_double, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp,
                                          C.c_size_t, vp]
     lib.com_emissivity_sweep.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, vp]
@@ -220,6 +222,7 @@ EXPORTED_SYMBOLS = [
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
     "com_write_stage1_csv", "com_format_float_repr", "com_scene_filter_certain_host",
+    "com_emissivity_integrate_indexed_host",
 ]
 
 

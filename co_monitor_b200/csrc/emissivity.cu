@@ -726,14 +726,26 @@ int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_
   return COM_OK;
 }
 
-int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
-                                  double concentration, const double* reff_h, const double* w_h, int64_t n,
-                                  double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
-                                  double* boundary_out_h) {
-  if (!tables_h || !profile_h || !reff_h || !w_h || !flux_out_h || n < 0 || K < 1) {
+}  // extern "C"
+
+// reff_h (n values), or reff_table_h + reff_index_h: voxel i has Reff reff_table_h[reff_index_h[i]] - the join of
+// Emissivity.get_plas_coords_with_rad_frac (reader.py:161-197), done while the inputs are staged for the upload.
+static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K, double concentration,
+                           const double* reff_h, const double* reff_table_h, int64_t n_table, const int64_t* reff_index_h,
+                           const double* w_h, int64_t n, double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                           double* boundary_out_h) {
+  if (!tables_h || !profile_h || (!reff_h && !(reff_table_h && reff_index_h && n_table > 0)) || !w_h || !flux_out_h || n < 0 ||
+      K < 1) {
     com::set_error("com_emissivity_integrate_host: bad arguments");
     return COM_E_BADARG;
   }
+  if (!reff_h)
+    for (int64_t i = 0; i < n; ++i)
+      if (reff_index_h[i] < 0 || reff_index_h[i] >= n_table) {
+        com::set_error("com_emissivity_integrate_indexed_host: index %lld of voxel %lld outside the Reff table (%lld rows)",
+                       (long long)reff_index_h[i], (long long)i, (long long)n_table);
+        return COM_E_BADARG;
+      }
   std::vector<double> blob;
   ComTables T;  // tables live in the shared host-call arena: nothing to free
   int rc = build_tables_blob(tables_h, blob, T.dev);
@@ -755,7 +767,12 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
   if (rc) return rc;
   std::memcpy(pin, blob.data(), blob.size() * sizeof(double));
   std::memcpy(pin + b_tab, profile_h, sizeof(double) * 3 * K);
-  std::memcpy(pin + b_tab + b_prof, reff_h, sizeof(double) * (size_t)n);
+  if (reff_h) {
+    std::memcpy(pin + b_tab + b_prof, reff_h, sizeof(double) * (size_t)n);
+  } else {
+    double* dst = reinterpret_cast<double*>(pin + b_tab + b_prof);
+    for (int64_t i = 0; i < n; ++i) dst[i] = reff_table_h[reff_index_h[i]];
+  }
   std::memcpy(pin + b_tab + b_prof + b_n, w_h, sizeof(double) * (size_t)n);
   cudaStream_t s = cudaStreamPerThread;
   COM_CUDA(cudaMemcpyAsync(d, pin, up, cudaMemcpyHostToDevice, s));
@@ -779,6 +796,32 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
   std::memcpy(flux_out_h, pin_out, sizeof(double) * (nt + 1));
   if (boundary_out_h) std::memcpy(boundary_out_h, pin_out + 128, sizeof(double));
   return COM_OK;
+}
+
+extern "C" {
+
+int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                                  double concentration, const double* reff_h, const double* w_h, int64_t n,
+                                  double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                                  double* boundary_out_h) {
+  if (!reff_h) {
+    com::set_error("com_emissivity_integrate_host: bad arguments");
+    return COM_E_BADARG;
+  }
+  return emissivity_host(tables_h, profile_h, K, concentration, reff_h, nullptr, 0, nullptr, w_h, n, flux_out_h,
+                         per_voxel_out_h, valid_out_h, boundary_out_h);
+}
+
+int com_emissivity_integrate_indexed_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                                          double concentration, const double* reff_table_h, int64_t n_table,
+                                          const int64_t* reff_index_h, const double* w_h, int64_t n, double* flux_out_h,
+                                          double* per_voxel_out_h, uint8_t* valid_out_h, double* boundary_out_h) {
+  if (!reff_table_h || !reff_index_h) {
+    com::set_error("com_emissivity_integrate_indexed_host: bad arguments");
+    return COM_E_BADARG;
+  }
+  return emissivity_host(tables_h, profile_h, K, concentration, nullptr, reff_table_h, n_table, reff_index_h, w_h, n,
+                         flux_out_h, per_voxel_out_h, valid_out_h, boundary_out_h);
 }
 
 }  // extern "C"

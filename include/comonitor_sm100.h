@@ -360,6 +360,14 @@ int com_histogram_rows(const double* profile, int32_t K, int32_t profile_sorted,
 int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_t n_slices, int32_t K,
                          const double* hist, double concentration, double* flux_out, com_stream_t stream);
 
+/* Same, with the Reff join of Emissivity.get_plas_coords_with_rad_frac (reader.py:161-197) done inside: voxel i has
+ * Reff reff_table_h[reff_index_h[i]] (reff_table_h: the n_table values of the Reff file, NaN outside the LCFS;
+ * reff_index_h: idx_sel_plas_points of the Stage-1 table).  NaN rows are dropped as the reference drops them. */
+int com_emissivity_integrate_indexed_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                                          double concentration, const double* reff_table_h, int64_t n_table,
+                                          const int64_t* reff_index_h, const double* w_h, int64_t n, double* flux_out_h,
+                                          double* per_voxel_out_h, uint8_t* valid_out_h, double* boundary_out_h);
+
 /* ---- Reff provider ------------------------------------------------------------
  * Replaces the VMEC web-service step (co_monitor/geometry/reff_VMEC.py:85-136) and its 3-decimal file
  * (reff_VMEC.py:138-176) for lattices that have no shipped file: Reff of the voxels [vox_begin, vox_end) of the

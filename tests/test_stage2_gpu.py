@@ -291,6 +291,25 @@ def test_host_buffer_emissivity_call(gold, reff10):
         np.testing.assert_allclose(flux, gold["main_C_flux"], rtol=RTOL)
         assert bnd.value == float(gold["main_C_reff_boundary"][0])
         assert valid.sum() == int(gold["main_C_nrows"][0])
+    # the indexed variant does the Reff join inside: same results from the whole Reff table + the voxel indices
+    idx_all = np.ascontiguousarray(obs[:, 0].astype(np.int64))
+    w_all = np.ascontiguousarray(obs[:, 4])
+    flux2, bnd2 = np.zeros(3), C.c_double()
+    valid2 = np.zeros(len(idx_all), dtype=np.uint8)
+    table = np.ascontiguousarray(reff10)
+    rc = lib.com_emissivity_integrate_indexed_host(C.byref(tables.desc), _lib.as_double_ptr(prof), len(prof), 0.02,
+                                                   _lib.as_double_ptr(table), len(table), C.c_void_p(idx_all.ctypes.data),
+                                                   _lib.as_double_ptr(w_all), len(idx_all), _lib.as_double_ptr(flux2), None,
+                                                   C.c_void_p(valid2.ctypes.data), C.byref(bnd2))
+    assert rc == 0
+    np.testing.assert_allclose(flux2, flux, rtol=1e-13)  # NaN rows are dropped inside; only the summation order differs
+    assert bnd2.value == bnd.value and valid2.sum() == valid.sum()
+    bad = idx_all.copy()
+    bad[5] = len(table)
+    assert lib.com_emissivity_integrate_indexed_host(C.byref(tables.desc), _lib.as_double_ptr(prof), len(prof), 0.02,
+                                                     _lib.as_double_ptr(table), len(table), C.c_void_p(bad.ctypes.data),
+                                                     _lib.as_double_ptr(w_all), len(bad), _lib.as_double_ptr(flux2), None, None,
+                                                     None) == _lib.COM_E_BADARG
     ref_rows = gold["main_C_rows"]  # stride 1 for C, sorted by idx
     mine = cols[valid.astype(bool)]
     order = np.argsort(obs[keep][valid.astype(bool), 0], kind="stable")
