@@ -367,6 +367,50 @@ def run_ours(args):
     lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_launch))
     lib.com_kernel_timing_enable(0)
 
+    # ---- the same step with every ray's detector test evaluated individually (SURVEY.md 8(d) asks for the rate without
+    # culling next to the headline): scenes built with COM_FILTER_NO_RUN_CULL, identical results, N = 1 only ----
+    every_ray = None
+    if world == 1 and not args.no_every_ray:
+        saved = dict(pipes)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for el in ELEMENTS:
+                sc_nc = make_channel(el, SLITS, H, L, lattice=lattice, run_cull=False)
+                scenes[el + "_nc"] = sc_nc
+                pipes[el] = ChannelPipeline(sc_nc, saved[el].tables, lattice, reff_table, lo, hi, 2.0, device=device)
+                pipes[el].set_profile(profile)
+        for _ in range(3):
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+        run_nc = step
+        g_nc = None
+        if graph is not None:
+            try:
+                g_nc = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_nc):
+                    step()
+                g_nc.replay()
+                torch.cuda.synchronize()
+                run_nc = g_nc.replay
+            except Exception:  # pragma: no cover - measure without a graph then
+                g_nc = None
+                torch.cuda.synchronize()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            e0[i].record()
+            run_nc()
+            e1[i].record()
+        torch.cuda.synchronize()
+        ms_nc = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        same = bool(np.allclose(flux.cpu().numpy(), flux_h, rtol=1e-12))
+        every_ray = {"value": tests_per_step_rank * args.steps / (ms_nc * 1e-3), "unit": "tests/s",
+                     "ms_per_step": ms_nc / args.steps, "flux_equal": same,
+                     "passing_rays": {el: pipes[el].plan.stats()["passing_rays"] for el in ELEMENTS}}
+        del g_nc
+        pipes.update(saved)
+
     # ---- e2e: the reference-facing host-buffer calls, per channel: com_visibility_weights_host (scene upload,
     # kernels, D2H of per-voxel weights + ray counts) then com_emissivity_integrate_host on the visible voxels ----
     n = hi - lo
@@ -553,6 +597,11 @@ def run_ours(args):
             "timing": "sum of per-step CUDA-event intervals, max over ranks",
             "launch": ("one CUDA graph per step, four channels on four streams" if graph is not None else
                        "four channels on four streams, no graph"),
+            "decided_how": "every (voxel, crystal point) ray is decided: by the FP32 filter (its detector test evaluated per "
+                           "ray, or for a whole run of z-consecutive voxels at once when the linearity of the test proves that "
+                           "none of them can pass) and, for the candidates, in fp64; nothing is pre-selected or skipped. "
+                           "`every_ray_evaluated` is the same step with the run-level proof switched off",
+            "every_ray_evaluated": every_ray,
             "passing_rays": {el: stats[el]["passing_rays"] for el in ELEMENTS},
             "fp64_candidates": {el: stats[el]["candidates"] for el in ELEMENTS},
             "near_edge_rays": {el: stats[el]["near_edge_rays"] for el in ELEMENTS},
@@ -584,6 +633,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-every-ray", action="store_true", help="skip the leg that re-times the step without run-level culling")
     ap.add_argument("--no-stage2-roofline", action="store_true", help="skip the HBM roofline leg of the Stage-2 voxel pass")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-graph-multi-gpu", action="store_true",

@@ -74,7 +74,7 @@ class ComSceneDesc(C.Structure):
         ("apertures_override", C.POINTER(ComAperture)),
         ("near_edge_mm", C.c_double),
         ("n_voxel_corners", C.c_int32),
-        ("reserved", C.c_int32),
+        ("filter_flags", C.c_int32),
         ("voxel_corners", (C.c_double * 3) * 8),
     ]
 

@@ -248,6 +248,7 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   // polygon, so the filter can only over-accept; the exact kernel decides.
   double eps = d.filter_eps_mm > 0 ? d.filter_eps_mm : 5e-3;
   dv.filter_disabled = eps >= 1e30 ? 1 : 0;
+  dv.no_run_cull = (d.filter_flags & COM_FILTER_NO_RUN_CULL) ? 1 : 0;
   if (dv.filter_disabled) eps = 5e-3;
 
   // slits: one polygon per side, repeated with period T along e1.  Verify the periodicity the collimator

@@ -30,6 +30,7 @@ struct DeviceScene {
   int n_apertures;       // 2S + 2: crys_0, plasma_0, crys_1, ..., port, detector
   int n_edges_total;
   int filter_disabled;   // 1: every ray goes to the fp64 stage
+  int no_run_cull;       // 1: the lattice kernel tests every ray individually (measurement aid)
   int slit_filter;       // 1: the collimator is periodic and stage B of the filter tests it
   int slit_same_w;       // 1: both collimator planes share their normal, so one W form serves both sides
   float slit_period;     // slit pitch along e1 (2 |vector_top_bottom|)

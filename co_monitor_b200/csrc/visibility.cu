@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   float4* base = s_base[warp];
   int2* segs = s_seg[warp];
   const long long n_items = (long long)P.n_tiles * n_cgroups;
+  const bool run_cull = sc.filter_disabled == 0 && sc.no_run_cull == 0;  // skip z-runs proven to miss the detector
 
   for (;;) {
     unsigned long long item = 0;
@@ -393,14 +394,14 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
         return (fabsf(xa) > fabsf(wa) && fabsf(xb) > fabsf(wb) && xa * xb > 0.f) ||
                (fabsf(ya) > fabsf(wa) && fabsf(yb) > fabsf(wb) && ya * yb > 0.f);
       };
-      if (sc.filter_disabled == 0) {
+      if (run_cull) {
         const float n1 = (float)(len - 1);
         if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(n1, dxs, xs), fmaf(n1, dys, ys), fmaf(n1, dws, w)))) continue;
       }
       int k = 0;
 #pragma unroll 1
       for (; k + kUnroll <= len; k += kUnroll) {
-        if (sc.filter_disabled == 0) {
+        if (run_cull) {
           constexpr float kLast = (float)(kUnroll - 1), kStep = (float)kUnroll;
           if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(kLast, dxs, xs), fmaf(kLast, dys, ys), fmaf(kLast, dws, w)))) {
             xs = fmaf(kStep, dxs, xs), ys = fmaf(kStep, dys, ys), w = fmaf(kStep, dws, w);
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
           while (qn >= 32) drain(32);
         }
       }
-      if (k < len && sc.filter_disabled == 0) {  // the ragged tail is one more run
+      if (k < len && run_cull) {  // the ragged tail is one more run
         const float n1 = (float)(len - 1 - k);
         if (__all_sync(0xffffffffu, culled(xs, ys, w, fmaf(n1, dxs, xs), fmaf(n1, dys, ys), fmaf(n1, dws, w)))) continue;
       }

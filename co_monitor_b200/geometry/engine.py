@@ -65,7 +65,7 @@ class ChannelScene:
     def __init__(self, crystal_points, normals, slit_crys, slit_plasma, vector_front_back, port_vertices,
                  port_ov, det_vertices, det_ov, origin, area_pt, refl_max, aoi0, refl_sigma=2.2,
                  voxel_corners=None, filter_eps_mm=DEFAULT_FILTER_EPS_MM, calibrate_apertures=True,
-                 near_edge_mm=0.0, host_only=False):
+                 near_edge_mm=0.0, host_only=False, run_cull=True):
         self._lib = _lib.load()
         self._keep = {}
 
@@ -94,6 +94,7 @@ class ChannelScene:
         d.area_pt, d.refl_max, d.aoi0, d.refl_sigma = float(area_pt), float(refl_max), float(aoi0), float(refl_sigma)
         d.filter_eps_mm = float(filter_eps_mm)
         d.near_edge_mm = float(near_edge_mm)
+        d.filter_flags = 0 if run_cull else 1  # COM_FILTER_NO_RUN_CULL: every ray's detector test evaluated on its own
         self.aperture_shifts = None
         if calibrate_apertures:
             arr, self.aperture_shifts = build_apertures(

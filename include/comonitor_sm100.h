@@ -50,6 +50,7 @@ extern "C" {
 typedef void* com_stream_t; /* cudaStream_t */
 
 #define COM_MAX_EDGES 32
+#define COM_FILTER_NO_RUN_CULL 1
 
 /* One aperture of the beam line reduced to "plane + convex polygon in that plane".
  * The reference tests  Delaunay(vertices +/- orientation_vector).find_simplex(X) >= 0  for the point X
@@ -105,9 +106,12 @@ typedef struct ComSceneDesc {
   double near_edge_mm;           /* |margin| below which a decided ray is counted in ComStats.near_edge_rays;
                                     <= 0 selects 1e-9 mm                                               */
   int32_t n_voxel_corners;       /* optional hint, 0..8: points whose convex hull contains every voxel that   */
-  int32_t reserved;              /* will be tested (the lattice corners).  Not needed for correctness: the    */
+  int32_t filter_flags;          /* will be tested (the lattice corners).  Not needed for correctness: the    */
   double voxel_corners[8][3];    /* filter accepts both nappes of the detector cone, as the reference's
-                                    infinite-line intersection does (simulation.py:143-173).              */
+                                    infinite-line intersection does (simulation.py:143-173).
+                                    filter_flags: COM_FILTER_NO_RUN_CULL (1) makes the lattice kernel evaluate the
+                                    detector test of every ray individually instead of skipping whole z-runs that
+                                    the linearity of the forms proves to miss (a measurement aid: same results).   */
 } ComSceneDesc;
 
 typedef struct ComScene ComScene; /* opaque: device-resident tables of one channel */

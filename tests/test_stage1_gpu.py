@@ -404,3 +404,26 @@ def test_chunked_launches_and_result_files(sims, tmp_path):
     pd.testing.assert_frame_equal(stage1_io.read(str(first).replace("slit_100", "slit_10*")), b)
     binary = chunked.save_to_file(binary=True)
     pd.testing.assert_frame_equal(stage1_io.read(binary, mesh=chunked.mesh), b)
+
+
+def test_run_level_cull_changes_nothing(sims):
+    """COM_FILTER_NO_RUN_CULL (every ray's detector test evaluated on its own) against the default lattice kernel that skips
+    whole z-runs proven to miss the detector: same candidates up to FP32 rounding of the band, identical decisions."""
+    import contextlib
+    import io
+
+    import torch
+
+    from co_monitor_b200.geometry.engine import make_channel
+
+    sim = sims("N")
+    lat = sim.mesh.lattice
+    with contextlib.redirect_stdout(io.StringIO()):
+        plain = make_channel("N", 10, 30, 20, lattice=lat, run_cull=False)
+    a = sim.scene.visibility(lattice=lat)
+    b = plain.visibility(lattice=lat)
+    assert torch.equal(a.nrays, b.nrays)
+    assert a.stats["passing_rays"] == b.stats["passing_rays"] == PASSING_RAYS["N"]
+    assert abs(a.stats["candidates"] - b.stats["candidates"]) <= 16  # the two paths round the forms differently
+    torch.testing.assert_close(a.weight, b.weight, rtol=1e-13, atol=0)
+    plain.close()
