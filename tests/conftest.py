@@ -28,8 +28,6 @@ def reff10():
     import contextlib
     import io
 
-    import numpy as np
-
     from co_monitor_b200.geometry.reff import reff_path, upsample_reff, write_reff_file
 
     path = reff_path(10)

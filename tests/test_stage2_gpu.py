@@ -264,8 +264,6 @@ def test_host_buffer_emissivity_call(gold, reff10):
     """com_emissivity_integrate_host (host in, host out) against the reference's C-channel result."""
     import ctypes as C
 
-    import pandas as pd
-
     from co_monitor_b200 import _lib
     from co_monitor_b200.emissivity.engine import cached_line_tables
     from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
