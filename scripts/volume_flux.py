@@ -8,8 +8,9 @@
 Everything happens on the device, nothing of size voxels x crystal points (or even voxels x 8 B per channel) is kept:
   Reff      the shipped 15 mm VMEC grid resampled onto this rank's block-cyclic shard of the lattice, as uint16
             millimetre bins (com_reff_resample; --reff quadratic: the analytic flux-surface model instead)
-  Stage 1   visibility + weights in launches of --chunk voxels; the exact kernel adds every passing ray's weight to the
-            channel's millimetre-bin histogram hist[reff_mm[voxel]] on the fly
+  Stage 1   visibility + weights in launches of --chunk voxels, each followed by one 10 B/voxel pass that adds the launch's
+            weights to the channel's millimetre-bin histogram (--histogram fused: the exact kernel adds every passing
+            ray to hist[reff_mm[voxel]] itself - fewer bytes, but many atomics on few bins)
   exchange  ONE all-reduce(SUM) over NVLink of the packed [channels, 4096] histograms plus the ray/voxel counters
   Stage 2   histogram -> profile rows -> flux per transition (com_histogram_rows + com_emissivity_sweep), every rank
 The timed region (CUDA events, barrier on both sides, max over ranks) covers Stage 1, the exchange and Stage 2 of all
@@ -58,6 +59,9 @@ def main():
     ap.add_argument("--reff", choices=("resample", "quadratic"), default="resample")
     ap.add_argument("--cols-per-block", type=int, default=8)
     ap.add_argument("--candidate-fraction", type=float, default=0.0)
+    ap.add_argument("--histogram", choices=("pass", "fused"), default="pass",
+                    help="pass: one 10 B/voxel histogram pass over each launch's weights (default); fused: the exact kernel "
+                         "adds every passing ray to the histogram itself (more atomics on few bins)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -113,17 +117,26 @@ def main():
             tables.append(LineTables(el, ion, wl, ["EXCIT", "RECOM"]))
     # one set of Stage-1 buffers, reused by every chunk of every channel (stream order keeps them consistent)
     plan_cap = max(hi - lo for lo, hi in chunks)
+    fused = a.histogram == "fused"
     plan_buf = scenes[0].plan(lat, 0, plan_cap, candidate_fraction=a.candidate_fraction, device=dev,
-                              reff_bin=reff_mm, hist=hist[0])
+                              reff_bin=reff_mm if fused else None, hist=hist[0] if fused else None)
+    if not fused and any(lo % 8 for lo, _ in chunks):
+        raise SystemExit("--chunk must be a multiple of 8 voxels for the histogram pass (16-byte aligned loads)")
     stream = torch.cuda.current_stream(dev)
     s_ptr = lambda: __import__("ctypes").c_void_p(stream.cuda_stream)  # noqa: E731
 
     def run_once():
         packed.zero_()
         for i in range(n_ch):
-            plan_buf.scene, plan_buf.hist = scenes[i], hist[i]
+            plan_buf.scene = scenes[i]
+            if fused:
+                plan_buf.hist = hist[i]
             for j, (lo, hi) in enumerate(chunks):
                 plan_buf.rebind(lo, hi, stats=stats[i, j]).launch()
+                if not fused:
+                    rc = lib.com_weight_histogram_mm(_ptr(reff_mm[lo:hi]), _ptr(plan_buf.weight), hi - lo, None, _ptr(hist[i]),
+                                                     s_ptr())
+                    _lib.check(rc, "com_weight_histogram_mm")
             counters[i].copy_(stats[i].sum(0).to(torch.float64))  # exact: counts < 2^53
         if world > 1:
             dist.all_reduce(packed)  # the single exchange: [channels, 4096] histograms + counters
