@@ -42,21 +42,6 @@ def bilinear_on_grid(x_nodes, y_nodes, table, x_new, y_new) -> np.ndarray:
     return sp
 
 
-def loglog_on_nodes(x_nodes, y_nodes, table, x, y) -> np.ndarray:
-    """NumPy statement of the ``pec_interpolation="loglog"`` extension (csrc/emissivity.cu::pec_loglog): bilinear in
-    (log x, log y) of log table through the nodes, arguments clamped to the node range."""
-    x_nodes, y_nodes, table = (np.asarray(a, dtype=float) for a in (x_nodes, y_nodes, table))
-    x = np.clip(np.asarray(x, dtype=float), x_nodes[0], x_nodes[-1])
-    y = np.clip(np.asarray(y, dtype=float), y_nodes[0], y_nodes[-1])
-    i = np.clip(np.searchsorted(x_nodes, x, side="right") - 1, 0, len(x_nodes) - 2)
-    j = np.clip(np.searchsorted(y_nodes, y, side="right") - 1, 0, len(y_nodes) - 2)
-    u = (np.log(x) - np.log(x_nodes[i])) / (np.log(x_nodes[i + 1]) - np.log(x_nodes[i]))
-    v = (np.log(y) - np.log(y_nodes[j])) / (np.log(y_nodes[j + 1]) - np.log(y_nodes[j]))
-    c00, c01, c10, c11 = table[i, j], table[i, j + 1], table[i + 1, j], table[i + 1, j + 1]
-    L = (1 - u) * (1 - v) * np.log(c00) + (1 - u) * v * np.log(c01) + u * (1 - v) * np.log(c10) + u * v * np.log(c11)
-    return np.exp(L)
-
-
 class PEC:
     def __init__(self, element, wavelength, ionization_state, transition, interp_step=2000, plot=False,
                  input_root=None):

@@ -15,9 +15,11 @@ Things kept exactly as the reference does them, because results depend on them:
     ``f"{x:.2e}"`` *string* (:396);
   * all paths are relative to ``Path.cwd()`` when an ``input_files`` directory is there (:116-122, 150-157);
     otherwise the copy shipped with the package is used.
-Deviations: the fractional-abundance file is found under both ``.txt`` and ``.dat``; a
-missing ``Reff_coordinates-<s>_mm`` file is synthesised by trilinear up-sampling of a shipped grid;
-``pec_data`` (the 2 x 96 MB dense PEC arrays) is built only when somebody reads it.
+Deviations (see DESIGN.md): the fractional-abundance file is found under both ``.txt`` and ``.dat``;
+``pec_data`` (the 2 x 96 MB dense PEC arrays) is built only when somebody reads it.  A missing
+``Reff_coordinates-<s>_mm`` file raises ``FileNotFoundError`` as in the reference unless the caller opts in with
+``reff_fallback="upsample"``: the shipped 15 mm grid is then resampled onto the lattice on the device
+(``com_reff_resample``), with a ``UserWarning`` - the physics input is then synthetic - and cached per process.
 Extension, off by default: ``pec_interpolation="loglog"`` evaluates the PEC by bilinear interpolation in log-log space
 through the ADAS nodes at each row's own (ne, Te) instead of the reference's nearest node of a linearly interpolated
 2000 x 2000 table (pec.py:153-187); results then differ from the reference's by design.
@@ -35,6 +37,10 @@ from .engine import cached_line_tables
 from .fractional_abundance import FractionalAbundance
 from .kinetic_profiles import ExperimentalProfile, TwoGaussSumProfile  # noqa: F401  (re-exported like the reference)
 from .pec import PEC  # noqa: F401
+
+
+#: Reff tables synthesised by ``reff_fallback="upsample"``, keyed by (spacing, input root)
+_UPSAMPLED_REFF: dict = {}
 
 
 class Emissivity:
@@ -57,12 +63,16 @@ class Emissivity:
         save=True,
         verbose=True,
         pec_interpolation="reference",
+        reff_fallback=None,
     ):
         self._say = print if verbose else (lambda *a, **k: None)
         self._input_root = stage2_input_root(input_root)
         self._output_dir = output_dir
         self._device = device
         self._pec_dense = None
+        if reff_fallback not in (None, "upsample"):
+            raise ValueError("reff_fallback must be None or 'upsample'")
+        self._reff_fallback = reff_fallback
         self.element = element
         self.ionization_state = ion_state
         self.wavelength = wavelength
@@ -96,12 +106,18 @@ class Emissivity:
         path = self._input_root / "geometry" / "reff" / f"{self.reff_magnetic_config}.dat"
         if not path.exists():
             m = re.fullmatch(r"Reff_coordinates-(\d+)_mm", str(self.reff_magnetic_config))
-            if not m:
-                raise FileNotFoundError(path)
+            if not m or self._reff_fallback != "upsample":
+                raise FileNotFoundError(path)  # what the reference does (reader.py:116-128)
+            import warnings
+
             from ..geometry.reff import upsample_reff
 
-            self._say(f"\n{path.name} not found: up-sampling the shipped 15 mm Reff grid (no VMEC service here).")
-            df = upsample_reff(15, int(m.group(1)), self._input_root)
+            warnings.warn(f"{path.name} not found: Reff is SYNTHETIC - the shipped 15 mm grid resampled onto the "
+                          f"{m.group(1)} mm lattice (reff_fallback='upsample'; no VMEC service here)", UserWarning, stacklevel=3)
+            key = (int(m.group(1)), str(self._input_root))
+            if key not in _UPSAMPLED_REFF:
+                _UPSAMPLED_REFF[key] = upsample_reff(15, key[0], self._input_root)
+            df = _UPSAMPLED_REFF[key].copy()
         else:
             df = pd.read_csv(path, sep=";")
         df.columns = ["idx_plasma", "x", "y", "z", "Reff [m]"]

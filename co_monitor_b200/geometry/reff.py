@@ -13,9 +13,11 @@ This module provides the replacements the north-star allows:
                         is NaN (outside the LCFS), exactly how the reference treats NaN rows (reader.py:176).
   * ``QuadraticReff``   an analytic flux-surface model fitted to a shipped grid (Reff^2 as a quadratic form of
                         position: nested elliptic cylinders), evaluable for 1e8-1e9 voxel lattices without a file.
-Both also run on the device (``resample_reff_device``, ``QuadraticReff.on_device``: csrc/reff.cu through
-``com_reff_resample`` / ``com_reff_quadratic``) and then produce the uint16 millimetre bins Stage 2 reads for any
-(sharded) range of a 1e8-1e9 voxel lattice; the NumPy forms here are what those kernels are tested against.
+Both run on the device (``resample_reff_device``, ``QuadraticReff.on_device``: csrc/reff.cu through
+``com_reff_resample`` / ``com_reff_quadratic``) and produce the uint16 millimetre bins Stage 2 reads for any
+(sharded) range of a 1e8-1e9 voxel lattice, or the 3-decimal doubles of the reference's file.  The NumPy statement the
+resampling kernel is tested against is test infrastructure (oracle/reff.py); ``QuadraticReff.__call__`` is the host
+form of the analytic model (used to fit and to check it).
 """
 from __future__ import annotations
 
@@ -99,65 +101,27 @@ def resample_reff_device(target_lattice, source_spacing: int = 15, begin: int = 
     return mm, reff
 
 
-def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None = None, decimals: int | None = 3) -> np.ndarray:
-    """Reff [m] on every voxel of *target_lattice* (any lattice spanning the standard cuboid), flat index order."""
-    vol, ls = source_volume(source_spacing, root)
-    lt = target_lattice
-
-    def axis(n_t, n_s):
-        f = np.arange(n_t) * ((n_s - 1) / (n_t - 1))
-        i0 = np.minimum(np.floor(f).astype(int), n_s - 2)
-        return i0, f - i0
-
-    (y0, fy), (x0, fx), (z0, fz) = axis(lt.ny, ls.ny), axis(lt.nx, ls.nx), axis(lt.nz, ls.nz)
-    out = np.zeros((lt.ny, lt.nx, lt.nz))
-    bad = np.zeros(out.shape, dtype=bool)
-    for dy, wy in ((0, 1 - fy), (1, fy)):
-        for dx, wx in ((0, 1 - fx), (1, fx)):
-            for dz, wz in ((0, 1 - fz), (1, fz)):
-                w = wy[:, None, None] * wx[None, :, None] * wz[None, None, :]
-                v = vol[(y0 + dy)[:, None, None], (x0 + dx)[None, :, None], (z0 + dz)[None, None, :]]
-                nanv = np.isnan(v)
-                bad |= nanv & (w > 0)
-                out += np.where(nanv, 0.0, v) * w
-    out[bad] = np.nan
-    out = out.ravel()
-    return np.round(out, decimals=decimals) if decimals is not None else out
-
-
-def interpolate_reff_at(target_lattice, flat, source_spacing: int = 15, root: Path | None = None,
-                        decimals: int | None = 3, source=None) -> np.ndarray:
-    """``interpolate_reff`` for selected flat indices only (shard-local when the lattice is a shard): the same
-    operations per voxel, so the values are bit-identical; usable on slabs of lattices too large to resample whole."""
-    vol, ls = source if source is not None else source_volume(source_spacing, root)
-    lt = target_lattice
-    ix, iy, iz = lt.unravel(np.asarray(flat, dtype=np.int64))
-
-    def axis(n_t, n_s, i):
-        f = np.arange(n_t) * ((n_s - 1) / (n_t - 1))
-        i0 = np.minimum(np.floor(f).astype(int), n_s - 2)
-        return i0[i], (f - i0)[i]
-
-    (y0, fy), (x0, fx), (z0, fz) = axis(lt.ny, ls.ny, iy), axis(lt.nx, ls.nx, ix), axis(lt.nz, ls.nz, iz)
-    out = np.zeros(len(ix))
-    bad = np.zeros(len(ix), dtype=bool)
-    for dy, wy in ((0, 1 - fy), (1, fy)):
-        for dx, wx in ((0, 1 - fx), (1, fx)):
-            for dz, wz in ((0, 1 - fz), (1, fz)):
-                w = wy * wx * wz
-                v = vol[y0 + dy, x0 + dx, z0 + dz]
-                nanv = np.isnan(v)
-                bad |= nanv & (w > 0)
-                out += np.where(nanv, 0.0, v) * w
-    out[bad] = np.nan
-    return np.round(out, decimals=decimals) if decimals is not None else out
+def interpolate_reff(target_lattice, source_spacing: int = 15, root: Path | None = None, device=None,
+                     chunk: int = 1 << 27) -> np.ndarray:
+    """Reff [m] (3 decimals, NaN outside the LCFS) on every voxel of *target_lattice*, flat index order, as a host
+    array.  Computed by the device kernel (``com_reff_resample``) in ranges of *chunk* voxels; like every compute
+    entry point of this package it raises without a CUDA device (the NumPy statement the kernel is tested against
+    lives in oracle/reff.py, test infrastructure)."""
+    n = target_lattice.n_points
+    source = source_volume(source_spacing, root)
+    out = np.empty(n, dtype=np.float64)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        _, reff = resample_reff_device(target_lattice, begin=lo, end=hi, want_reff=True, device=device, source=source)
+        out[lo:hi] = reff.cpu().numpy()
+    return out
 
 
 def upsample_reff(source_spacing: int = 15, target_spacing: int = 10, root: Path | None = None) -> pd.DataFrame:
     """Reff file contents for the *target_spacing* lattice by trilinear interpolation of the shipped
     *source_spacing* grid (same columns and rounding as reff_VMEC.py:138-165)."""
     mt = _quiet_mesh(target_spacing)
-    reff = interpolate_reff(mt.lattice, source_spacing, root, decimals=3)
+    reff = interpolate_reff(mt.lattice, source_spacing, root)
     rounded = np.round(mt.outer_cube_mesh / 1000.0, decimals=4)
     return pd.DataFrame(
         {

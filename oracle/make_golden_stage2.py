@@ -48,7 +48,7 @@ TE_SWEEP_HI = [10000, 0, 0.175, 1500, 0.38, 0.07]
 
 
 def scratch_cwd() -> str:
-    from co_monitor_b200.geometry.reff import upsample_reff, write_reff_file
+    from . import reff as oreff
 
     tmp = tempfile.mkdtemp(prefix="comonitor_ref_")
     inp = os.path.join(tmp, "input_files")
@@ -63,7 +63,7 @@ def scratch_cwd() -> str:
         os.symlink(os.path.join(ref_in, "fractional_abundance", f"fractional_abundance_{el}.dat"),
                    os.path.join(inp, "fractional_abundance", f"fractional_abundance_{el}.txt"))
     with contextlib.redirect_stdout(io.StringIO()):
-        write_reff_file(upsample_reff(15, 10), os.path.join(inp, "geometry", "reff", "Reff_coordinates-10_mm.dat"))
+        oreff.write_file(oreff.file_frame(10, 15), os.path.join(inp, "geometry", "reff", "Reff_coordinates-10_mm.dat"))
     return tmp
 
 

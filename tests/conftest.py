@@ -20,20 +20,31 @@ def golden_dir():
     return GOLDEN
 
 
-@pytest.fixture(scope="session")
-def reff10():
-    """Reff per voxel of the 10 mm lattice.  The reference's own 10 mm file is a missing blob; the repo's
-    deterministic trilinear up-sampling of the shipped 15 mm grid stands in for it (also used when the golden
-    Stage-2 vectors were generated).  Written once next to the shipped grids."""
+def _reff10_path():
+    """The reference's own 10 mm Reff file is a missing blob; the deterministic trilinear up-sampling of the shipped
+    15 mm grid (oracle/reff.py - also what the golden Stage-2 vectors were generated with) stands in for it.  Written
+    once next to the shipped grids, where ``Emissivity`` looks for it."""
     import contextlib
     import io
 
-    from co_monitor_b200.geometry.reff import reff_path, upsample_reff, write_reff_file
+    from co_monitor_b200.geometry.reff import reff_path
+    from oracle import reff as oreff
 
     path = reff_path(10)
     if not path.exists():
         with contextlib.redirect_stdout(io.StringIO()):
-            write_reff_file(upsample_reff(15, 10), path)
+            oreff.write_file(oreff.file_frame(10, 15), path)
+    return path
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _reff10_file():
+    return _reff10_path()
+
+
+@pytest.fixture(scope="session")
+def reff10(_reff10_file):
+    """Reff per voxel of the 10 mm lattice."""
     import pandas as pd
 
-    return pd.read_csv(path, sep=";").iloc[:, 4].to_numpy(dtype=float)
+    return pd.read_csv(_reff10_file, sep=";").iloc[:, 4].to_numpy(dtype=float)

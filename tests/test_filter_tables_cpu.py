@@ -133,6 +133,68 @@ def test_filter_never_rejects_a_ray_the_oracle_accepts(el, spacing, h, l, lo):
     assert skipped > 0.3 * C * len(runs)  # even in a column inside the visible region a good part of the pairs go
 
 
+# brightest voxel of each channel on the 10 mm lattice (ix, iy) - where the z-columns of a fine lattice cross the visible region
+BRIGHT_10MM = {"B": (10, 25), "C": (3, 26), "N": (9, 32), "O": (8, 25)}
+
+
+@pytest.mark.parametrize("el,spacing", [("C", 1), ("N", 1), ("C", 0.65), ("O", 0.65)])
+def test_run_cull_on_fine_lattice_columns(el, spacing):
+    """The run-level cull on the lattices of configs 3 and 5: z-columns of 250 voxels (segments 64, 64, 64, 58) and of
+    384 voxels (six segments of 64), every segment re-based from its own fp64 position as the kernel does
+    (visibility.cu: filter_kernel_lattice).  Float32 emulation against the oracle: no oracle-accepted ray in a culled
+    run, in the whole-segment test and in the groups of 8, for two columns through the visible region."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        mesh = CuboidMesh(spacing)
+        scene = make_channel(el, 10, 30, 20, lattice=mesh.lattice, host_only=True)
+    lat = mesh.lattice
+    assert lat.nz == (250 if spacing == 1 else 384)
+    t = scene.filter_tables()
+    C = 600
+    ix10, iy10 = BRIGHT_10MM[el]
+    ix = int(round(ix10 * (lat.nx - 1) / 134)), int(round(iy10 * (lat.ny - 1) / 79))
+    osc = oracle.build_scene(el, 10, 30, 20)
+    dz = (lat.step[2] * lat.rotation[2]).astype(np.float32)
+    d = [(t["det_forms"][i][:, :3].astype(np.float32) @ dz).astype(np.float32) for i in range(3)]
+    accepted = skipped = pairs = 0
+    for dx in (0, 3):
+        col = ix[1] * lat.nx + ix[0] + dx
+        idx = np.arange(col * lat.nz, (col + 1) * lat.nz)
+        ref = oracle.run_chunk(osc, gs.voxel_mesh(gs.load_db(), spacing, flat_indices=idx), want_rays=True)
+        accepted += int(ref.mask.sum())
+        for z0 in range(0, lat.nz, 64):
+            n = min(64, lat.nz - z0)
+            base = (mesh.points_at([idx[z0]]) - t["origin"]).astype(np.float32)
+            cur = [forms(t["det_forms"][i], base)[:, 0] for i in range(3)]
+            acc = [np.empty((len(cur[0]), n), np.float32) for _ in range(3)]
+            for j in range(n):
+                for i in range(3):
+                    acc[i][:, j] = cur[i]
+                    cur[i] = (cur[i] + d[i]).astype(np.float32)
+            X, Y, W = acc
+            fd = (np.abs(W) - np.maximum(np.abs(X), np.abs(Y)) >= 0)[:C].T  # (n, C)
+            sel = ref.mask[z0:z0 + n]
+            assert not (sel & ~fd).any(), "forward-differenced stage A rejected a ray the oracle accepts"
+
+            def culled(a, b):
+                m = np.float32(b - a)
+                xa, ya, wa = X[:, a], Y[:, a], W[:, a]
+                xb, yb, wb = (xa + m * d[0]).astype(np.float32), (ya + m * d[1]).astype(np.float32), (wa + m * d[2]).astype(np.float32)
+                return ((np.abs(xa) > np.abs(wa)) & (np.abs(xb) > np.abs(wb)) & (xa * xb > 0)) | \
+                       ((np.abs(ya) > np.abs(wa)) & (np.abs(yb) > np.abs(wb)) & (ya * yb > 0))
+
+            runs = [(0, n - 1)] + [(a, a + 7) for a in range(0, n - 7, 8)]
+            if n % 8:
+                runs.append((n - n % 8, n - 1))  # the ragged tail is one more run
+            for a, b in runs:
+                c = culled(a, b)[:C]
+                assert not (sel[a:b + 1] & c[None, :]).any(), f"z0={z0} run [{a},{b}] culled although the oracle accepts a ray in it"
+                assert not (fd[a:b + 1] & c[None, :]).any(), "a culled run holds a voxel that passes stage A"
+                skipped += int(c.sum())
+                pairs += C
+    assert accepted > 50, accepted
+    assert skipped > 0.3 * pairs
+
+
 def test_padding_lanes_never_pass():
     with contextlib.redirect_stdout(io.StringIO()):
         mesh = CuboidMesh(20)

@@ -1,5 +1,6 @@
-"""Reff provider: the NumPy resampling against itself on CPU, the CUDA kernels
-(com_reff_resample / com_reff_quadratic) against the NumPy forms on the GPU - bit-exact for the resampling."""
+"""Reff provider: the oracle's NumPy resampling (oracle/reff.py) against the shipped
+grids on CPU, the CUDA kernels (com_reff_resample / com_reff_quadratic) against the oracle on the GPU - bit-exact for
+the resampling."""
 import contextlib
 import io
 
@@ -8,6 +9,7 @@ import pytest
 
 from co_monitor_b200.geometry import reff as R
 from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+from oracle import reff as oreff
 
 
 def _mesh(spacing):
@@ -20,17 +22,24 @@ def _mm(reff):
     return np.where(np.isnan(mm), 65535, np.clip(mm, 0, 65534)).astype(np.uint16)
 
 
-def test_pointwise_resampling_equals_whole_lattice_resampling(reff10):
+def _shape(lat):
+    return lat.nx, lat.ny, lat.nz
+
+
+def test_oracle_resampling_is_consistent(reff10):
     lat = _mesh(10).lattice
-    whole = R.interpolate_reff(lat)
-    np.testing.assert_array_equal(whole, reff10)  # the committed 10 mm table is this resampling
+    whole = oreff.on_lattice(_shape(lat))
+    np.testing.assert_array_equal(whole, reff10)  # the 10 mm table the Stage-2 fixtures were generated with
     rng = np.random.default_rng(0)
     flat = np.concatenate((rng.integers(0, lat.n_points, 20000), [0, lat.n_points - 1]))
-    np.testing.assert_array_equal(R.interpolate_reff_at(lat, flat), whole[flat])
-    # a shard addresses the same voxels through local indices
-    sh = lat.shard(3, 1, cols_per_block=8)
-    loc = rng.integers(0, sh.n_points, 5000)
-    np.testing.assert_array_equal(R.interpolate_reff_at(sh, loc), whole[sh.local_to_global(loc)])
+    np.testing.assert_array_equal(oreff.on_lattice(_shape(lat), flat), whole[flat])
+    # resampling a shipped grid onto its own lattice returns it (the lattices share their end points)
+    for spacing in (15, 30):
+        l2 = _mesh(spacing).lattice
+        vol = oreff.shipped_volume(spacing)
+        np.testing.assert_array_equal(oreff.on_lattice(_shape(l2), source_spacing=spacing), np.round(vol.ravel(), 3))
+    # the product's host view of a shipped grid is the oracle's
+    np.testing.assert_array_equal(R.source_volume(15)[0], oreff.shipped_volume(15))
 
 
 def test_provider_refuses_to_run_without_cuda():
@@ -45,12 +54,13 @@ def test_provider_refuses_to_run_without_cuda():
 
 
 @pytest.mark.gpu
-def test_resample_kernel_is_bit_identical_to_numpy(reff10):
+def test_resample_kernel_is_bit_identical_to_the_oracle(reff10):
     import torch
 
     lat = _mesh(10).lattice
     mm, reff = R.resample_reff_device(lat, want_reff=True)
-    np.testing.assert_array_equal(reff.cpu().numpy(), reff10)  # NaN positions included
+    np.testing.assert_array_equal(reff.cpu().numpy(), oreff.on_lattice(_shape(lat)))  # NaN positions included
+    np.testing.assert_array_equal(R.interpolate_reff(lat), reff10)  # the host-array form of the same kernel
     np.testing.assert_array_equal(mm.cpu().numpy(), _mm(reff10))
     # the pipeline's own conversion of the float table gives the same bins
     from co_monitor_b200.pipeline import reff_to_mm
@@ -79,13 +89,13 @@ def test_resample_kernel_on_fine_lattice_slabs():
             lo = int(lat.n_points * frac)
             hi = lo + 150_000
             mm, reff = R.resample_reff_device(lat, begin=lo, end=hi, want_reff=True, source=src)
-            want = R.interpolate_reff_at(lat, np.arange(lo, hi), source=src)
+            want = oreff.on_lattice(_shape(lat), np.arange(lo, hi))
             np.testing.assert_array_equal(reff.cpu().numpy(), want)
             np.testing.assert_array_equal(mm.cpu().numpy(), _mm(want))
         sh = lat.shard(8, 5)
         lo = sh.n_points // 2
         mm, _ = R.resample_reff_device(sh, begin=lo, end=lo + 100_000, source=src)
-        np.testing.assert_array_equal(mm.cpu().numpy(), _mm(R.interpolate_reff_at(sh, np.arange(lo, lo + 100_000), source=src)))
+        np.testing.assert_array_equal(mm.cpu().numpy(), _mm(oreff.on_lattice(_shape(sh), sh.local_to_global(np.arange(lo, lo + 100_000)))))
 
 
 @pytest.mark.gpu

@@ -374,7 +374,7 @@ def test_loglog_pec_extension(tmp_path):
 
     from co_monitor_b200.emissivity.engine import LineTables
     from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
-    from co_monitor_b200.emissivity.pec import loglog_on_nodes
+    from oracle.extensions import loglog_pec as loglog_on_nodes
     from co_monitor_b200.emissivity.reader import Emissivity
 
     prof_df = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df
