@@ -50,6 +50,22 @@ class ComAperture(C.Structure):
         return np.array([list(self.vertex[k]) for k in range(self.n_edges)])
 
 
+COM_MAX_SHIELDS = 4
+COM_PHYS_SEGMENT_CHECK = 1
+
+
+class ComShield(C.Structure):
+    _fields_ = [
+        ("centre", c_double3),
+        ("axis", c_double3),
+        ("u", c_double3),
+        ("v", c_double3),
+        ("radius", C.c_double),
+        ("n_sides", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class ComSceneDesc(C.Structure):
     _fields_ = [
         ("n_crystal", C.c_int32),
@@ -76,6 +92,10 @@ class ComSceneDesc(C.Structure):
         ("n_voxel_corners", C.c_int32),
         ("filter_flags", C.c_int32),
         ("voxel_corners", (C.c_double * 3) * 8),
+        ("near_band_mm", C.c_double),
+        ("physics_flags", C.c_int32),
+        ("n_shields", C.c_int32),
+        ("shields", C.POINTER(ComShield)),
     ]
 
 
@@ -106,11 +126,18 @@ class ComStats(C.Structure):
         ("candidate_capacity", C.c_uint64),
         ("overflow", C.c_uint64),
         ("certain_candidates", C.c_uint64),
+        ("near_band_rays", C.c_uint64),
+        ("shield_blocked_rays", C.c_uint64),
+        ("segment_rejected_rays", C.c_uint64),
+        ("reserved", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
         return {name: int(getattr(self, name)) for name, _ in self._fields_ }
 
+
+#: number of 64-bit words of a device-side ComStats block
+N_STATS = len(ComStats._fields_)
 
 COM_MAX_TRANSITIONS = 4
 COM_MM_BINS = 4096

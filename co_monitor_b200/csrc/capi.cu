@@ -33,23 +33,32 @@ namespace com {
 namespace {
 // One arena per host thread: the *_host entry points may be called concurrently from several threads (one channel
 // per thread), each on its own per-thread CUDA stream.
-thread_local char* g_arena_dev = nullptr;
-thread_local size_t g_arena_dev_cap = 0;
-thread_local int g_arena_device = -1;
-thread_local char* g_arena_pinned = nullptr;
-thread_local size_t g_arena_pinned_cap = 0;
+struct ThreadArena {
+  char* dev = nullptr;
+  size_t dev_cap = 0;
+  int device = -1;
+  char* pinned = nullptr;
+  size_t pinned_cap = 0;
+  void release() {
+    // at process exit the CUDA context may already be gone: the calls then fail harmlessly
+    if (dev) cudaFree(dev);
+    if (pinned) cudaFreeHost(pinned);
+    dev = pinned = nullptr;
+    dev_cap = pinned_cap = 0;
+    device = -1;
+    cudaGetLastError();
+  }
+  ~ThreadArena() { release(); }  // a worker thread that exits gives its blocks back
+};
+thread_local ThreadArena g_arena;
+#define g_arena_dev g_arena.dev
+#define g_arena_dev_cap g_arena.dev_cap
+#define g_arena_device g_arena.device
+#define g_arena_pinned g_arena.pinned
+#define g_arena_pinned_cap g_arena.pinned_cap
 }  // namespace
 
-void HostArena::lock() {}
-void HostArena::unlock() {}
-
-void HostArena::release_all() {
-  if (g_arena_dev) cudaFree(g_arena_dev);
-  if (g_arena_pinned) cudaFreeHost(g_arena_pinned);
-  g_arena_dev = g_arena_pinned = nullptr;
-  g_arena_dev_cap = g_arena_pinned_cap = 0;
-  g_arena_device = -1;
-}
+void HostArena::release_all() { g_arena.release(); }
 
 int HostArena::reserve(size_t device_bytes, size_t pinned_bytes, char** device_out, char** pinned_out) {
   int dev = 0;
@@ -380,7 +389,6 @@ static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* la
   const size_t b_wc = dense ? 0 : b_w;
   const size_t b_misc = 512;
   const size_t total = b_scene + b_w + b_n + b_vox + b_rays + b_idx + b_wc + b_misc + align_up(cws_bytes, 256) + ws_bytes;
-  com::HostArenaGuard guard;
   char *d = nullptr, *pin = nullptr;
   rc = com::HostArena::reserve(total, align_up(blob.bytes.size(), 256) + 512, &d, &pin);
   if (rc) return rc;
@@ -488,7 +496,6 @@ int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* latti
 }
 
 int com_host_arena_release(void) {
-  com::HostArenaGuard guard;
   com::HostArena::release_all();
   return COM_OK;
 }

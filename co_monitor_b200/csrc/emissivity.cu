@@ -642,11 +642,8 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
     COM_CUDA(cudaGetLastError());
   } else if (n > 0) {
     const size_t smem = sizeof(double) * K;
-    static bool attr_set = false;
-    if (!attr_set) {
-      COM_CUDA(cudaFuncSetAttribute(com::weight_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-      attr_set = true;
-    }
+    // per device and cheap: set it on every call rather than remember it per process
+    COM_CUDA(cudaFuncSetAttribute(com::weight_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
     const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 4);
     if (!mapped_reff_max) com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
     com::weight_histogram_kernel<<<blocks, com::kK2Threads, smem, s>>>(P);
@@ -761,7 +758,6 @@ static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_
   const size_t b_pv = per_voxel_out_h ? align_up(sizeof(double) * (size_t)n * ncol, 256) : 0;
   const size_t b_valid = valid_out_h ? align_up((size_t)n, 256) : 0;
   const size_t up = b_tab + b_prof + 2 * b_n;  // staged through pinned memory in one copy
-  com::HostArenaGuard guard;
   char *d = nullptr, *pin = nullptr;
   rc = com::HostArena::reserve(up + b_pv + b_valid + 256 + ws, up + 256, &d, &pin);
   if (rc) return rc;

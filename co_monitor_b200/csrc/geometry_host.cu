@@ -184,7 +184,8 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   if (d.n_crystal <= 0 || d.n_slits <= 0 || !d.crystal_xyz || !d.crystal_normal || !d.slit_crys_side ||
       !d.slit_plasma_side || !d.port_vertices || !d.detector_vertices || d.n_port_vertices < 3 ||
       d.n_port_vertices > 16 || d.n_detector_vertices < 3 || d.n_detector_vertices > 16 ||
-      d.n_voxel_corners < 0 || d.n_voxel_corners > 8) {
+      d.n_voxel_corners < 0 || d.n_voxel_corners > 8 || d.n_shields < 0 || d.n_shields > COM_MAX_SHIELDS ||
+      (d.n_shields > 0 && !d.shields)) {
     set_error("com_scene_create: incomplete or inconsistent scene description");
     return COM_E_BADARG;
   }
@@ -201,6 +202,20 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
 
   // ---- apertures: crys_0, plasma_0, crys_1, ..., port, detector -------------------------------------
   dv.near_edge_mm = d.near_edge_mm > 0 ? d.near_edge_mm : 1e-9;
+  dv.near_band_mm = std::max(dv.near_edge_mm, d.near_band_mm > 0 ? d.near_band_mm : 1e-4);
+  dv.physics_flags = d.physics_flags;
+  dv.n_shields = d.n_shields;
+  for (int s = 0; s < d.n_shields; ++s) {
+    const ComShield& sh = d.shields[s];
+    const V3 a = load(sh.axis), u = load(sh.u), v = load(sh.v);
+    if (!(sh.radius > 0) || sh.n_sides < 0 || sh.n_sides == 1 || sh.n_sides == 2 || std::fabs(norm(a) - 1) > 1e-9 ||
+        std::fabs(norm(u) - 1) > 1e-9 || std::fabs(norm(v) - 1) > 1e-9 || std::fabs(dot(a, u)) > 1e-9 ||
+        std::fabs(dot(a, v)) > 1e-9 || std::fabs(dot(u, v)) > 1e-9) {
+      set_error("shield %d: radius must be positive and (axis, u, v) orthonormal", s);
+      return COM_E_GEOMETRY;
+    }
+    dv.shields[s] = sh;
+  }
   hs.apertures.assign(dv.n_apertures, ComAperture{});
   if (d.apertures_override) {
     for (int a = 0; a < dv.n_apertures; ++a) {
@@ -283,6 +298,11 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   dv.slit_period = (float)period;
   dv.slit_inv_period = (float)(1.0 / period);
   dv.slit_period_d = periodic ? period : 0.0;
+  dv.slit_xlo_d = 1e300, dv.slit_xhi_d = -1e300;
+  for (int k = 0; k < c0.n_edges; ++k) {
+    dv.slit_xlo_d = std::min(dv.slit_xlo_d, c0.vertex[k][0]);
+    dv.slit_xhi_d = std::max(dv.slit_xhi_d, c0.vertex[k][0]);
+  }
   auto rect_of = [&](const ComAperture& ap, double grow, double& xlo, double& xhi, double& ylo, double& yhi) {
     xlo = ylo = 1e300, xhi = yhi = -1e300;
     for (int k = 0; k < ap.n_edges; ++k) {

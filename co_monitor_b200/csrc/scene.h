@@ -42,9 +42,14 @@ struct DeviceScene {
   SlitRect inner_crys, inner_plasma;
   float certain_mm;
   double slit_period_d;  // 0 when the collimator is not periodic (exact kernel then tries every slit)
+  double slit_xlo_d, slit_xhi_d;  // extent along e1 of the crystal-side polygon of slit 0 (which neighbours a hit can be in)
   double origin[3];
   double area_pt, refl_max, aoi0, refl_sigma;
   double near_edge_mm;
+  double near_band_mm;           // second near-edge counter (>= near_edge_mm)
+  int physics_flags;             // COM_PHYS_* (extensions; 0 on the parity path)
+  int n_shields;
+  ComShield shields[COM_MAX_SHIELDS];  // circular stops (extension), by value: a few hundred bytes
   const double* crystal_xyz;     // (C,3) global
   const double* crystal_normal;  // (C,3)
   const DevAperture* apertures;  // (2S+2)
@@ -77,18 +82,12 @@ void set_error(const char* fmt, ...);
 
 // Grow-only device block + pinned staging block kept per host thread by the synchronous *_host entry points, so that a
 // reference-facing call does not pay cudaMalloc/cudaFree (both synchronise the device) every time.  Each thread
-// works on its own per-thread CUDA stream, so calls from different threads overlap on the device.
+// works on its own per-thread CUDA stream and its own blocks, so calls from different threads overlap on the device
+// and need no lock; the blocks are freed when the thread exits (or by com_host_arena_release).
 // reserve() returns COM_OK or COM_E_*.
 struct HostArena {
-  static void lock();
-  static void unlock();
   static int reserve(size_t device_bytes, size_t pinned_bytes, char** device_out, char** pinned_out);
-  static void release_all();  // frees both blocks (com_host_arena_release)
-};
-
-struct HostArenaGuard {
-  HostArenaGuard() { HostArena::lock(); }
-  ~HostArenaGuard() { HostArena::unlock(); }
+  static void release_all();  // frees the calling thread's blocks (com_host_arena_release)
 };
 
 }  // namespace com
@@ -98,5 +97,5 @@ struct ComScene {
   std::vector<ComAperture> apertures_h;
   void* d_blob = nullptr;  // single device allocation holding all tables
   double filter_eps_mm = 0;
-  int device = 0;
+  int device = -1;  // device holding d_blob (-1: tables live in a caller-managed arena)
 };

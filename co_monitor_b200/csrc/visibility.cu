@@ -440,11 +440,12 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1b: the reference arithmetic, one candidate ray per thread.
+// K1b: the reference arithmetic, one candidate ray per thread (grid-stride over the candidate list).
 struct HitResult {
   bool pass;
   double margin;
   double x, y;  // in-plane coordinates along e1, e2 (x picks the slit; both address the detector image)
+  double s;     // line parameter of the hit: X = dst + s (src - dst)
 };
 
 // simulation.py:143-173 (+175-207): line through `dst` with direction src - dst against the aperture plane,
@@ -453,7 +454,7 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
                                                   const float* __restrict__ edges_f, float tau, D3 src, D3 dst) {
   const D3 N = ld3(ap.normal), u = src - dst;
   const double ndotu = dot(N, u);
-  if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0, 0.0};  // the reference writes NaN -> never inside
+  if (fabs(ndotu) < 1e-6) return {false, -1e300, 0.0, 0.0, 0.0};  // the reference writes NaN -> never inside
   const D3 w = dst - ld3(ap.p1);
   const double si = -(dot(N, w) / ndotu);
   const D3 r = w + si * u;  // X - p1
@@ -466,12 +467,42 @@ __device__ __forceinline__ HitResult aperture_hit(const DevAperture& ap, const d
     const float* ef = edges_f + 3 * ap.edge_offset;
     float mf = 3.0e38f;
     for (int k = 0; k < ap.n_edges; ++k) mf = fminf(mf, fmaf(ef[3 * k], xf, fmaf(ef[3 * k + 1], yf, ef[3 * k + 2])));
-    if (fabsf(mf) > tau) return {mf > 0.f, (double)mf, x, y};
+    if (fabsf(mf) > tau) return {mf > 0.f, (double)mf, x, y, si};
   }
   double m = 1e300;
   const double* e = edges + 3 * ap.edge_offset;
   for (int k = 0; k < ap.n_edges; ++k) m = fmin(m, e[3 * k] * x + e[3 * k + 1] * y + e[3 * k + 2]);
-  return {m >= 0.0, m, x, y};
+  return {m >= 0.0, m, x, y, si};
+}
+
+// Extension (off on the parity path): one ECRH shield as a circular stop - the line src -> dst against the shield's
+// mid-plane, inside the regular n-gon rim (ComShield).  margin > 0 inside.  A line parallel to the plane never goes
+// through the stop.
+__device__ __forceinline__ HitResult shield_hit(const ComShield& sh, D3 src, D3 dst) {
+  const D3 a = ld3(sh.axis), u = src - dst;
+  const double adotu = dot(a, u);
+  if (fabs(adotu) < 1e-12) return {false, -1e300, 0.0, 0.0, 0.0};
+  const D3 w = dst - ld3(sh.centre);
+  const double si = -(dot(a, w) / adotu);
+  const D3 r = w + si * u;
+  const double x = dot(r, ld3(sh.u)), y = dot(r, ld3(sh.v));
+  const double rr = sqrt(x * x + y * y);
+  if (sh.n_sides <= 0) return {sh.radius - rr >= 0.0, sh.radius - rr, x, y, si};
+  const double step = 6.283185307179586 / (double)sh.n_sides;
+  const double inr = sh.radius * cos(0.5 * step);  // inradius of the rim polygon
+  double m = inr - rr;                              // >= 0: inside whatever the direction
+  if (m < 0.0 || m < 1e-2) {
+    // between inradius and circumradius (or close): the edge of the hit's own sector and its two neighbours decide
+    double phi = atan2(y, x);
+    if (phi < 0.0) phi += 6.283185307179586;
+    const int k0 = (int)floor(phi / step);
+    m = 1e300;
+    for (int dk = -1; dk <= 1; ++dk) {
+      const double th = ((double)(k0 + dk) + 0.5) * step;
+      m = fmin(m, inr - (x * cos(th) + y * sin(th)));
+    }
+  }
+  return {m >= 0.0, m, x, y, si};
 }
 
 constexpr int kExactThreads = 256;
@@ -480,17 +511,18 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   extern __shared__ __align__(16) unsigned char s_raw[];
   const DeviceScene& sc = P.sc;
   // front region (certain first, or everything from the explicit-voxel kernel) and back region (uncertain)
-  const unsigned long long n_front = min(P.counters[0], P.cand_capacity);
-  const unsigned long long n_back = min(P.counters[2], P.cand_capacity - n_front);
-  const unsigned long long n = n_front + n_back;
-  if ((unsigned long long)blockIdx.x * kExactThreads >= n) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      P.stats->candidates = P.counters[0] + P.counters[2];
-      P.stats->candidate_capacity = P.cand_capacity;
-      P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
-    }
-    return;
+  const unsigned long long total = P.counters[0] + P.counters[2];
+  const bool overflow = total > P.cand_capacity;  // the two regions collided: nothing of this launch can be trusted
+  const unsigned long long n_front = overflow ? 0ull : P.counters[0];
+  const unsigned long long n = overflow ? 0ull : total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    P.stats->candidates = total;
+    P.stats->certain_candidates = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
+    P.stats->candidate_capacity = P.cand_capacity;
+    P.stats->overflow = overflow ? 1 : 0;
+    P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
   }
+  if ((unsigned long long)blockIdx.x * kExactThreads >= n) return;
   // apertures + edge pool -> shared memory (a few kB)
   DevAperture* s_ap = reinterpret_cast<DevAperture*>(s_raw);
   double* s_edges = reinterpret_cast<double*>(s_raw + sizeof(DevAperture) * sc.n_apertures);
@@ -509,12 +541,13 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   __syncthreads();
 
   const int S = sc.n_slits;
-  unsigned int n_pass = 0, n_edge = 0, n_vis = 0;
-  const double kNear = sc.near_edge_mm;
-  // FP32 edge distances decide beyond this; twice the near-edge radius so that the near-edge count stays exact
-  const float tau = fmaxf(2.0e-3f, 2.f * (float)sc.near_edge_mm);
-  const unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x;
-  if (i < n) {
+  unsigned int n_pass = 0, n_edge = 0, n_band = 0, n_vis = 0, n_shield = 0, n_seg = 0;
+  const double kNear = sc.near_edge_mm, kBand = sc.near_band_mm;
+  const bool seg_check = (sc.physics_flags & COM_PHYS_SEGMENT_CHECK) != 0;
+  // FP32 edge distances decide beyond this; twice the near-edge radii so that the near-edge counts stay exact
+  const float tau = fmaxf(2.0e-3f, 2.f * (float)sc.near_band_mm);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * kExactThreads) {
     const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
@@ -526,58 +559,74 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     const D3 r = d - (2.0 * dot(d, nrm)) * nrm;
     const D3 reflected = c + r, plasma = c - d, crystal = p + d;
 
-    bool near_edge = false;
+    double near = 1e300;      // smallest |margin| over the apertures this ray was tested on
+    bool seg_ok = true;       // every accepted hit lies on the physical part of its line (extension)
+    auto note = [&](const HitResult& h) { near = fmin(near, fabs(h.margin)); };
     HitResult h = aperture_hit(s_ap[2 * S], s_edges, s_edges_f, tau, plasma, crystal);  // port :372-384
-    near_edge |= fabs(h.margin) < kNear;
+    note(h);
     bool ok = h.pass;
+    seg_ok = seg_ok && h.s >= 0.0 && h.s <= 1.0;
     if (ok && !certain) {  // collimator :344-369, the same slit on both sides
       auto both_sides = [&](int k) {
         const HitResult a = aperture_hit(s_ap[2 * k], s_edges, s_edges_f, tau, plasma, crystal);
-        near_edge |= fabs(a.margin) < kNear;
+        note(a);
         if (!a.pass) return false;
         const HitResult b = aperture_hit(s_ap[2 * k + 1], s_edges, s_edges_f, tau, plasma, crystal);
-        near_edge |= fabs(b.margin) < kNear;
+        note(b);
+        if (b.pass) seg_ok = seg_ok && a.s >= 0.0 && a.s <= 1.0 && b.s >= 0.0 && b.s <= 1.0;
         return b.pass;
       };
       // the slit the FP32 filter saw is tried first: "any slit passes" is all the reference asks (:408-411)
       ok = slit_hint < S && slit_hint != kSlitUnknown && both_sides(slit_hint);
       if (!ok) {
         int k_first = -1, k_lo = 0, k_hi = S - 1;
-        bool try_neighbours = true;
         if (sc.slit_period_d > 0.0) {
-          // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slit that can contain it
+          // slit k is slit 0 moved by k*T along e1, so the hit on slit 0's plane names the only slits that can contain
+          // it: k0 = floor(x / T), k0 + 1 when the hit is within slit 0's reach below a period boundary (its polygon
+          // starts at xlo < 0), k0 - 1 when it is within its reach above one (xhi > T)
           const HitResult h0 = aperture_hit(s_ap[0], s_edges, s_edges_f, tau, plasma, crystal);
           if (h0.margin == -1e300) {
             k_hi = -1;  // parallel to the collimator plane: NaN in the reference
           } else {
-            const double q = h0.x / sc.slit_period_d;
+            const double T = sc.slit_period_d, q = h0.x / T;
             const int k0 = (int)floor(q);
+            const double off = (q - floor(q)) * T;  // position inside the period, [0, T)
             k_first = min(max(k0, 0), S - 1);
-            k_lo = max(0, k0 - 1), k_hi = min(S - 1, k0 + 1);
-            // neighbours matter only near a period boundary (polygon skew is 0.02 mm at most)
-            const double fr = q - floor(q);
-            try_neighbours = fr < 0.05 || fr > 0.95;
+            k_lo = off <= sc.slit_xhi_d - T + 1e-3 ? max(0, k0 - 1) : max(0, k0);
+            k_hi = off >= T + sc.slit_xlo_d - 1e-3 ? min(S - 1, k0 + 1) : min(S - 1, k0);
           }
         }
         if (k_hi >= 0) {
-          if (k_first >= 0) {
-            ok = k_first != slit_hint && both_sides(k_first);
-            if (!ok && try_neighbours)
-              for (int k = k_lo; k <= k_hi && !ok; ++k)
-                if (k != k_first && k != slit_hint) ok = both_sides(k);
-          } else {
-            for (int k = k_lo; k <= k_hi && !ok; ++k)
-              if (k != slit_hint) ok = both_sides(k);
-          }
+          if (k_first >= 0) ok = k_first != slit_hint && both_sides(k_first);
+          for (int k = k_lo; k <= k_hi && !ok; ++k)
+            if (k != k_first && k != slit_hint) ok = both_sides(k);
         }
       }
     }
     if (ok) {
       h = aperture_hit(s_ap[2 * S + 1], s_edges, s_edges_f, tau, reflected, crystal);  // detector :387-400
-      near_edge |= fabs(h.margin) < kNear;
+      note(h);
       ok = h.pass;
+      seg_ok = seg_ok && h.s >= 0.0;
     }
-    n_edge += near_edge ? 1u : 0u;
+    n_edge += near < kNear ? 1u : 0u;
+    n_band += near < kBand ? 1u : 0u;
+    if (ok && seg_check && !seg_ok) {  // extension: the reference's infinite lines accept it, the physical ray does not
+      ++n_seg;
+      ok = false;
+    }
+    if (ok && sc.n_shields > 0) {  // extension: every ECRH shield of the channel is a circular stop
+      bool through = true;
+      for (int q = 0; q < sc.n_shields && through; ++q) {
+        const HitResult g = shield_hit(sc.shields[q], plasma, crystal);
+        if (fabs(g.margin) < kBand) ++n_band;
+        through = g.pass && (!seg_check || (g.s >= 0.0 && g.s <= 1.0));
+      }
+      if (!through) {
+        ++n_shield;
+        ok = false;
+      }
+    }
     if (ok) {
       // simulation.py:494-497, 516-531, 564-577
       const D3 v = plasma - crystal, rc = reflected - crystal;
@@ -613,32 +662,25 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   }
 
   // block-level stats
-  __shared__ unsigned int s_acc[3];
-  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
+  constexpr int kStats = 6;
+  __shared__ unsigned int s_acc[kStats];
+  if (threadIdx.x < kStats) s_acc[threadIdx.x] = 0;
   __syncthreads();
-  for (int off = 16; off; off >>= 1) {
-    n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);
-    n_edge += __shfl_down_sync(0xffffffffu, n_edge, off);
-    n_vis += __shfl_down_sync(0xffffffffu, n_vis, off);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_acc[0], n_pass);
-    atomicAdd(&s_acc[1], n_edge);
-    atomicAdd(&s_acc[2], n_vis);
+  unsigned int mine[kStats] = {n_pass, n_edge, n_vis, n_band, n_shield, n_seg};
+#pragma unroll
+  for (int q = 0; q < kStats; ++q) {
+    unsigned int v = mine[q];
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc[q], v);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
-    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->near_edge_rays, (unsigned long long)s_acc[1]);
-    if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[2]);
-    if (blockIdx.x == 0) {
-      const unsigned long long total = P.counters[0] + P.counters[2];
-      P.stats->candidates = total;
-      P.stats->certain_candidates = (P.sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
-      P.stats->candidate_capacity = P.cand_capacity;
-      P.stats->overflow = total > P.cand_capacity ? 1 : 0;
-      P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
-    }
+    unsigned long long* out[kStats] = {(unsigned long long*)&P.stats->passing_rays, (unsigned long long*)&P.stats->near_edge_rays,
+                                       (unsigned long long*)&P.stats->visible_voxels, (unsigned long long*)&P.stats->near_band_rays,
+                                       (unsigned long long*)&P.stats->shield_blocked_rays,
+                                       (unsigned long long*)&P.stats->segment_rejected_rays};
+    for (int q = 0; q < kStats; ++q)
+      if (s_acc[q]) atomicAdd(out[q], (unsigned long long)s_acc[q]);
   }
 }
 
@@ -783,6 +825,12 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     set_error("%s failed: %s", #x, cudaGetErrorString(e));                 \
     return COM_E_CUDA;                                                     \
   }
+  int dev = 0, sms = 0;
+  COM_CUDA(cudaGetDevice(&dev));
+  if (scene->device >= 0 && scene->device != dev) {
+    set_error("com_visibility_weights: the scene lives on device %d, the current device is %d", scene->device, dev);
+    return COM_E_BADARG;
+  }
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
   COM_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(ComStats), stream));
   if (n_vox) COM_CUDA(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)n_vox, stream));
@@ -790,8 +838,6 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   if (rays_count_out) COM_CUDA(cudaMemsetAsync(rays_count_out, 0, sizeof(unsigned long long), stream));
   if (n_vox == 0) return COM_OK;
 
-  int dev = 0, sms = 0;
-  COM_CUDA(cudaGetDevice(&dev));
   COM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int threads = P.warps_per_cta * 32;
   int occ = 0;
@@ -815,10 +861,15 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   COM_CUDA(cudaGetLastError());
   if (g_timing_on) cudaEventRecord(g_ev[1], stream);
   {
-    // one thread per candidate slot; blocks beyond the actual count exit at once
-    const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
-    const unsigned int blocks = (unsigned int)std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, 0x7fffffffull);
+    // grid-stride over the candidate list: at most a few blocks per SM, whatever the list's capacity (a grid sized by
+    // the capacity costs ~4 ns per empty block: 13 ms per launch of 6.7e7 voxels at the default 2 % capacity)
     const size_t smem = sizeof(DevAperture) * P.sc.n_apertures + (sizeof(double) + sizeof(float)) * 3 * P.sc.n_edges_total;
+    int occ_x = 0;
+    COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_x, exact_kernel, kExactThreads, smem));
+    if (occ_x < 1) occ_x = 1;
+    const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
+    const unsigned int blocks = (unsigned int)std::max<unsigned long long>(
+        1, std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, (unsigned long long)sms * occ_x * 4ull));
     exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
   }
   COM_CUDA(cudaGetLastError());

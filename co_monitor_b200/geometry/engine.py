@@ -65,7 +65,11 @@ class ChannelScene:
     def __init__(self, crystal_points, normals, slit_crys, slit_plasma, vector_front_back, port_vertices,
                  port_ov, det_vertices, det_ov, origin, area_pt, refl_max, aoi0, refl_sigma=2.2,
                  voxel_corners=None, filter_eps_mm=DEFAULT_FILTER_EPS_MM, calibrate_apertures=True,
-                 near_edge_mm=0.0, host_only=False, run_cull=True):
+                 near_edge_mm=0.0, host_only=False, run_cull=True, near_band_mm=0.0, segment_check=False, shields=None):
+        """*near_edge_mm* / *near_band_mm*: widths of the two near-edge counters (defaults 1e-9 and 1e-4 mm).
+        Extensions, off by default (not reference behaviour): *segment_check* accepts an aperture hit only on the
+        physical part of the ray's line; *shields* is a list of ``ComShield``-like dicts (see ``ecrh_shields``) every
+        ray must also pass."""
         self._lib = _lib.load()
         self._keep = {}
 
@@ -95,6 +99,20 @@ class ChannelScene:
         d.filter_eps_mm = float(filter_eps_mm)
         d.near_edge_mm = float(near_edge_mm)
         d.filter_flags = 0 if run_cull else 1  # COM_FILTER_NO_RUN_CULL: every ray's detector test evaluated on its own
+        d.near_band_mm = float(near_band_mm)
+        d.physics_flags = _lib.COM_PHYS_SEGMENT_CHECK if segment_check else 0
+        if shields:
+            if len(shields) > _lib.COM_MAX_SHIELDS:
+                raise ValueError(f"at most {_lib.COM_MAX_SHIELDS} shields per channel")
+            arr_s = (_lib.ComShield * len(shields))()
+            for q, sh in enumerate(shields):
+                for i in range(3):
+                    arr_s[q].centre[i], arr_s[q].axis[i] = float(sh["centre"][i]), float(sh["axis"][i])
+                    arr_s[q].u[i], arr_s[q].v[i] = float(sh["u"][i]), float(sh["v"][i])
+                arr_s[q].radius, arr_s[q].n_sides = float(sh["radius"]), int(sh.get("n_sides", 360))
+            self._keep["shields"] = arr_s
+            d.n_shields = len(shields)
+            d.shields = C.cast(arr_s, C.POINTER(_lib.ComShield))
         self.aperture_shifts = None
         if calibrate_apertures:
             arr, self.aperture_shifts = build_apertures(
@@ -230,7 +248,7 @@ class ChannelScene:
             stream = torch.cuda.current_stream().cuda_stream
             w = torch.empty(n, dtype=torch.float64, device=device)
             nr = torch.empty(n, dtype=torch.int32, device=device)
-            stats_t = torch.empty(8, dtype=torch.int64, device=device)
+            stats_t = torch.empty(_lib.N_STATS, dtype=torch.int64, device=device)
             frac = candidate_fraction
             rays_cap = 0
             for attempt in range(max_retries + 1):
@@ -318,7 +336,7 @@ class VisibilityPlan:
         with torch.cuda.device(self.device):
             self.weight = torch.empty(n, dtype=torch.float64, device=self.device)
             self.nrays = torch.empty(n, dtype=torch.int32, device=self.device)
-            self.stats_t = torch.zeros(8, dtype=torch.int64, device=self.device)
+            self.stats_t = torch.zeros(_lib.N_STATS, dtype=torch.int64, device=self.device)
             self.ws_bytes = scene._lib.com_visibility_workspace_bytes(scene.handle, n, candidate_fraction)
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self._stats = self.stats_t

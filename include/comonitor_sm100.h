@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define COM_ABI_VERSION 2
+#define COM_ABI_VERSION 3
 
 #define COM_OK 0
 #define COM_E_BADARG (-1)   /* null pointer, bad size, inconsistent description            */
@@ -51,6 +51,26 @@ typedef void* com_stream_t; /* cudaStream_t */
 
 #define COM_MAX_EDGES 32
 #define COM_FILTER_NO_RUN_CULL 1
+#define COM_MAX_SHIELDS 4
+/* ComSceneDesc.physics_flags - optional physics the reference does not compute; 0 = parity path */
+#define COM_PHYS_SEGMENT_CHECK 1 /* an aperture only counts where the physical ray meets it: on the segment voxel ->
+                                    crystal point for slits, port and shields, on the half-line leaving the crystal for
+                                    the detector.  The reference intersects infinite lines (simulation.py:143-173) */
+
+/* One ECRH stray-radiation shield reduced to a circular stop (extension; the reference only draws the shields:
+ * radiation_shield.py:52-101 builds, per shield, a 1 mm long cylinder of `radius` around `central point` along
+ * `orientation vector`, 360 vertices per rim, and takes its convex hull).  A ray passes the shield iff the point where
+ * its line meets the mid-plane of that cylinder lies inside the hull's cross-section: the regular n_sides-gon with
+ * vertex k at  centre + radius * (cos(2 pi k / n_sides) u + sin(2 pi k / n_sides) v). */
+typedef struct ComShield {
+  double centre[3]; /* point of the mid-plane on the cylinder axis                           */
+  double axis[3];   /* unit normal of the plane (cylinder axis)                              */
+  double u[3];      /* in-plane orthonormal basis; vertex 0 of the rim polygon lies along +u */
+  double v[3];
+  double radius;    /* circumradius of the rim polygon, mm                                    */
+  int32_t n_sides;  /* 360 in the reference's model; 0 = a true circle                        */
+  int32_t reserved;
+} ComShield;
 
 /* One aperture of the beam line reduced to "plane + convex polygon in that plane".
  * The reference tests  Delaunay(vertices +/- orientation_vector).find_simplex(X) >= 0  for the point X
@@ -110,8 +130,15 @@ typedef struct ComSceneDesc {
   double voxel_corners[8][3];    /* filter accepts both nappes of the detector cone, as the reference's
                                     infinite-line intersection does (simulation.py:143-173).
                                     filter_flags: COM_FILTER_NO_RUN_CULL (1) makes the lattice kernel evaluate the
-                                    detector test of every ray individually instead of skipping whole z-runs that
-                                    the linearity of the forms proves to miss (a measurement aid: same results).   */
+                                    detector test of every ray individually instead of skipping whole boxes, columns
+                                    and z-runs that the linearity of the forms proves to miss (a measurement aid: same
+                                    results).   */
+  double near_band_mm;           /* second, wider near-edge counter (ComStats.near_band_rays): the width that bounds the
+                                    residual disagreement between the polygon test and scipy's find_simplex on edges
+                                    the calibration cannot move exactly; <= 0 selects 1e-4 mm                     */
+  int32_t physics_flags;         /* COM_PHYS_* bits; 0 = what the reference computes                            */
+  int32_t n_shields;             /* 0..COM_MAX_SHIELDS circular stops every ray must also pass (extension)      */
+  const ComShield* shields;      /* (n_shields) HOST                                                            */
 } ComSceneDesc;
 
 typedef struct ComScene ComScene; /* opaque: device-resident tables of one channel */
@@ -188,8 +215,12 @@ typedef struct ComStats {
   uint64_t visible_voxels;  /* voxels with >= 1 passing ray                                          */
   uint64_t candidate_capacity; /* capacity the launch ran with                                       */
   uint64_t overflow;        /* != 0: candidates > capacity, results incomplete (COM_E_OVERFLOW)      */
-  uint64_t certain_candidates; /* candidates the filter found >= 2e-2 mm inside one slit on both sides: the exact
-                                  kernel skips the slit tests for them (lattice kernel only)               */
+  uint64_t certain_candidates; /* candidates the FP32 filter vouched for (well inside every aperture it tested):
+                                  the fp64 stage skips those tests for them (lattice kernel only)            */
+  uint64_t near_band_rays;  /* like near_edge_rays at the wider near_band_mm (default 1e-4 mm)                */
+  uint64_t shield_blocked_rays;   /* rays through every reference aperture but stopped by an ECRH shield (extension) */
+  uint64_t segment_rejected_rays; /* rays the infinite-line test accepts but COM_PHYS_SEGMENT_CHECK rejects (extension) */
+  uint64_t reserved;
 } ComStats;
 
 /* One passing ray (optional output): what the reference keeps per selected ray

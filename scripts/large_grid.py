@@ -35,7 +35,15 @@ def main():
     ap.add_argument("--slits", type=int, default=10)
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--image", action="store_true", help="also accumulate the 0.1 mm detector image (config 3 extension)")
+    ap.add_argument("--kernel-times", action="store_true", help="per-chunk times of the FP32 filter kernel and of the fp64 kernels")
+    ap.add_argument("--only-chunks", default="", help="comma-separated chunk indices to run (default: all)")
     a = ap.parse_args()
+    import ctypes as C
+
+    from co_monitor_b200 import _lib
+
+    lib = _lib.load()
+    only = {int(x) for x in a.only_chunks.split(",") if x}
     with contextlib.redirect_stdout(io.StringIO()):
         lat = CuboidMesh(a.spacing).lattice
     P = lat.n_points
@@ -47,9 +55,13 @@ def main():
         for _ in range(a.repeat):
             if img is not None:
                 img.zero_()
-            sum_w, vis, rays, cand, near, ms_total, chunks = 0.0, 0, 0, 0, 0, 0.0, []
-            for lo in range(0, P, a.chunk):
+            sum_w, vis, rays, cand, near, ms_total, chunks, ktimes = 0.0, 0, 0, 0, 0, 0.0, [], []
+            for j, lo in enumerate(range(0, P, a.chunk)):
+                if only and j not in only:
+                    continue
                 hi = min(P, lo + a.chunk)
+                if a.kernel_times:
+                    lib.com_kernel_timing_enable(1)
                 plan = scene.plan(lat, lo, hi)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -60,6 +72,11 @@ def main():
                 if st["overflow"]:
                     raise SystemExit(f"candidate overflow in chunk [{lo},{hi}): {st}")
                 ms = e0.elapsed_time(e1)
+                if a.kernel_times:
+                    f_ms, x_ms, n_l = C.c_double(), C.c_double(), C.c_int64()
+                    lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_l))
+                    lib.com_kernel_timing_enable(0)
+                    ktimes.append([round(f_ms.value, 3), round(x_ms.value, 3), st["candidates"], st["passing_rays"]])
                 ms_total += ms
                 chunks.append(round(ms, 3))
                 sum_w += float(plan.weight.sum().item())
@@ -73,6 +90,8 @@ def main():
                    "ms": ms_total, "tests_per_s": tests / (ms_total * 1e-3), "visible_voxels": vis, "passing_rays": rays,
                    "fp64_candidates": cand, "near_edge_rays": near, "sum_w": sum_w,
                    "sum_w_times_voxel_volume_mm3": sum_w * a.spacing**3, "chunk_ms": chunks}
+            if a.kernel_times:
+                rec["chunk_filter_ms_exact_ms_candidates_passing"] = ktimes
             if img is not None:
                 rec["detector_image"] = {"shape": list(img.shape), "pixel_mm": 0.1, "sum": float(img.sum().item()),
                                          "max_pixel": float(img.max().item()),

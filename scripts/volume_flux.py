@@ -102,10 +102,10 @@ def main():
     prof_sorted = int(np.all(np.diff(profile[:, 0]) >= 0))
     prof_max = float(profile[:, 0].max())
     chunks = [(lo, min(n, lo + a.chunk)) for lo in range(0, n, a.chunk)]
-    packed = torch.zeros(n_ch * _lib.COM_MM_BINS + n_ch * 8, dtype=torch.float64, device=dev)  # histograms | counters
+    packed = torch.zeros(n_ch * _lib.COM_MM_BINS + n_ch * _lib.N_STATS, dtype=torch.float64, device=dev)  # histograms | counters
     hist = packed[: n_ch * _lib.COM_MM_BINS].view(n_ch, _lib.COM_MM_BINS)
-    counters = packed[n_ch * _lib.COM_MM_BINS:].view(n_ch, 8)
-    stats = torch.zeros((n_ch, len(chunks), 8), dtype=torch.int64, device=dev)
+    counters = packed[n_ch * _lib.COM_MM_BINS:].view(n_ch, _lib.N_STATS)
+    stats = torch.zeros((n_ch, len(chunks), _lib.N_STATS), dtype=torch.int64, device=dev)
     rows = torch.zeros((n_ch, K), dtype=torch.float64, device=dev)
     boundary = torch.zeros(n_ch, dtype=torch.float64, device=dev)
     flux = torch.zeros((n_ch, 3), dtype=torch.float64, device=dev)

@@ -34,7 +34,8 @@ def test_every_declared_symbol_is_exported(lib):
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "binding list and header disagree"
-    assert lib.com_abi_version() == 2
+    declared = int(re.search(r"#define COM_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "comonitor_sm100.h")).read()).group(1))
+    assert lib.com_abi_version() == declared == 3
 
 
 def test_struct_layouts_match_the_header(lib):
@@ -44,9 +45,9 @@ def test_struct_layouts_match_the_header(lib):
 
     from co_monitor_b200 import _lib
 
-    src = '#include <stdio.h>\n#include "comonitor_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "comonitor_sm100.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           "sizeof(ComAperture),sizeof(ComSceneDesc),sizeof(ComLattice),sizeof(ComStats),sizeof(ComRayRecord)," \
-          "sizeof(ComPecDesc),sizeof(ComTablesDesc));return 0;}\n"
+          "sizeof(ComPecDesc),sizeof(ComTablesDesc),sizeof(ComShield));return 0;}\n"
     with tempfile.TemporaryDirectory() as tmp:
         c = os.path.join(tmp, "probe.c")
         open(c, "w").write(src)
@@ -54,7 +55,7 @@ def test_struct_layouts_match_the_header(lib):
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     mine = [C.sizeof(_lib.ComAperture), C.sizeof(_lib.ComSceneDesc), C.sizeof(_lib.ComLattice), C.sizeof(_lib.ComStats),
-            _lib.RAY_RECORD_DTYPE.itemsize, C.sizeof(_lib.ComPecDesc), C.sizeof(_lib.ComTablesDesc)]
+            _lib.RAY_RECORD_DTYPE.itemsize, C.sizeof(_lib.ComPecDesc), C.sizeof(_lib.ComTablesDesc), C.sizeof(_lib.ComShield)]
     assert mine == sizes
 
 

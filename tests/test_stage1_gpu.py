@@ -356,7 +356,7 @@ def test_edge_cases_empty_range_overflow_and_bad_arguments(sims):
     n = hi - lo
     w = torch.empty(n, dtype=torch.float64, device="cuda")
     nr = torch.empty(n, dtype=torch.int32, device="cuda")
-    st = torch.zeros(8, dtype=torch.int64, device="cuda")
+    st = torch.zeros(_lib.N_STATS, dtype=torch.int64, device="cuda")
     ws = torch.empty(256 + 8 * 100, dtype=torch.uint8, device="cuda")  # room for 100 candidates only
     ls = lattice_struct(lat)
     rc = lib.com_visibility_weights(sim.scene.handle, C.byref(ls), None, lo, hi, C.c_void_p(w.data_ptr()),
