@@ -3,20 +3,34 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A *step* = Stage 1 (visibility + geometric weight) for all four channels B/C/N/O on the default
-10 mm voxel grid with 30 x 20 crystal points and 10 slits (BASELINE.json configs[1]:
-4 x 270 000 x 600 = 6.48e8 voxel-detector visibility tests), followed by Stage 2 when built.
-At N > 1 the grid is refined N-fold along z and its flat index range is sharded evenly over the ranks
-(weak scaling: 6.48e8 tests per GPU), with one NCCL all-reduce of the per-channel weight sums.
+Headline workload = BASELINE.json configs[4]: the dense 0.65 mm observation volume (2076 x 1230 x 384 = 9.8e8 voxels)
+x 600 crystal points x 10 slits for all four channels B/C/N/O = 2.35e12 voxel-detector visibility tests per step,
+STRONG scaling: the z-columns of the lattice are dealt block-cyclically over the N ranks.  A step is the whole path:
 
-Prints ONE JSON line (rank 0).  `value` = whole-job tests/s from CUDA-event times (inputs resident in HBM),
-`e2e` = the same metric through the host-buffer C-ABI call, `roofline` = the FP32 filter kernel against the
-FP32 issue peak, `cpu_baseline` = the NumPy/Qhull oracle on a bounded sample on this box's host cores.
+    Stage 1 (visibility + weight) of the rank's shard, launch by launch, each launch folded into the channel's
+    Reff-millimetre histogram  ->  ONE all-reduce(SUM) of the packed [4 x 4096 bins | counters] buffer (NCCL)
+    ->  Stage 2 (EXCIT + RECOM emissivity -> flux) from the global histograms, one launch
+
+One JSON line (rank 0):
+  value            tests/s with every ray's detector test evaluated individually (COM_FILTER_NO_RUN_CULL; SURVEY.md 8(d)
+                   wants the rate without culling as the headline), CUDA events, max over ranks, inputs resident in HBM
+  production       the same step as shipped (runs of voxels proven dark by the linearity of the test are skipped):
+                   rate, ms per step and `flux_time_s` = seconds from nothing to the four channels' flux
+  e2e              the same two through the host-buffer C-ABI calls (com_volume_histograms_host: Reff source grid up,
+                   histograms + counters down; exchange; com_histograms_flux_host: profile + histograms up, flux down)
+  small_grid       configs[1] (10 mm lattice, the golden-parity workload), device step and host-buffer calls
+  grid_1mm         configs[2] lattice (1 mm) rate;  sweep_1000  configs[3]: 1000 profile slices from cached weights
+  roofline         dominant kernel (K1a FP32 filter) against the issue peak, instruction counts and DRAM bytes MEASURED in
+                   this run by an `ncu --metrics` pass over one channel (counters only - never times)
+  roofline_stage2  the Stage-2 voxel pass (10 B/voxel) on this run's real weights against the measured HBM peak
+  cpu_baseline     the NumPy/Qhull oracle on a bounded sample of the same lattice on this box's host cores
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes as C
+import io
 import json
 import os
 import subprocess
@@ -30,19 +44,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ELEMENTS = "BCNO"
-SPACING, H, L, SLITS = 10, 30, 20, 10
-FLOP_PER_TEST = 247  # canonical no-early-out count, FMA = 2
+H, L, SLITS = 30, 20, 10
 METRIC = "voxel-detector visibility tests/s"
 NE_MAIN = [7e13, 0, 0.37, 9.8e12, 0.5, 0.11]  # reference __main__.py:35-36
 TE_MAIN = [1870, 0, 0.155, 210, 0.38, 0.07]
+NE_SWEEP = [4e13, 0, 0.937, 1.8e12, 0.5, 0.11]  # emissivity/main.py:39-45
+TE_SWEEP_LO = np.array([500, 0, 0.175, 30, 0.38, 0.07])
+TE_SWEEP_HI = np.array([10000, 0, 0.175, 1500, 0.38, 0.07])
+#: (ix, iy) of each channel's brightest voxel on the 10 mm lattice: where the CPU sample of a fine lattice is taken
+BRIGHT_10MM = {"B": (10, 25), "C": (3, 26), "N": (9, 32), "O": (8, 25)}
 
 
-def nominal_fp32_tflops(sm_mhz: float, sms: int = 148) -> float:
-    return sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def workload_name(spacing: float) -> str:
+    tag = {0.65: "configs[4]", 1.0: "configs[2]", 10.0: "configs[1]"}.get(float(spacing), "custom")
+    return (f"{tag}: dense {spacing} mm observation volume, channels B/C/N/O, Stage 1 (visibility + weight) -> Reff-mm "
+            f"histograms -> one reduce -> Stage 2 (EXCIT + RECOM flux); {H}x{L} crystal points, {SLITS} slits")
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -71,138 +96,196 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 9]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
+        loaded = [s for s, p in zip(sm, pw) if p > 300.0]  # samples while the GPU was drawing power
+        busy = loaded or sm
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded),
+                "power_w_max": max(pw) if pw else None}
 
 
-def refined_lattice(n_ranks: int):
-    """Default CuboidMesh lattice, z-sampling refined n_ranks-fold (same cuboid, same rotation)."""
-    import contextlib
-    import io
-    from dataclasses import replace
-
-    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
-
-    with contextlib.redirect_stdout(io.StringIO()):
-        lat = CuboidMesh(SPACING).lattice
-    if n_ranks > 1:
-        nz = lat.nz * n_ranks
-        step = lat.step.copy()
-        step[2] = (lat.stop[2] - lat.start[2]) / (nz - 1)
-        lat = replace(lat, nz=nz, step=step)
-    return lat
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def cpu_baseline(sample_voxels_per_core: int = 1500):
-    """Oracle (NumPy + Qhull restatement of the reference) on a bounded C-channel sample, all host cores, Stage 1 + 2."""
-    import contextlib
-    import io
-
-    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
-    from co_monitor_b200.geometry.reff import interpolate_reff
-
-    with contextlib.redirect_stdout(io.StringIO()):
-        reff_all = interpolate_reff(CuboidMesh(SPACING).lattice, 15)
-    value, d = reference_step("C", sample_voxels_per_core, reff_all)
-    return {"value": value, "unit": "tests/s", "cores": d["processes"], "kind": "port",
-            "sample": f"C channel, voxels {d['voxels']} of the 10 mm grid x {H*L} crystal points x 22 apertures (Stage 1 oracle, "
-                      f"{d['stage1_s']:.1f} s on {d['processes']} processes of {d['cores_visible']} cores) + Stage-2 oracle on the "
-                      f"visible voxels of that range ({d['stage2_s']:.2f} s + {d['tables_s_prorated']:.2f} s of table building pro rata)"}
-
-
-def reference_step(element, sample_voxels_per_core, reff_all):
-    """One bounded sample of the workload on the CPU path: Stage 1 (oracle, all host cores) on a voxel range of one
-    channel, then Stage 2 (oracle) on the visible voxels of that range.  The reference rebuilds its PEC / FA tables in
-    every Emissivity call (reader.py:83-97, 245-261); that fixed cost is counted pro rata (range / whole grid)."""
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on a bounded sample of the same lattice
+def reference_step(element, spacing, voxels_per_core, reff_vol):
+    """One bounded sample on the CPU path: Stage 1 (oracle, all host cores) on a range of consecutive voxels through the
+    channel's bright region, then Stage 2 (oracle) on the visible voxels of that range.  The reference rebuilds its PEC /
+    FA tables in every Emissivity call (reader.py:83-97, 245-261): that fixed cost is counted pro rata (range / lattice)."""
+    from co_monitor_b200.pipeline import LYMAN_ALPHA
+    from oracle import geometry_setup as gs
+    from oracle import reff as oreff
     from oracle import stage1 as o1
     from oracle import stage2 as o2
-    from co_monitor_b200.pipeline import LYMAN_ALPHA
 
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
-    lo = 120000
-    hi = min(270000, lo + sample_voxels_per_core * procs)
+    nx, ny, nz = gs.mesh_shape(gs.load_db(), spacing)
+    ix10, iy10 = BRIGHT_10MM[element]
+    col = int(round(iy10 * (ny - 1) / 79)) * nx + int(round(ix10 * (nx - 1) / 134))
+    n = voxels_per_core * procs
+    lo = max(0, min(col * nz - n // 2, nx * ny * nz - n))
+    hi = lo + n
     t0 = time.perf_counter()
-    w, nr, used = o1.run_range(element, lo, hi, S=SLITS, spacing=SPACING, h=H, l=L, processes=procs, chunk=500)
+    w, nr, used = o1.run_range(element, lo, hi, S=SLITS, spacing=spacing, h=H, l=L, processes=procs, chunk=200)
     t1 = time.perf_counter() - t0
     ion, wl = LYMAN_ALPHA[element]
     t0 = time.perf_counter()
     tables = o2.load_tables(element, ion, wl, ["EXCIT", "RECOM"])
     t_tables = time.perf_counter() - t0
     vis = np.flatnonzero(nr > 0)
-    obs = np.column_stack((vis + lo, np.zeros((len(vis), 3)), w[vis]))
     t0 = time.perf_counter()
     flux = None
     if len(vis):
-        res = o2.emissivity(element, ion, wl, 2, ["EXCIT", "RECOM"], o2.two_gauss_profile(NE_MAIN, TE_MAIN), obs, reff_all,
-                            tables=tables)
-        flux = res.flux["TOTAL"]
+        reff = oreff.on_lattice((nx, ny, nz), vis + lo, vol=reff_vol)
+        if np.isfinite(reff).any():
+            obs = np.column_stack((np.arange(len(vis)), np.zeros((len(vis), 3)), w[vis]))
+            flux = o2.emissivity(element, ion, wl, 2, ["EXCIT", "RECOM"], o2.two_gauss_profile(NE_MAIN, TE_MAIN), obs, reff,
+                                 tables=tables).flux["TOTAL"]
     t2 = time.perf_counter() - t0
-    frac = (hi - lo) / 270000.0
+    frac = n / float(nx * ny * nz)
     seconds = t1 + t2 + t_tables * frac
-    tests = (hi - lo) * H * L
-    return tests / seconds, {"element": element, "voxels": [lo, hi], "tests": tests, "stage1_s": t1, "stage2_s": t2,
-                              "tables_s_prorated": t_tables * frac, "processes": used, "cores_visible": cores, "flux": flux}
+    tests = n * H * L
+    return tests / seconds, {"element": element, "voxels": [lo, hi], "tests": tests, "seconds": seconds, "stage1_s": t1,
+                              "stage2_s": t2, "tables_s_prorated": t_tables * frac, "processes": used,
+                              "cores_visible": cores, "passing_rays": int(nr.sum()), "flux_total": flux}
+
+
+def cpu_baseline(spacing):
+    from oracle import reff as oreff
+
+    value, d = reference_step("C", spacing, 800, oreff.shipped_volume(15))
+    return {"value": value, "unit": "tests/s", "cores": d["processes"], "kind": "port",
+            "sample": f"C channel, voxels {d['voxels']} of the {spacing} mm lattice x {H * L} crystal points x 22 apertures "
+                      f"through the NumPy/Qhull oracle ({d['stage1_s']:.1f} s on {d['processes']} processes of "
+                      f"{d['cores_visible']} cores, {d['passing_rays']} passing rays) + Stage-2 oracle on the visible voxels "
+                      f"of that range ({d['stage2_s']:.2f} s + {d['tables_s_prorated']:.3f} s of table building pro rata)"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on all host cores.  The reference itself needs
     dask / opt_einsum / pyvista (absent, no network), so this is the oracle port of it - the NumPy + Qhull restatement
     that reproduces the reference's shipped outputs exactly.  Each step is a bounded sample of the workload (one channel
-    per step, B/C/N/O in turn)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    per step, B/C/N/O in turn, a range of consecutive voxels of the same lattice)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import contextlib
-    import io
+    from oracle import reff as oreff
 
-    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
-    from co_monitor_b200.geometry.reff import interpolate_reff
-
-    with contextlib.redirect_stdout(io.StringIO()):
-        reff_all = interpolate_reff(CuboidMesh(SPACING).lattice, 15)
-    per_core = 400 if args.steps + args.warmup > 6 else 1000
+    vol = oreff.shipped_volume(15)
+    per_core = 400 if args.steps + args.warmup > 6 else 800
     vals, details = [], []
     for i in range(args.warmup + args.steps):
-        v, d = reference_step(ELEMENTS[i % len(ELEMENTS)], per_core, reff_all)
+        v, d = reference_step(ELEMENTS[i % len(ELEMENTS)], args.spacing, per_core, vol)
         if i >= args.warmup:
             vals.append(v)
             details.append(d)
-    value = float(np.mean(vals))
-    full_step_tests = 270000 * H * L * len(ELEMENTS)  # what one step of the accelerated arm processes at N = 1
-    base = {"value": value, "unit": "tests/s", "cores": details[-1]["processes"], "kind": "port",
-            "sample": f"per step: one channel (B/C/N/O in turn), voxels {details[-1]['voxels']} of the 10 mm grid x {H*L} crystal "
-                      f"points x 22 apertures through the NumPy/Qhull oracle on {details[-1]['processes']} processes, then the "
-                      f"Stage-2 oracle on the visible voxels of that range; last step: {details[-1]}"}
+    tests = float(np.mean([d["tests"] for d in details]))
+    seconds = float(np.mean([d["seconds"] for d in details]))
+    value = tests / seconds
+    sample = (f"per step: one channel (B/C/N/O in turn), {details[-1]['voxels'][1] - details[-1]['voxels'][0]} consecutive "
+              f"voxels of the {args.spacing} mm lattice through the channel's bright region x {H * L} crystal points x 22 "
+              f"apertures through the NumPy/Qhull oracle on {details[-1]['processes']} processes, then the Stage-2 oracle "
+              f"on the visible voxels of that range; last step: {details[-1]}")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * full_step_tests / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: B/C/N/O, Stage 1 + Stage 2 on the default 10 mm grid (270 000 voxels x 600 crystal "
-                               "points x 10 slits); each step is a bounded sample (one channel, a voxel range)",
-                   "tests_per_step": full_step_tests,
-                   "ms_per_step_is": "the time one full step (6.48e8 tests) would take at the sampled rate; the sampled "
-                                     "steps themselves take a few seconds each"},
-        "cpu_baseline": base,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.spacing), "tests_per_step": tests,
+                   "sample": "each step is a bounded sample of the workload (the oracle's cost per test does not depend on "
+                             "the data: every ray goes through all 22 apertures); ms_per_step is the measured time of a "
+                             "sampled step, value = its tests / its seconds"},
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": details[-1]["processes"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out))
 
 
-def run_ours(args):
-    import contextlib
-    import io
+# ---------------------------------------------------------------------------------------------------------
+def ncu_counters(spacing, element="C", timeout_s=240):
+    """Instruction counts and DRAM bytes of one channel's whole-volume Stage 1 + histogram pass, measured now by an
+    `ncu --metrics` pass over `bench.py --probe` in a subprocess (hardware counters only; no time from it is used)."""
+    import shutil
 
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"unavailable": "ncu not found"}
+    metrics = "smsp__thread_inst_executed.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum"
+    cmd = [ncu, "--csv", "--metrics", metrics, "--clock-control", "none", "-k",
+           "regex:filter_kernel|exact_kernel|weight_histogram_mm", sys.executable, os.path.abspath(__file__),
+           "--probe", element, "--spacing", str(spacing)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except (subprocess.TimeoutExpired, OSError) as exc:
+        return {"unavailable": f"ncu pass failed: {type(exc).__name__}"}
+    import csv
+
+    rows = [r for r in csv.reader(proc.stdout.splitlines()) if len(r) > 10]
+    if not rows or "Kernel Name" not in rows[0]:
+        return {"unavailable": "no ncu output (profiling may be closed on this box)", "rc": proc.returncode,
+                "tail": (proc.stdout + proc.stderr)[-300:]}
+    hdr = rows[0]
+    ik, im, iv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    agg = {}
+    for r in rows[1:]:
+        name = r[ik].split("(")[0].replace("com::", "")
+        try:
+            val = float(r[iv].replace(",", ""))
+        except ValueError:
+            continue
+        d = agg.setdefault(name, {"launches": 0})
+        d[r[im]] = d.get(r[im], 0.0) + val
+        if r[im] == "smsp__inst_executed.sum":
+            d["launches"] += 1
+    probe = None
+    for line in proc.stdout.splitlines():
+        if line.startswith("{\"probe\""):
+            probe = json.loads(line)
+    return {"kernels": agg, "probe": probe, "command": " ".join(cmd[:10]) + " python bench.py --probe " + element}
+
+
+def run_probe(args):
+    """One channel's whole-volume Stage 1 + histogram pass, once (the workload the ncu counter pass profiles)."""
+    import torch
+
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.geometry.reff import source_volume
+    from co_monitor_b200.pipeline import LYMAN_ALPHA
+    from co_monitor_b200.volume import ObservationVolume
+
+    el = args.probe
+    lat = quiet(CuboidMesh, args.spacing).lattice
+    scene = quiet(make_channel, el, SLITS, H, L, lattice=lat)
+    cached_line_tables(el, *LYMAN_ALPHA[el], ("EXCIT", "RECOM"), None)
+    vol = ObservationVolume(lat, args.chunk)
+    vol.set_reff_resampled(source_volume(15))
+    hist, stats = vol.histograms([scene])
+    torch.cuda.synchronize()
+    print(json.dumps({"probe": el, "voxels": lat.n_points, "tests": lat.n_points * H * L, "launches": vol.n_launches,
+                      "passing_rays": int(stats[0, 2].item())}))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
     import torch
     import torch.distributed as dist
 
@@ -210,8 +293,10 @@ def run_ours(args):
     from co_monitor_b200.emissivity.engine import LineTables
     from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
     from co_monitor_b200.geometry.engine import lattice_struct, make_channel
-    from co_monitor_b200.geometry.reff import interpolate_reff
-    from co_monitor_b200.pipeline import LYMAN_ALPHA, ChannelPipeline
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.geometry.reff import source_volume
+    from co_monitor_b200.pipeline import LYMAN_ALPHA
+    from co_monitor_b200.volume import VolumePipeline, flux_from_histograms_host
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,263 +308,127 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
+    warmup = max(args.warmup, 3)
+    steps = args.steps
 
-    full_lattice = refined_lattice(world)
-    P = full_lattice.n_points
-    # block-cyclic shard of the z-columns: the visible voxels are spatially clustered, contiguous ranges would not balance
-    cols_per_block = int(os.environ.get("COM_BENCH_COLS_PER_BLOCK", "8"))
-    lattice = full_lattice.shard(world, rank, cols_per_block=cols_per_block)
-    lo, hi = 0, lattice.n_points
-    # Reff of every lattice voxel: the shipped 15 mm VMEC grid resampled onto the lattice (no VMEC service here),
-    # re-ordered to this shard's local voxel order
-    reff_all = interpolate_reff(full_lattice, 15)
-    reff_table = torch.from_numpy(reff_all[lattice.local_to_global(np.arange(lattice.n_points))]).to(device)
-    profile = TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy()
-    scenes, pipes = {}, {}
-    with contextlib.redirect_stdout(io.StringIO()):
-        for el in ELEMENTS:
-            scenes[el] = make_channel(el, SLITS, H, L, lattice=lattice)
-            ion, wl = LYMAN_ALPHA[el]
-            tables = LineTables(el, ion, wl, ["EXCIT", "RECOM"])
-            pipes[el] = ChannelPipeline(scenes[el], tables, lattice, reff_table, lo, hi, 2.0, device=device)
-            pipes[el].set_profile(profile)
-    tests_per_step_rank = (hi - lo) * H * L * len(ELEMENTS)
-    flux = torch.zeros((len(ELEMENTS), 3), dtype=torch.float64, device=device)
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- the workload ----
+    full = quiet(CuboidMesh, args.spacing).lattice
+    lat = full.shard(world, rank, cols_per_block=args.cols_per_block)
+    n_ch = len(ELEMENTS)
+    tests_per_step = full.n_points_global * H * L * n_ch
+    profile = np.ascontiguousarray(TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy())
+    scenes = [quiet(make_channel, el, SLITS, H, L, lattice=full) for el in ELEMENTS]
+    scenes_nc = [quiet(make_channel, el, SLITS, H, L, lattice=full, run_cull=False) for el in ELEMENTS]
+    tables = [quiet(LineTables, el, *LYMAN_ALPHA[el], ["EXCIT", "RECOM"]) for el in ELEMENTS]
+    src = source_volume(15)  # the shipped 15 mm VMEC grid (host), resampled onto the lattice on the device
+    pipe = VolumePipeline(lat, scenes, tables, profile, 2.0, chunk=args.chunk, device=device)
+    pipe.volume.set_reff_resampled(src)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
-    main_stream = torch.cuda.current_stream(device)
-    streams = {el: torch.cuda.Stream(device=device) for el in ELEMENTS}
-    fork_ev = torch.cuda.Event()
-    join_ev = {el: torch.cuda.Event() for el in ELEMENTS}
+    def timed(run, n_warm, n_steps):
+        """n_warm untimed + n_steps timed steps: barrier + sync on both sides, one CUDA-event interval per step, L2
+        flushed (untimed) between steps; returns the max over ranks of the summed intervals in ms."""
+        for _ in range(n_warm):
+            flush.fill_(1)
+            run()
+        barrier()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            flush.fill_(i & 0xFF)
+            e0[i].record()
+            run()
+            e1[i].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(e0, e1))), wall
 
-    def step_sequential():
-        """One stream, channel after channel (used for the per-kernel timing pass)."""
-        for el in ELEMENTS:
-            pipes[el].launch_geometry()
-            if world > 1:
-                dist.all_reduce(pipes[el].hist_mm)
-        for i, el in enumerate(ELEMENTS):
-            pipes[el].launch_emissivity()
-            flux[i].copy_(pipes[el].flux)
+    def check_overflow(what):
+        bad = [ELEMENTS[i] for i, st in enumerate(pipe.global_stats()) if st["overflow"]]
+        if bad:
+            raise SystemExit(f"bench.py: candidate-list overflow in channel(s) {bad} during {what}; raise --candidate-fraction")
 
-    def step():
-        """Stage 1 + Stage 2 for the four channels, each channel on its own stream (they are independent).  Stage 2
-        works from the millimetre-bin weight histogram of the rank's voxels; at N > 1 the per-rank histograms
-        (4096 fp64 bins, 32 kB) are summed with one NCCL all-reduce per channel on the channel's stream, after which
-        every rank holds the whole-grid flux - the single exchange of the path."""
-        cur = torch.cuda.current_stream(device)
-        fork_ev.record(cur)
-        for i, el in launch_order:
-            with torch.cuda.stream(streams[el]):
-                streams[el].wait_event(fork_ev)
-                pipes[el].launch_geometry()
-                if world > 1:
-                    dist.all_reduce(pipes[el].hist_mm)
-                pipes[el].launch_emissivity()
-                flux[i].copy_(pipes[el].flux)
-                join_ev[el].record(streams[el])
-        for el in ELEMENTS:
-            cur.wait_event(join_ev[el])
-
-    # channels are enqueued heaviest first (by fp64 candidates, known after the first warm-up step): the filter
-    # kernels fill the GPU one after the other, so the channel enqueued last leaves its exact kernel and Stage 2
-    # exposed at the end of the step - that should be the cheapest one
-    launch_order = list(enumerate(ELEMENTS))
-    for w in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        step()
-        if w == 0:
-            torch.cuda.synchronize()
-            cand = {el: pipes[el].plan.stats()["candidates"] for el in ELEMENTS}
-            launch_order = sorted(enumerate(ELEMENTS), key=lambda ie: -cand[ie[1]])
-    torch.cuda.synchronize()
-    stats = {el: pipes[el].plan.stats() for el in ELEMENTS}
-
-    # one CUDA graph of the whole step (every launch of the path is stream-ordered, nothing syncs with the host)
-    graph = None
-    if not args.no_graph and (world == 1 or not args.no_graph_multi_gpu):
-        try:
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(device=device)
-            side.wait_stream(main_stream)
-            with torch.cuda.stream(side):
-                step()
-            main_stream.wait_stream(side)
-            torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
-                step()
-            for _ in range(3):
-                graph.replay()
-            torch.cuda.synchronize()
-        except Exception as exc:  # e.g. an NCCL build that cannot be captured: launch kernel by kernel instead
-            if rank == 0:
-                print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); running without", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
-    if world > 1:  # all ranks must take the same path
-        flag = torch.tensor([1 if graph is not None else 0], device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            graph = None
-    run_step = graph.replay if graph is not None else step
-
-    # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps (untimed) ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        starts[i].record()
-        run_step()
-        ends[i].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_tests = tests_per_step_rank * world * args.steps
-    value = total_tests / (ms_max * 1e-3)
-    flux_h = flux.cpu().numpy()
 
-    # per-kernel timing pass: same step, one stream, no graph, events around K1a / K1b inside the library
+    # ---- headline: every ray's detector test evaluated individually ----
+    pipe.scenes = scenes_nc
+    ms_nc, wall_nc = timed(pipe.step, warmup, steps)
+    check_overflow("the headline steps")
+    flux_nc = pipe.flux.cpu().numpy()[:, 0]
+    # ---- the step as shipped ----
+    pipe.scenes = scenes
+    ms_prod, wall_prod = timed(pipe.step, warmup, steps)
+    check_overflow("the production steps")
+    flux_prod = pipe.flux.cpu().numpy()[:, 0]
+    stats = pipe.global_stats()
+    boundary = pipe.boundary.cpu().numpy()
+
+    # ---- per-kernel times of the production step (events inside the library, rank 0's shard) ----
     lib.com_kernel_timing_enable(1)
-    seq_start, seq_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_seq = min(args.steps, 10)
-    seq_ms = 0.0
-    for i in range(n_seq):
-        flush.fill_(i & 0xFF)
-        seq_start.record()
-        step_sequential()
-        seq_end.record()
-        torch.cuda.synchronize()
-        seq_ms += seq_start.elapsed_time(seq_end)
-    f_ms, x_ms, n_launch = C.c_double(), C.c_double(), C.c_int64()
-    lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_launch))
-    lib.com_kernel_timing_enable(0)
-
-    # ---- the same step with every ray's detector test evaluated individually (SURVEY.md 8(d) asks for the rate without
-    # culling next to the headline): scenes built with COM_FILTER_NO_RUN_CULL, identical results, N = 1 only ----
-    every_ray = None
-    if world == 1 and not args.no_every_ray:
-        saved = dict(pipes)
-        with contextlib.redirect_stdout(io.StringIO()):
-            for el in ELEMENTS:
-                sc_nc = make_channel(el, SLITS, H, L, lattice=lattice, run_cull=False)
-                scenes[el + "_nc"] = sc_nc
-                pipes[el] = ChannelPipeline(sc_nc, saved[el].tables, lattice, reff_table, lo, hi, 2.0, device=device)
-                pipes[el].set_profile(profile)
-        for _ in range(3):
-            flush.fill_(1)
-            step()
-        torch.cuda.synchronize()
-        run_nc = step
-        g_nc = None
-        if graph is not None:
-            try:
-                g_nc = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_nc):
-                    step()
-                g_nc.replay()
-                torch.cuda.synchronize()
-                run_nc = g_nc.replay
-            except Exception:  # pragma: no cover - measure without a graph then
-                g_nc = None
-                torch.cuda.synchronize()
-        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            e0[i].record()
-            run_nc()
-            e1[i].record()
-        torch.cuda.synchronize()
-        ms_nc = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
-        same = bool(np.allclose(flux.cpu().numpy(), flux_h, rtol=1e-12))
-        every_ray = {"value": tests_per_step_rank * args.steps / (ms_nc * 1e-3), "unit": "tests/s",
-                     "ms_per_step": ms_nc / args.steps, "flux_equal": same,
-                     "passing_rays": {el: pipes[el].plan.stats()["passing_rays"] for el in ELEMENTS}}
-        del g_nc
-        pipes.update(saved)
-
-    # ---- e2e: the reference-facing host-buffer calls, per channel: com_visibility_weights_host (scene upload,
-    # kernels, D2H of per-voxel weights + ray counts) then com_emissivity_integrate_host on the visible voxels ----
-    n = hi - lo
-    cap = n
-    idx_np = {el: np.empty(cap, dtype=np.int64) for el in ELEMENTS}
-    w_np = {el: np.empty(cap, dtype=np.float64) for el in ELEMENTS}
-    reff_np = reff_table.cpu().numpy()
-    prof_np = np.ascontiguousarray(profile)
-    lat_s = lattice_struct(lattice)
-    flux_e2e = np.zeros((len(ELEMENTS), 3))
-    bytes_io = {"h2d": 0, "d2h": 0}
-
-    def e2e_channel(i, el, count_bytes=False):
-        """The reference-facing calls of one channel, host buffers in and out (ctypes releases the GIL inside)."""
-        st, cnt = _lib.ComStats(), C.c_uint64()
-        rc = lib.com_visible_weights_host(C.byref(scenes[el].desc), C.byref(lat_s), None, lo, hi,
-                                          C.c_void_p(idx_np[el].ctypes.data), C.c_void_p(w_np[el].ctypes.data), cap,
-                                          C.byref(cnt), C.byref(st))
-        _lib.check(rc, "com_visible_weights_host")
-        m = cnt.value
-        # the join with the Reff table (reader.py:161-197) happens inside the call, on the visible voxels' indices
-        rc = lib.com_emissivity_integrate_indexed_host(
-            C.byref(pipes[el].tables.desc), _lib.as_double_ptr(prof_np), len(prof_np), 0.02, _lib.as_double_ptr(reff_np),
-            len(reff_np), C.c_void_p(idx_np[el].ctypes.data), _lib.as_double_ptr(w_np[el]), m,
-            _lib.as_double_ptr(flux_e2e[i]), None, None, None)
-        _lib.check(rc, "com_emissivity_integrate_indexed_host")
-        if count_bytes:
-            k = scenes[el]._keep
-            up = sum(k[x].nbytes for x in ("xyz", "nrm", "sc", "sp", "pv", "dv"))
-            up += C.sizeof(_lib.ComAperture) * (2 * SLITS + 2) + prof_np.nbytes + 16 * m
-            up += sum(a.nbytes for a in pipes[el].tables._keep)
-            return up, 16 * m + 512 + 24
-        return 0, 0
-
-    from concurrent.futures import ThreadPoolExecutor
-
-    pool = ThreadPoolExecutor(max_workers=len(ELEMENTS))
-
-    def e2e_step(count_bytes=False):
-        """Four channels from four host threads: each thread has its own arena and CUDA stream inside the library."""
-        futs = [pool.submit(e2e_channel, i, el, count_bytes) for i, el in enumerate(ELEMENTS)]
-        for f in futs:
-            up, down = f.result()
-            bytes_io["h2d"] += up
-            bytes_io["d2h"] += down
-
-    e2e_step(count_bytes=True)
-    for _ in range(max(args.warmup, 3) + 2):  # every pool thread grows its arena, whichever channel it gets
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    e2e_times = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        t1 = time.perf_counter()
-        e2e_step()
-        e2e_times.append(time.perf_counter() - t1)
+    t_seq0 = torch.cuda.Event(enable_timing=True)
+    t_seq1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None  # sampled across the timed steps, the kernel-timing pass and the e2e steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_tests / float(t.item())
+    t_seq0.record()
+    pipe.stage1()
+    t_seq1.record()
+    torch.cuda.synchronize()
+    f_ms, x_ms, n_l = C.c_double(), C.c_double(), C.c_int64()
+    lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_l))
+    lib.com_kernel_timing_enable(0)
+    stage1_ms = t_seq0.elapsed_time(t_seq1)
+
+    # ---- e2e: the host-buffer C-ABI calls, exchange included ----
+    packed_h = torch.empty(n_ch * (_lib.COM_MM_BINS + _lib.N_STATS), dtype=torch.float64).pin_memory()
+    packed_np = packed_h.numpy()
+    hist_np = packed_np[: n_ch * _lib.COM_MM_BINS].reshape(n_ch, _lib.COM_MM_BINS)
+    flux_e2e = np.zeros((n_ch, 3))
+    io_bytes = {"h2d": 0, "d2h": 0}
+
+    def e2e_step(sc):
+        hist, st = pipe.volume.histograms_host(sc, reff_source=src, hist_out=hist_np)
+        if world > 1:  # the path's single exchange, from and to host memory
+            raw = np.array([[s[f[0]] for f in _lib.ComStats._fields_] for s in st], dtype=np.float64)
+            packed_np[n_ch * _lib.COM_MM_BINS:] = raw.ravel()
+            dev_buf = packed_h.to(device, non_blocking=True)
+            dist.all_reduce(dev_buf)
+            packed_h.copy_(dev_buf)  # synchronous D2H into pinned memory
+        fl, _ = flux_from_histograms_host(tables, profile, hist_np, 0.02, device=device)
+        flux_e2e[:] = fl[:, 0]
+
+    def e2e_timed(sc, n_warm, n_steps):
+        for _ in range(n_warm):
+            e2e_step(sc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            e2e_step(sc)
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    e2e_nc_s = e2e_timed(scenes_nc, 1, steps)
+    flux_e2e_nc = flux_e2e.copy()
+    e2e_prod_s = e2e_timed(scenes, 1, steps)
+    flux_e2e_prod = flux_e2e.copy()
+    exch = 2 * packed_np.nbytes if world > 1 else 0
+    io_bytes["h2d"] = src[0].nbytes + profile.nbytes + hist_np.nbytes + exch // 2
+    io_bytes["d2h"] = hist_np.nbytes + n_ch * C.sizeof(_lib.ComStats) + flux_e2e.nbytes + 8 * n_ch + exch // 2
+    clocks = sampler.stop() if rank == 0 else None
 
     def teardown():
-        """Every rank leaves the same way: captured graph released first, then a barrier, then the process group."""
-        nonlocal graph, run_step
-        graph = run_step = None
         import gc
 
         gc.collect()
@@ -489,157 +438,338 @@ def run_ours(args):
             dist.destroy_process_group()
 
     if rank != 0:
+        pipe.close()
         teardown()
         return
 
-    # ---- roofline of the dominant kernel (K1a FP32 filter) ----
-    launches = max(1, n_launch.value)
-    filter_ms = f_ms.value / launches
-    exact_ms = x_ms.value / launches
-    tests_per_launch = (hi - lo) * H * L
-    achieved = FLOP_PER_TEST * tests_per_launch / (filter_ms * 1e-3) / 1e12 if filter_ms > 0 else None
-    measured_peak = lib.com_measure_fp32_tflops()
+    # =========================== rank 0 only from here: sub-records, rooflines, baselines ===========================
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
-    peak = nominal_fp32_tflops(sm_max)
-    # Hardware-side figure next to the canonical one: lane-instructions actually executed per test, taken from the
-    # committed ncu capture of this kernel on this workload (profiles/r1c_ncu_full_summary_k1.txt: warp instructions x
-    # active threads per instruction / 1.62e8 tests, mean of the four channels), against the issue peak
-    # 148 SM x 4 schedulers x 32 lanes x f_max.
-    LANE_INSTR_PER_TEST = 11.3
-    issue_peak = 148 * 4 * 32 * sm_max * 1e6
-    issue_frac = (tests_per_launch / (filter_ms * 1e-3)) * LANE_INSTR_PER_TEST / issue_peak if filter_ms > 0 else None
+    issue_peak = 148 * 4 * 32 * sm_max * 1e6  # lane-instructions per second: 148 SMs x 4 schedulers x 32 lanes x f_max
+    n_launch = max(1, n_l.value)
+
+    # ---- measured counters (ncu pass over one channel of this workload) ----
+    counters = None if args.no_ncu else ncu_counters(args.spacing, "C")
+    k1a = k1b = khist = None
+    if counters and "kernels" in counters:
+        k1a = counters["kernels"].get("filter_kernel_lattice")
+        k1b = counters["kernels"].get("exact_kernel")
+        khist = counters["kernels"].get("weight_histogram_mm_kernel")
+    # K1a time of channel C alone on this rank's shard, measured live (events around the kernels)
+    lib.com_kernel_timing_enable(1)
+    pipe.volume.histograms([scenes[1]])
+    torch.cuda.synchronize()
+    fc_ms, xc_ms, nc_l = C.c_double(), C.c_double(), C.c_int64()
+    lib.com_kernel_timing_read(C.byref(fc_ms), C.byref(xc_ms), C.byref(nc_l))
+    lib.com_kernel_timing_enable(0)
+    tests_c_rank = lat.n_points * H * L
     roofline = {
-        "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if achieved else None,
-        "traffic": 1.19e5,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/ "
-                        "(119 kB: geometry tables only; the lattice kernel reads no voxel data and writes 8 B per candidate via L2)",
-        "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure); "
-                       f"register-only FMA probe measured {measured_peak:.1f} TFLOP/s on this GPU in this run",
-        "measured_fp32_tflops": measured_peak,
-        "kernel": "com::filter_kernel_lattice (K1a)", "kernel_ms_per_launch": filter_ms, "exact_kernel_ms_per_launch": exact_ms,
-        "kernel_share_of_step": (f_ms.value + x_ms.value) / seq_ms if seq_ms > 0 else None,
-        "filter_kernel_share_of_step": f_ms.value / seq_ms if seq_ms > 0 else None,
-        "sequential_ms_per_step": seq_ms / n_seq,
-        "timing_pass": "kernel times and shares come from a separate pass of the same step on one stream without the "
-                       "CUDA graph (the headline step overlaps the four channels on four streams)",
-        "algorithmic_flop_per_test": FLOP_PER_TEST,
-        "executed_lane_instr_per_test": LANE_INSTR_PER_TEST,
-        "issue_frac": issue_frac,
-        "note": "`frac` uses the canonical 247 FLOP/test of SURVEY.md 8(d) as the contract asks; it exceeds 1 because the kernel does "
-                "not execute that arithmetic: mirroring the detector in the crystal makes the aperture coordinates linear "
-                "forms of the voxel position, advanced along z with 3 FADD per test (DESIGN.md section 4). The hardware "
-                "figure is `issue_frac`: executed lane-instructions per second over the issue peak (ncu: 70-75 % issue-slot "
-                "utilisation while the kernel runs).",
+        "bound": "issue (FP32/ALU instruction issue; not HBM, not tensor)", "kernel": "com::filter_kernel_lattice (K1a)",
+        "unit": "Tlane-inst/s", "peak": issue_peak / 1e12,
+        "peak_source": f"148 SM x 4 schedulers x 32 lanes x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no instruction-issue figure)",
+        "kernel_ms_per_launch": f_ms.value / n_launch, "exact_kernel_ms_per_launch": x_ms.value / n_launch,
+        "launches_per_step_this_rank": int(n_launch),
+        "kernel_share_of_step": (f_ms.value + x_ms.value) / stage1_ms if stage1_ms > 0 else None,
+        "filter_kernel_share_of_step": f_ms.value / stage1_ms if stage1_ms > 0 else None,
+        "timing": "CUDA events inside the library around every K1a / K1b launch of one production step of this rank",
+        "achieved": None, "frac": None, "traffic": None,
     }
+    if k1a and fc_ms.value > 0:
+        scale = tests_c_rank / counters["probe"]["tests"]  # the probe ran the unsharded lattice
+        lane = k1a["smsp__thread_inst_executed.sum"] * scale
+        roofline.update({
+            "achieved": lane / (fc_ms.value * 1e-3) / 1e12, "frac": lane / (fc_ms.value * 1e-3) / issue_peak,
+            "executed_lane_instr_per_test": k1a["smsp__thread_inst_executed.sum"] / counters["probe"]["tests"],
+            "threads_per_warp_instr": k1a["smsp__thread_inst_executed.sum"] / k1a["smsp__inst_executed.sum"],
+            "traffic": (k1a["dram__bytes_read.sum"] + k1a["dram__bytes_write.sum"]) / k1a["launches"],
+            "counters": "measured in this run: ncu --metrics pass over channel C of this workload (counters only); the time "
+                        "is this rank's live event timing of the same channel",
+            "exact_kernel": None if not k1b else {
+                "executed_lane_instr_per_candidate": k1b["smsp__thread_inst_executed.sum"] / max(1, stats[1]["candidates"]),
+                "issue_frac": k1b["smsp__thread_inst_executed.sum"] * scale / (xc_ms.value * 1e-3) / issue_peak if xc_ms.value > 0 else None,
+                "traffic": (k1b["dram__bytes_read.sum"] + k1b["dram__bytes_write.sum"]) / k1b["launches"]},
+        })
+    elif counters:
+        roofline["counters"] = counters
 
-    # ---- second roofline: the Stage-2 voxel pass (HBM bound; SURVEY.md 8(d): 10 B per voxel per channel) ----
-    # At the benchmark's 270 000 voxels per channel that pass is launch-latency bound, so it is measured here on a
-    # synthetic array of 5e8 voxels (5 GB, far beyond L2; a 0.65 mm grid has 9.8e8 per channel): uint16 Reff
-    # millimetres, fp64 weights of which ~89 % are zero like a real Stage-1 output.
+    # ---- metric 2 + Stage-2 roofline: full-channel flux from device-resident weights of this run (channel N) ----
     roofline_stage2 = None
+    flux_time = {"full_step_s": ms_prod / steps * 1e-3,
+                 "what": "production step: Stage 1 + exchange + Stage 2 of all four channels, nothing cached"}
     if not args.no_stage2_roofline:
-        n2 = 500_000_000
-        gen = torch.Generator(device=device).manual_seed(0)
-        r2 = torch.randint(0, 600, (n2,), dtype=torch.int32, device=device, generator=gen).to(torch.int16)
-        w2 = torch.rand(n2, dtype=torch.float64, device=device, generator=gen)
-        w2[torch.rand(n2, device=device, generator=gen) < 0.89] = 0.0
-        h2 = torch.zeros(_lib.COM_MM_BINS, dtype=torch.float64, device=device)
-        cur = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        times = []
-        for _ in range(7):
-            h2.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(lib.com_weight_histogram_mm(C.c_void_p(r2.data_ptr()), C.c_void_p(w2.data_ptr()), n2, None,
-                                                   C.c_void_p(h2.data_ptr()), cur), "com_weight_histogram_mm")
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        ms2 = float(np.mean(times[2:]))  # average launch duration after two warm-up launches
-        want = torch.bincount(r2.to(torch.int64), weights=w2, minlength=_lib.COM_MM_BINS)[: _lib.COM_MM_BINS]
-        err2 = float(((h2 - want).abs().max() / want.abs().max()).item())
-        del r2, w2
-        hbm_peak, src = 6650.0, "fallback of B200_PROFILING.md"
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
-                hbm_peak, src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-        except (OSError, KeyError, ValueError):
-            pass
-        gbs = 10.0 * n2 / (ms2 * 1e-3) / 1e9
-        roofline_stage2 = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                           "traffic": 5.0044e9,
-                           "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full "
-                                           "capture profiles/r1c_ncu_full_summary_hist_mm.txt (5.000 GB read = the algorithmic "
-                                           "10 B x 5e8 voxels, 4.4 MB written)",
-                           "peak_source": src, "kernel": "com::weight_histogram_mm_kernel",
-                           "kernel_ms_per_launch": ms2, "launch_ms": [round(t, 4) for t in times],
-                           "voxels_per_launch": n2, "algorithmic_bytes_per_voxel": 10,
-                           "max_rel_err_vs_bincount": err2,
-                           "note": "the Stage-2 voxel pass on a synthetic 5e8-voxel channel (inputs larger than L2); in the "
-                                   "timed step above the same kernel runs on 270 000 voxels and is latency bound"}
+        el_i = 2  # N: the channel with the most visible voxels
+        n = lat.n_points
+        w_all = torch.empty(n, dtype=torch.float64, device=device)
+        plan = scenes[el_i].plan(lat, 0, min(n, pipe.volume.chunk), device=device)
+        for lo in range(0, n, pipe.volume.chunk):
+            hi = min(n, lo + pipe.volume.chunk)
+            plan.rebind(lo, hi).launch()
+            w_all[lo:hi] = plan.weight[: hi - lo]
+        del plan
+        reff_mm = pipe.volume.reff_mm()
+        h2 = torch.zeros((1, _lib.COM_MM_BINS), dtype=torch.float64, device=device)
+        fl2 = torch.zeros((1, 1, 3), dtype=torch.float64, device=device)
+        from co_monitor_b200.volume import flux_from_histograms
 
+        cur = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        t_pass, t_all = [], []
+        for _ in range(7):
+            flush.fill_(3)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            h2.zero_()
+            e[0].record()
+            _lib.check(lib.com_weight_histogram_mm(C.c_void_p(reff_mm.data_ptr()), C.c_void_p(w_all.data_ptr()), n, None,
+                                                   C.c_void_p(h2.data_ptr()), cur), "com_weight_histogram_mm")
+            e[1].record()
+            flux_from_histograms([tables[el_i]], pipe.profiles, h2, 0.02, fl2, None, pipe.meta)
+            fl_host = fl2.cpu()
+            e[2].record()
+            torch.cuda.synchronize()
+            t_pass.append(e[0].elapsed_time(e[1]))
+            t_all.append(e[0].elapsed_time(e[2]))
+        ms2 = float(np.mean(t_pass[2:]))
+        peak, peak_src = hbm_peak()
+        gbs = 10.0 * n / (ms2 * 1e-3) / 1e9
+        rel = float(abs(fl_host[0, 0, 2].item() / flux_prod[el_i, 2] - 1)) if world == 1 else None
+        roofline_stage2 = {
+            "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+            "kernel": "com::weight_histogram_mm_kernel", "kernel_ms_per_launch": ms2, "launch_ms": [round(t, 4) for t in t_pass],
+            "voxels_per_launch": n, "algorithmic_bytes_per_voxel": 10,
+            "traffic": None if not khist else (khist["dram__bytes_read.sum"] + khist["dram__bytes_write.sum"]) / khist["launches"],
+            "traffic_note": "DRAM bytes per launch of this kernel in the ncu counter pass of this run (launches of one "
+                            f"Stage-1 chunk, {pipe.volume.chunk} voxels = {10 * pipe.volume.chunk} algorithmic bytes)",
+            "data": f"channel N of this run: real Stage-1 weights and resampled Reff bins of this rank's {n} voxels",
+            "flux_rel_diff_vs_pipeline": rel,
+        }
+        flux_time.update({"from_cached_weights_s": float(np.mean(t_all[2:])) * 1e-3,
+                          "from_cached_weights_what": f"one channel (N), {n} voxels of this rank: 10 B/voxel histogram pass + fused "
+                                                      "Stage 2 + flux to the host (metric 2 of SURVEY.md 8(d))"})
+        del w_all
+
+    sub = {}
+    if not args.no_subrecords:
+        sub = subrecords(args, lib, device, tables, profile, flush)
     base = None
     if world == 1 and not args.no_cpu_baseline:
-        base = cpu_baseline()
+        base = cpu_baseline(args.spacing)
+
+    value = tests_per_step * steps / (ms_nc * 1e-3)
+    prod_value = tests_per_step * steps / (ms_prod * 1e-3)
+
+    def rel_diff(a, b):
+        return float(np.max(np.abs(np.asarray(a) / np.asarray(b) - 1)))
 
     out = {
-        "metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 filter + f64 decision/weight/emissivity", "data": "synthetic",
+        "metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_nc / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 filter + f64 decision/weight/emissivity", "data": "synthetic",
         "config": {
-            "workload": f"configs[1]: B/C/N/O, Stage 1 (visibility + weight) then Stage 2 (EXCIT + RECOM emissivity -> flux), "
-                        f"10 mm CuboidMesh lattice {lattice.nx}x{lattice.ny}x{lattice.nz} ({P} voxels, {hi - lo} per GPU, "
-                        f"block-cyclic shards of {cols_per_block} z-columns) "
-                        f"x {H}x{L} crystal points x {SLITS} slits, Reff = shipped 15 mm VMEC grid resampled",
-            "tests_per_step": tests_per_step_rank * world,
-            "l2": "256 MB buffer written between timed steps (L2 flushed, untimed)",
-            "timing": "sum of per-step CUDA-event intervals, max over ranks",
-            "launch": ("one CUDA graph per step, four channels on four streams" if graph is not None else
-                       "four channels on four streams, no graph"),
-            "decided_how": "every (voxel, crystal point) ray is decided: by the FP32 filter (its detector test evaluated per "
-                           "ray, or for a whole run of z-consecutive voxels at once when the linearity of the test proves that "
-                           "none of them can pass) and, for the candidates, in fp64; nothing is pre-selected or skipped. "
-                           "`every_ray_evaluated` is the same step with the run-level proof switched off",
-            "every_ray_evaluated": every_ray,
-            "passing_rays": {el: stats[el]["passing_rays"] for el in ELEMENTS},
-            "fp64_candidates": {el: stats[el]["candidates"] for el in ELEMENTS},
-            "near_edge_rays": {el: stats[el]["near_edge_rays"] for el in ELEMENTS},
-            "flux_excit_recom_total": {el: [float(x) for x in flux_h[i]] for i, el in enumerate(ELEMENTS)},
-            "flux_e2e_total": {el: float(flux_e2e[i, 2]) for i, el in enumerate(ELEMENTS)},
+            "workload": workload_name(args.spacing),
+            "lattice": [full.nx, full.ny, full.nz], "voxels": full.n_points_global, "voxels_per_gpu": lat.n_points,
+            "tests_per_step": tests_per_step, "shards": f"block-cyclic, {args.cols_per_block} z-columns per block",
+            "launches_per_channel_per_gpu": pipe.volume.n_launches, "voxels_per_launch": pipe.volume.chunk,
+            "reff": "shipped 15 mm VMEC grid resampled onto the lattice on the device (2 B/voxel, resident)",
+            "l2": "256 MB buffer written between timed steps (untimed) and inputs larger than L2 (Reff bins: "
+                  f"{2 * lat.n_points / 1e6:.0f} MB per GPU)",
+            "timing": "sum of per-step CUDA-event intervals, barrier + synchronize on both sides, max over ranks",
+            "value_is": "every ray's detector test evaluated individually (COM_FILTER_NO_RUN_CULL); `production` is the "
+                        "shipped step, which skips runs of voxels the linearity of the test proves dark - every ray is decided "
+                        "either way and the results are identical (flux_rel_diff)",
+            "exchange": f"one all-reduce(SUM) of {pipe.packed.numel()} fp64 per step" if world > 1 else "none (one rank)",
+            "passing_rays": {el: stats[i]["passing_rays"] for i, el in enumerate(ELEMENTS)},
+            "visible_voxels": {el: stats[i]["visible_voxels"] for i, el in enumerate(ELEMENTS)},
+            "fp64_candidates": {el: stats[i]["candidates"] for i, el in enumerate(ELEMENTS)},
+            "near_edge_rays_1e-9mm": {el: stats[i]["near_edge_rays"] for i, el in enumerate(ELEMENTS)},
+            "near_edge_rays_1e-4mm": {el: stats[i]["near_band_rays"] for i, el in enumerate(ELEMENTS)},
+            "flux_excit_recom_total": {el: [float(x) for x in flux_prod[i]] for i, el in enumerate(ELEMENTS)},
+            "total_emissivity": {el: f"{flux_prod[i, 2]:.2e}" for i, el in enumerate(ELEMENTS)},
+            "reff_boundary_m": {el: float(boundary[i]) for i, el in enumerate(ELEMENTS)},
+            "flux_rel_diff_value_vs_production": rel_diff(flux_nc, flux_prod),
         },
-        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(bytes_io["h2d"]),
-                "d2h_bytes_per_step": int(bytes_io["d2h"]),
-                "ms_per_step": 1e3 * e2e_s / args.steps, "ms_per_step_median": 1e3 * float(np.median(e2e_times)),
-                "ms_per_step_max": 1e3 * float(np.max(e2e_times)),
-                "call": "per channel, four channels from four host threads: com_visible_weights_host (geometry up, K1a/K1b + "
-                        "compaction, visible voxels' indices and weights down) then com_emissivity_integrate_indexed_host (tables, "
-                        "profile, Reff of the visible voxels and weights up, flux down)"},
-        "gpu_launches": int(args.steps * len(ELEMENTS) * pipes[ELEMENTS[0]].kernels_per_launch),
-        "wall_s_timed_region": wall,
+        "production": {"value": prod_value, "unit": "tests/s", "ms_per_step": ms_prod / steps, "steps": steps,
+                       "flux_time_s": ms_prod / steps * 1e-3},
+        "flux_time_s": flux_time,
+        "e2e": {
+            "value": tests_per_step * steps / e2e_nc_s, "unit": "tests/s", "ms_per_step": 1e3 * e2e_nc_s / steps,
+            "h2d_bytes_per_step": int(io_bytes["h2d"]), "d2h_bytes_per_step": int(io_bytes["d2h"]),
+            "ms_per_step_over_device_ms_per_step": (1e3 * e2e_nc_s / steps) / (ms_nc / steps),
+            "production": {"value": tests_per_step * steps / e2e_prod_s, "unit": "tests/s", "ms_per_step": 1e3 * e2e_prod_s / steps,
+                           "ms_per_step_over_device_ms_per_step": (1e3 * e2e_prod_s / steps) / (ms_prod / steps)},
+            "flux_e2e_total": {el: float(flux_e2e_prod[i, 2]) for i, el in enumerate(ELEMENTS)},
+            "flux_rel_diff_vs_device": max(rel_diff(flux_e2e_prod, flux_prod), rel_diff(flux_e2e_nc, flux_prod)),
+            "timing": "wall clock around the K steps, barrier + synchronize on both sides, max over ranks",
+            "call": "per step and rank: com_volume_histograms_host (Reff source grid up and resampled, Stage 1 of the shard "
+                    "in launches + histogram passes, histograms + counters down)"
+                    + (", all-reduce of the packed host buffer through pinned memory (H2D, NCCL, D2H)" if world > 1 else "")
+                    + ", com_histograms_flux_host (profile + global histograms up, fused Stage 2, flux down); scene and table "
+                      "handles are created once (com_scene_create / com_tables_create) and reused",
+        },
+        "gpu_launches": int(steps * (n_ch * pipe.volume.n_launches * 3 + 1)),
+        "wall_s_timed_region": wall_nc,
         "clocks": clocks,
         "roofline": roofline,
         "roofline_stage2": roofline_stage2,
         "cpu_baseline": base,
+        **sub,
     }
     print(json.dumps(out), flush=True)
+    pipe.close()
     teardown()
+
+
+def subrecords(args, lib, device, tables, profile, flush):
+    """Rank-0-only legs that keep the other BASELINE configs visible in the driver's line (none uses a collective)."""
+    import torch
+
+    from co_monitor_b200 import _lib
+    from co_monitor_b200.geometry.engine import lattice_struct, make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.geometry.reff import source_volume
+    from co_monitor_b200.volume import VolumePipeline, flux_from_histograms
+
+    out = {}
+    n_ch = len(ELEMENTS)
+    src = source_volume(15)
+    n_rep = 5
+
+    def time_steps(run, n):
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(n):
+            flush.fill_(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.mean(ms))
+
+    # ---- configs[1]: the golden-parity workload (10 mm lattice, 270 000 voxels x 4 channels) ----
+    lat10 = quiet(CuboidMesh, 10).lattice
+    sc10 = [quiet(make_channel, el, SLITS, H, L, lattice=lat10) for el in ELEMENTS]
+    p10 = VolumePipeline(lat10, sc10, tables, profile, 2.0, chunk=lat10.n_points, device=device)
+    p10.volume.set_reff_resampled(src)
+    ms10 = time_steps(p10.step, 20)
+    st10 = p10.global_stats()
+    fl10 = p10.flux.cpu().numpy()[:, 0]
+    tests10 = lat10.n_points * H * L * n_ch
+    # the per-channel host-buffer calls of the drop-ins (scene / table handles kept), four channels from four threads
+    from concurrent.futures import ThreadPoolExecutor
+
+    from co_monitor_b200.geometry.reff import interpolate_reff
+
+    reff_np = interpolate_reff(lat10, 15)
+    ls = lattice_struct(lat10)
+    n10 = lat10.n_points
+    idx_np = [np.empty(n10, dtype=np.int64) for _ in ELEMENTS]
+    w_np = [np.empty(n10) for _ in ELEMENTS]
+    fl_e2e = np.zeros((n_ch, 3))
+
+    def channel_call(i):
+        st, cnt = _lib.ComStats(), C.c_uint64()
+        _lib.check(lib.com_visible_weights_host_scene(sc10[i].handle, C.byref(ls), None, 0, n10, C.c_void_p(idx_np[i].ctypes.data),
+                                                      C.c_void_p(w_np[i].ctypes.data), n10, C.byref(cnt), C.byref(st)),
+                   "com_visible_weights_host_scene")
+        m = cnt.value
+        _lib.check(lib.com_emissivity_integrate_indexed_host_tables(
+            tables[i].handle, _lib.as_double_ptr(profile), len(profile), 0.02, _lib.as_double_ptr(reff_np), len(reff_np),
+            C.c_void_p(idx_np[i].ctypes.data), _lib.as_double_ptr(w_np[i]), m, _lib.as_double_ptr(fl_e2e[i]), None, None, None),
+            "com_emissivity_integrate_indexed_host_tables")
+        return m
+
+    pool = ThreadPoolExecutor(max_workers=n_ch)
+
+    def host_step():
+        return [f.result() for f in [pool.submit(channel_call, i) for i in range(n_ch)]]
+
+    with torch.cuda.device(device):
+        for _ in range(6):
+            m10 = host_step()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            host_step()
+        e2e10 = (time.perf_counter() - t0) / 20
+    pool.shutdown()
+    out["small_grid"] = {
+        "workload": "configs[1]: 10 mm lattice (270 000 voxels) x B/C/N/O, the golden-file workload",
+        "tests_per_step": tests10, "ms_per_step": ms10, "value": tests10 / (ms10 * 1e-3), "unit": "tests/s",
+        "passing_rays": {el: st10[i]["passing_rays"] for i, el in enumerate(ELEMENTS)},
+        "visible_voxels": {el: st10[i]["visible_voxels"] for i, el in enumerate(ELEMENTS)},
+        "flux_total": {el: float(fl10[i, 2]) for i, el in enumerate(ELEMENTS)},
+        "e2e": {"value": tests10 / e2e10, "ms_per_step": 1e3 * e2e10,
+                "h2d_bytes_per_step": int(n_ch * profile.nbytes + 16 * sum(m10)), "d2h_bytes_per_step": int(16 * sum(m10) + n_ch * 600),
+                "flux_total": {el: float(fl_e2e[i, 2]) for i, el in enumerate(ELEMENTS)},
+                "call": "per channel (four host threads): com_visible_weights_host_scene (visible voxels' indices + weights "
+                        "down) then com_emissivity_integrate_indexed_host_tables (profile, Reff join, weights up; flux down)"},
+    }
+    p10.close()
+
+    # ---- configs[3]: 1000 profile time slices from the cached weights of the 10 mm grid ----
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+
+    n_slices = 1000
+    profs = np.stack([TwoGaussSumProfile(NE_SWEEP, list(TE_SWEEP_LO + (TE_SWEEP_HI - TE_SWEEP_LO) * (s / (n_slices - 1)))).profiles_df[
+        ["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy() for s in range(n_slices)])
+    p10 = VolumePipeline(lat10, sc10, tables, profs, 2.0, chunk=lat10.n_points, device=device)
+    p10.volume.set_reff_resampled(src)
+    p10.stage1()
+    ms_sw = time_steps(p10.stage2, 10)
+    fl_sw = p10.flux.cpu().numpy()
+    visible = sum(s["visible_voxels"] for s in p10.global_stats())
+    rec = {"workload": "configs[3]: 1000 T_e slices x B/C/N/O from the cached weight histograms of the 10 mm grid",
+           "sweep_1000_ms": ms_sw, "voxel_slices_per_s": visible * n_slices / (ms_sw * 1e-3), "launches": 1,
+           "flux_total_slice0": {el: float(fl_sw[i, 0, 2]) for i, el in enumerate(ELEMENTS)},
+           "flux_total_slice999": {el: float(fl_sw[i, 999, 2]) for i, el in enumerate(ELEMENTS)}}
+    gpath = os.path.join(ROOT, "tests", "golden", "stage2_reference.npz")
+    if os.path.exists(gpath):
+        gold = np.load(gpath)
+        rec["max_rel_err_vs_reference_slices_0_499_999"] = float(max(
+            np.max(np.abs(fl_sw[ELEMENTS.index(el), s] / gold[f"sweep{s}_{el}_flux"] - 1))
+            for el in "CO" for s in (0, 499, 999) if f"sweep{s}_{el}_flux" in gold))
+    out["sweep_1000"] = rec
+    p10.close()
+    for s in sc10:
+        s.close()
+
+    # ---- configs[2]: the 1 mm lattice (2.7e8 voxels), whole step on this GPU ----
+    if args.spacing != 1.0:
+        lat1 = quiet(CuboidMesh, 1).lattice
+        sc1 = [quiet(make_channel, el, SLITS, H, L, lattice=lat1) for el in ELEMENTS]
+        p1 = VolumePipeline(lat1, sc1, tables, profile, 2.0, chunk=args.chunk, device=device)
+        p1.volume.set_reff_resampled(src)
+        ms1 = time_steps(p1.step, n_rep)
+        st1 = p1.global_stats()
+        tests1 = lat1.n_points * H * L * n_ch
+        out["grid_1mm"] = {"workload": "configs[2] lattice: 1 mm (1350x800x250 = 2.7e8 voxels) x B/C/N/O, whole step on one GPU",
+                           "tests_per_step": tests1, "ms_per_step": ms1, "value": tests1 / (ms1 * 1e-3), "unit": "tests/s",
+                           "passing_rays": {el: st1[i]["passing_rays"] for i, el in enumerate(ELEMENTS)},
+                           "flux_total": {el: float(x) for el, x in zip(ELEMENTS, p1.flux.cpu().numpy()[:, 0, 2])}}
+        p1.close()
+        for s in sc1:
+            s.close()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spacing", type=float, default=0.65, help="lattice spacing in mm (0.65: configs[4], the headline)")
+    ap.add_argument("--chunk", type=int, default=1 << 26, help="voxels per Stage-1 launch")
+    ap.add_argument("--cols-per-block", type=int, default=8, help="z-columns per block of the block-cyclic shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-every-ray", action="store_true", help="skip the leg that re-times the step without run-level culling")
-    ap.add_argument("--no-stage2-roofline", action="store_true", help="skip the HBM roofline leg of the Stage-2 voxel pass")
-    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--no-graph-multi-gpu", action="store_true",
-                    help="at N > 1 do not capture the step (NCCL all-reduces included) in a CUDA graph")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu counter pass (roofline instruction counts / DRAM bytes)")
+    ap.add_argument("--no-stage2-roofline", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the small_grid / sweep_1000 / grid_1mm legs")
+    ap.add_argument("--probe", default="", help="internal: run one channel's whole-volume Stage 1 once (ncu counter pass)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.probe:
+        run_probe(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

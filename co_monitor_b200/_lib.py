@@ -141,6 +141,7 @@ N_STATS = len(ComStats._fields_)
 
 COM_MAX_TRANSITIONS = 4
 COM_MM_BINS = 4096
+COM_MAX_CHANNELS = 8
 
 
 class ComPecDesc(C.Structure):
@@ -206,6 +207,25 @@ def _declare(lib):
     lib.com_visible_weights_host.argtypes = [
         C.POINTER(ComSceneDesc), C.POINTER(ComLattice), vp, i64, i64, vp, vp, i64, u64p, C.POINTER(ComStats),
     ]
+    lib.com_visibility_weights_host_scene.argtypes = [vp, C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, u64p,
+                                                      C.POINTER(ComStats)]
+    lib.com_visible_weights_host_scene.argtypes = [vp, C.POINTER(ComLattice), vp, i64, i64, vp, vp, i64, u64p,
+                                                   C.POINTER(ComStats)]
+    lib.com_emissivity_integrate_indexed_host_tables.argtypes = [vp, dp, i32, C.c_double, dp, i64, vp, dp, i64, dp, vp, vp, dp]
+    lib.com_volume_create.argtypes = [C.POINTER(ComLattice), i64, C.c_double, C.POINTER(vp)]
+    lib.com_volume_destroy.argtypes = [vp]
+    lib.com_volume_voxels.restype = C.c_int64
+    lib.com_volume_voxels.argtypes = [vp]
+    lib.com_volume_chunk.restype = C.c_int64
+    lib.com_volume_chunk.argtypes = [vp]
+    lib.com_volume_reff_mm.restype = vp
+    lib.com_volume_reff_mm.argtypes = [vp]
+    lib.com_volume_set_reff_resampled.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+    lib.com_volume_set_reff_quadratic.argtypes = [vp, dp, C.c_double, vp]
+    lib.com_volume_histograms.argtypes = [vp, i32, C.POINTER(vp), vp, vp, vp]
+    lib.com_volume_histograms_host.argtypes = [vp, i32, C.POINTER(vp), vp, i64, i64, i64, vp, vp]
+    lib.com_histograms_flux.argtypes = [i32, C.POINTER(vp), vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, i32, vp, vp]
+    lib.com_histograms_flux_host.argtypes = [i32, C.POINTER(vp), vp, i32, i32, C.c_double, vp, vp, i32, vp]
     lib.com_compact_workspace_bytes.restype = C.c_size_t
     lib.com_compact_workspace_bytes.argtypes = [i64]
     lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
@@ -249,7 +269,11 @@ EXPORTED_SYMBOLS = [
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
     "com_write_stage1_csv", "com_format_float_repr", "com_scene_filter_certain_host",
-    "com_emissivity_integrate_indexed_host",
+    "com_emissivity_integrate_indexed_host", "com_emissivity_integrate_indexed_host_tables",
+    "com_visibility_weights_host_scene", "com_visible_weights_host_scene",
+    "com_volume_create", "com_volume_destroy", "com_volume_voxels", "com_volume_chunk", "com_volume_reff_mm",
+    "com_volume_set_reff_resampled", "com_volume_set_reff_quadratic", "com_volume_histograms",
+    "com_volume_histograms_host", "com_histograms_flux", "com_histograms_flux_host",
 ]
 
 

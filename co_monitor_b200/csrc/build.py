@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["geometry_host.cu", "visibility.cu", "emissivity.cu", "reff.cu", "io_host.cu", "capi.cu"]
+SOURCES = ["geometry_host.cu", "visibility.cu", "emissivity.cu", "reff.cu", "io_host.cu", "capi.cu", "volume.cu"]
 LIB = os.path.join(HERE, "libcomonitor_sm100.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,6 +18,7 @@ size_t visibility_workspace_bytes(const DeviceScene&, long long, double);
 long long lattice_local_voxels(const ComLattice&);
 void kernel_timing_enable(int on);
 void kernel_timing_read(double*, double*, long long*);
+int host_call_wait(cudaStream_t s);  // blocking (non-spinning) wait for the stream, volume.cu
 }  // namespace com
 
 #define COM_CUDA(x)                                                            \
@@ -172,7 +173,8 @@ __global__ void compact_scan(unsigned int* block_counts, long long n_blocks, uns
 }
 
 __global__ void compact_scatter(const unsigned int* nrays, const double* w, long long n, long long vox_begin,
-                                const unsigned long long* offsets, long long* idx_out, double* w_out) {
+                                const unsigned long long* offsets, long long* idx_out, double* w_out,
+                                unsigned long long capacity) {
   __shared__ unsigned int s_warp[32];
   long long i = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
   bool flag = i < n && nrays[i] > 0;
@@ -191,8 +193,10 @@ __global__ void compact_scatter(const unsigned int* nrays, const double* w, long
   __syncthreads();
   if (flag) {
     unsigned long long pos = offsets[blockIdx.x] + s_warp[warp] + __popc(b & ((1u << lane) - 1u));
-    idx_out[pos] = vox_begin + i;
-    if (w_out) w_out[pos] = w[i];
+    if (pos < capacity) {
+      idx_out[pos] = vox_begin + i;
+      if (w_out) w_out[pos] = w[i];
+    }
   }
 }
 
@@ -362,35 +366,44 @@ int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, c
                                 static_cast<cudaStream_t>(stream));
 }
 
-// Shared body of the two host-buffer Stage-1 calls.  dense: per-voxel arrays come back; otherwise the visible voxels
-// are compacted on the device and only (flat index, weight) pairs come back.
-static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
-                                int64_t vox_begin, int64_t vox_end, bool dense, double* w_out_h, uint32_t* nrays_out_h,
-                                int64_t* idx_out_h, int64_t visible_capacity, uint64_t* visible_count_h,
-                                ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
-                                ComStats* stats_out_h) {
-  com::HostScene hs;
-  int rc = com::build_host_scene(*desc_h, hs);
-  if (rc) return rc;
-  SceneBlob blob;
-  make_scene_blob(hs, blob);
-  ComScene scene;  // tables live in the arena: nothing to free
-  scene.dev = hs.dev;
-  scene.filter_eps_mm = desc_h->filter_eps_mm;
+// Shared body of the host-buffer Stage-1 calls.  dense: per-voxel arrays come back; otherwise the visible voxels are
+// compacted on the device straight into pinned host memory (zero-copy stores) and only (flat index, weight) pairs
+// come back.  scene_h != NULL: the caller's scene handle is used as it is (nothing is rebuilt or uploaded).
+static int compact_visible_capped(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
+                                  double* w_compact, int64_t capacity, uint64_t* count_out, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t s);
 
+static int visibility_host_impl(const ComScene* scene_h, const ComSceneDesc* desc_h, const ComLattice* lattice_h,
+                                const double* vox_xyz_h, int64_t vox_begin, int64_t vox_end, bool dense, double* w_out_h,
+                                uint32_t* nrays_out_h, int64_t* idx_out_h, int64_t visible_capacity,
+                                uint64_t* visible_count_h, ComRayRecord* rays_out_h, int64_t rays_capacity,
+                                uint64_t* rays_count_out_h, ComStats* stats_out_h) {
+  com::HostScene hs;
+  SceneBlob blob;
+  ComScene local;  // description given instead of a handle: tables live in the arena, nothing to free
+  const ComScene* scene = scene_h;
+  if (!scene) {
+    int rc0 = com::build_host_scene(*desc_h, hs);
+    if (rc0) return rc0;
+    make_scene_blob(hs, blob);
+    local.dev = hs.dev;
+    local.filter_eps_mm = desc_h->filter_eps_mm;
+    scene = &local;
+  }
+  int rc = COM_OK;
   const int64_t n = vox_end - vox_begin;
-  const size_t ws_bytes = com::visibility_workspace_bytes(scene.dev, n, 0.0);
+  const int64_t cap = dense ? 0 : std::min<int64_t>(visible_capacity, n);
+  const size_t ws_bytes = com::visibility_workspace_bytes(scene->dev, n, 0.0);
   const size_t cws_bytes = dense ? 0 : com_compact_workspace_bytes(n);
   const size_t b_scene = align_up(blob.bytes.size(), 256);
   const size_t b_w = align_up(sizeof(double) * (size_t)n, 256), b_n = align_up(sizeof(uint32_t) * (size_t)n, 256);
   const size_t b_vox = (!lattice_h) ? align_up(sizeof(double) * 3 * (size_t)n, 256) : 0;
   const size_t b_rays = rays_out_h ? align_up(sizeof(ComRayRecord) * (size_t)rays_capacity, 256) : 0;
-  const size_t b_idx = dense ? 0 : align_up(sizeof(int64_t) * (size_t)n, 256);
-  const size_t b_wc = dense ? 0 : b_w;
   const size_t b_misc = 512;
-  const size_t total = b_scene + b_w + b_n + b_vox + b_rays + b_idx + b_wc + b_misc + align_up(cws_bytes, 256) + ws_bytes;
+  const size_t b_cap = align_up(sizeof(int64_t) * (size_t)cap, 256);  // per compacted array, in pinned memory
+  const size_t total = b_scene + b_w + b_n + b_vox + b_rays + b_misc + align_up(cws_bytes, 256) + ws_bytes;
   char *d = nullptr, *pin = nullptr;
-  rc = com::HostArena::reserve(total, align_up(blob.bytes.size(), 256) + 512, &d, &pin);
+  rc = com::HostArena::reserve(total, b_scene + 512 + 2 * b_cap, &d, &pin);
   if (rc) return rc;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -403,47 +416,51 @@ static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* la
   uint32_t* d_n = reinterpret_cast<uint32_t*>(take(b_n));
   double* d_vox = b_vox ? reinterpret_cast<double*>(take(b_vox)) : nullptr;
   ComRayRecord* d_rays = b_rays ? reinterpret_cast<ComRayRecord*>(take(b_rays)) : nullptr;
-  int64_t* d_idx = b_idx ? reinterpret_cast<int64_t*>(take(b_idx)) : nullptr;
-  double* d_wc = b_wc ? reinterpret_cast<double*>(take(b_wc)) : nullptr;
   char* d_misc = take(b_misc);
   ComStats* d_stats = reinterpret_cast<ComStats*>(d_misc);
   uint64_t* d_rcount = reinterpret_cast<uint64_t*>(d_misc + 256);
   uint64_t* d_vcount = reinterpret_cast<uint64_t*>(d_misc + 264);
   void* d_cws = take(align_up(cws_bytes, 256));
   void* d_ws = take(ws_bytes);
+  char* pin_misc = pin + b_scene;
+  int64_t* pin_idx = reinterpret_cast<int64_t*>(pin + b_scene + 512);
+  double* pin_w = reinterpret_cast<double*>(pin + b_scene + 512 + b_cap);
 
   cudaStream_t s = cudaStreamPerThread;  // concurrent host threads overlap on the device
-  std::memcpy(pin, blob.bytes.data(), blob.bytes.size());
-  COM_CUDA(cudaMemcpyAsync(d_scene, pin, blob.bytes.size(), cudaMemcpyHostToDevice, s));
-  bind_scene(scene.dev, d_scene, blob);
+  if (!scene_h) {
+    std::memcpy(pin, blob.bytes.data(), blob.bytes.size());
+    COM_CUDA(cudaMemcpyAsync(d_scene, pin, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    bind_scene(local.dev, d_scene, blob);
+  }
   const double* d_vox_base = nullptr;
   if (d_vox) {  // explicit voxels: the caller passes rows [vox_begin, vox_end) only; shift so that flat indexing works
     COM_CUDA(cudaMemcpyAsync(d_vox, vox_xyz_h, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
     d_vox_base = d_vox - 3 * vox_begin;
   }
-  rc = com::visibility_launch(&scene, lattice_h, d_vox_base, vox_begin, vox_end, d_w, d_n, d_rays, rays_capacity,
+  rc = com::visibility_launch(scene, lattice_h, d_vox_base, vox_begin, vox_end, d_w, d_n, d_rays, rays_capacity,
                               d_rays ? reinterpret_cast<unsigned long long*>(d_rcount) : nullptr, nullptr, nullptr, 0,
                               d_stats, d_ws, ws_bytes, s);
   if (rc) return rc;
-  char* pin_misc = pin + align_up(blob.bytes.size(), 256);
   if (dense) {
     COM_CUDA(cudaMemcpyAsync(w_out_h, d_w, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
     if (nrays_out_h) COM_CUDA(cudaMemcpyAsync(nrays_out_h, d_n, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
   } else {
-    rc = com_compact_visible(d_n, d_w, n, vox_begin, d_idx, d_wc, d_vcount, d_cws, cws_bytes, s);
+    // pinned host memory is addressable from the device: the scatter kernel stores the compacted pairs there
+    rc = compact_visible_capped(d_n, d_w, n, vox_begin, pin_idx, pin_w, cap, d_vcount, d_cws, cws_bytes, s);
     if (rc) return rc;
   }
   COM_CUDA(cudaMemcpyAsync(pin_misc, d_misc, 512, cudaMemcpyDeviceToHost, s));
-  COM_CUDA(cudaStreamSynchronize(s));
+  rc = com::host_call_wait(s);  // the only wait of the call unless a ray list was asked for
+  if (rc) return rc;
   std::memcpy(stats_out_h, pin_misc, sizeof(ComStats));
   if (!dense) {
     uint64_t count = 0;
     std::memcpy(&count, pin_misc + 264, sizeof(count));
     *visible_count_h = count;
-    const size_t m = (size_t)std::min<uint64_t>(count, (uint64_t)visible_capacity);
+    const size_t m = (size_t)std::min<uint64_t>(count, (uint64_t)cap);
     if (m) {
-      COM_CUDA(cudaMemcpyAsync(idx_out_h, d_idx, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, s));
-      COM_CUDA(cudaMemcpyAsync(w_out_h, d_wc, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+      std::memcpy(idx_out_h, pin_idx, sizeof(int64_t) * m);
+      std::memcpy(w_out_h, pin_w, sizeof(double) * m);
     }
   }
   if (d_rays) {
@@ -451,9 +468,12 @@ static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* la
     std::memcpy(&count, pin_misc + 256, sizeof(count));
     *rays_count_out_h = count;
     const size_t m = (size_t)std::min<uint64_t>(count, (uint64_t)rays_capacity);
-    if (m) COM_CUDA(cudaMemcpyAsync(rays_out_h, d_rays, sizeof(ComRayRecord) * m, cudaMemcpyDeviceToHost, s));
+    if (m) {
+      COM_CUDA(cudaMemcpyAsync(rays_out_h, d_rays, sizeof(ComRayRecord) * m, cudaMemcpyDeviceToHost, s));
+      rc = com::host_call_wait(s);
+      if (rc) return rc;
+    }
   }
-  COM_CUDA(cudaStreamSynchronize(s));
   if (stats_out_h->overflow) {
     com::set_error("candidate list overflow: %llu candidates > capacity %llu",
                    (unsigned long long)stats_out_h->candidates, (unsigned long long)stats_out_h->candidate_capacity);
@@ -470,28 +490,63 @@ static int visibility_host_impl(const ComSceneDesc* desc_h, const ComLattice* la
   return COM_OK;
 }
 
+static bool dense_args_ok(const void* scene_or_desc, const ComLattice* lattice_h, const double* vox_xyz_h, int64_t vox_begin,
+                          int64_t vox_end, const double* w_out_h, const ComRayRecord* rays_out_h,
+                          const uint64_t* rays_count_out_h, const ComStats* stats_out_h) {
+  return scene_or_desc && (lattice_h || vox_xyz_h) && w_out_h && stats_out_h && vox_end >= vox_begin &&
+         !(rays_out_h && !rays_count_out_h);
+}
+
+static bool sparse_args_ok(const void* scene_or_desc, const ComLattice* lattice_h, const double* vox_xyz_h, int64_t vox_begin,
+                           int64_t vox_end, const int64_t* idx_out_h, const double* w_out_h, int64_t capacity,
+                           const uint64_t* count_out_h, const ComStats* stats_out_h) {
+  return scene_or_desc && (lattice_h || vox_xyz_h) && idx_out_h && w_out_h && count_out_h && stats_out_h &&
+         vox_end >= vox_begin && capacity >= 0;
+}
+
 int com_visibility_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
                                 int64_t vox_begin, int64_t vox_end, double* w_out_h, uint32_t* nrays_out_h,
                                 ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
                                 ComStats* stats_out_h) {
-  if (!desc_h || (!lattice_h && !vox_xyz_h) || !w_out_h || !stats_out_h || vox_end < vox_begin ||
-      (rays_out_h && !rays_count_out_h)) {
+  if (!dense_args_ok(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, w_out_h, rays_out_h, rays_count_out_h, stats_out_h)) {
     com::set_error("com_visibility_weights_host: bad arguments");
     return COM_E_BADARG;
   }
-  return visibility_host_impl(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, true, w_out_h, nrays_out_h, nullptr, 0,
-                              nullptr, rays_out_h, rays_capacity, rays_count_out_h, stats_out_h);
+  return visibility_host_impl(nullptr, desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, true, w_out_h, nrays_out_h, nullptr,
+                              0, nullptr, rays_out_h, rays_capacity, rays_count_out_h, stats_out_h);
+}
+
+int com_visibility_weights_host_scene(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                      int64_t vox_begin, int64_t vox_end, double* w_out_h, uint32_t* nrays_out_h,
+                                      ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
+                                      ComStats* stats_out_h) {
+  if (!dense_args_ok(scene, lattice_h, vox_xyz_h, vox_begin, vox_end, w_out_h, rays_out_h, rays_count_out_h, stats_out_h)) {
+    com::set_error("com_visibility_weights_host_scene: bad arguments");
+    return COM_E_BADARG;
+  }
+  return visibility_host_impl(scene, nullptr, lattice_h, vox_xyz_h, vox_begin, vox_end, true, w_out_h, nrays_out_h, nullptr,
+                              0, nullptr, rays_out_h, rays_capacity, rays_count_out_h, stats_out_h);
 }
 
 int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* lattice_h, const double* vox_xyz_h,
                              int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
                              int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h) {
-  if (!desc_h || (!lattice_h && !vox_xyz_h) || !idx_out_h || !w_out_h || !count_out_h || !stats_out_h ||
-      vox_end < vox_begin || capacity < 0) {
+  if (!sparse_args_ok(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, idx_out_h, w_out_h, capacity, count_out_h, stats_out_h)) {
     com::set_error("com_visible_weights_host: bad arguments");
     return COM_E_BADARG;
   }
-  return visibility_host_impl(desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, false, w_out_h, nullptr, idx_out_h,
+  return visibility_host_impl(nullptr, desc_h, lattice_h, vox_xyz_h, vox_begin, vox_end, false, w_out_h, nullptr, idx_out_h,
+                              capacity, count_out_h, nullptr, 0, nullptr, stats_out_h);
+}
+
+int com_visible_weights_host_scene(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                   int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
+                                   int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h) {
+  if (!sparse_args_ok(scene, lattice_h, vox_xyz_h, vox_begin, vox_end, idx_out_h, w_out_h, capacity, count_out_h, stats_out_h)) {
+    com::set_error("com_visible_weights_host_scene: bad arguments");
+    return COM_E_BADARG;
+  }
+  return visibility_host_impl(scene, nullptr, lattice_h, vox_xyz_h, vox_begin, vox_end, false, w_out_h, nullptr, idx_out_h,
                               capacity, count_out_h, nullptr, 0, nullptr, stats_out_h);
 }
 
@@ -520,12 +575,20 @@ size_t com_compact_workspace_bytes(int64_t n) {
 int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
                         double* w_compact, uint64_t* count_out, void* workspace, size_t workspace_bytes,
                         com_stream_t stream) {
-  if (!nrays || !idx_out || !count_out || n < 0 || !workspace || workspace_bytes < com_compact_workspace_bytes(n) ||
-      (w_compact && !w)) {
+  return compact_visible_capped(nrays, w, n, vox_begin, idx_out, w_compact, n, count_out, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+static int compact_visible_capped(const uint32_t* nrays, const double* w, int64_t n, int64_t vox_begin, int64_t* idx_out,
+                                  double* w_compact, int64_t capacity, uint64_t* count_out, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t s) {
+  if (!nrays || (!idx_out && capacity > 0) || !count_out || n < 0 || !workspace ||
+      workspace_bytes < com_compact_workspace_bytes(n) || (w_compact && !w)) {
     com::set_error("com_compact_visible: bad arguments");
     return COM_E_BADARG;
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n == 0) {
     COM_CUDA(cudaMemsetAsync(count_out, 0, sizeof(uint64_t), s));
     return COM_OK;
@@ -537,9 +600,8 @@ int com_compact_visible(const uint32_t* nrays, const double* w, int64_t n, int64
   compact_count<<<(unsigned int)blocks, kCompactBlock, 0, s>>>(nrays, n, counts);
   compact_scan<<<1, 1024, 0, s>>>(counts, blocks, offsets, reinterpret_cast<unsigned long long*>(count_out));
   compact_scatter<<<(unsigned int)blocks, kCompactBlock, 0, s>>>(nrays, w, n, vox_begin, offsets,
-                                                                 reinterpret_cast<long long*>(idx_out), w_compact);
+                                                                 reinterpret_cast<long long*>(idx_out), w_compact,
+                                                                 (unsigned long long)capacity);
   COM_CUDA(cudaGetLastError());
   return COM_OK;
 }
-
-}  // extern "C"

@@ -444,6 +444,80 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams P) {
   }
 }
 
+// Stage 2 of a whole-volume run in ONE launch: block (channel, slice) applies the Reff cut to the channel's
+// millimetre histogram (largest non-empty bin, reader.py:210-217), maps the bins to profile rows in shared memory
+// (:220-238), evaluates the rows that carry weight (:282-378) and reduces the flux (:380-401) in a fixed order.
+// Replaces histogram_rows_kernel<<<1,256>>> + sweep_kernel<<<1,1024>>> + the fill of the row histogram per channel.
+constexpr int kMaxChannels = 8;
+constexpr int kFluxThreads = 1024;
+
+struct FluxParams {
+  DevTables tab[kMaxChannels];
+  const double* profiles;  // (n_slices, K, 3)
+  const double* hist_mm;   // (n_channels, kMmBins)
+  int K, n_slices, profile_sorted;
+  double profile_reff_max, conc;
+  double* flux_out;      // (n_channels, n_slices, n_trans + 1)
+  double* boundary_out;  // (n_channels) or null
+  int n_out;             // row stride of flux_out per (channel, slice): max over channels of n_trans + 1
+};
+
+__global__ void __launch_bounds__(kFluxThreads) histogram_flux_kernel(const __grid_constant__ FluxParams P) {
+  extern __shared__ double s_rows[];  // (K)
+  __shared__ int s_max;
+  __shared__ double s_red[kFluxThreads / 32][kMaxTransitions + 1];
+  const int ch = blockIdx.x, s = blockIdx.y;
+  const DevTables& T = P.tab[ch];
+  const int nt = T.n_trans;
+  const double* hist_mm = P.hist_mm + (size_t)ch * kMmBins;
+  const double* prof = P.profiles + (size_t)s * P.K * 3;
+  if (threadIdx.x == 0) s_max = -1;
+  for (int k = threadIdx.x; k < P.K; k += kFluxThreads) s_rows[k] = 0.0;
+  __syncthreads();
+  int m = -1;
+  for (int b = threadIdx.x; b < kMmBins; b += kFluxThreads)
+    if (hist_mm[b] != 0.0) m = b;
+  if (m >= 0) atomicMax(&s_max, m);
+  __syncthreads();
+  const double mapped = s_max >= 0 ? (double)s_max / 1000.0 : 0.0;
+  const double boundary = fmin(mapped, P.profile_reff_max);
+  K2Params R{};  // profile_row() reads these
+  R.profile = prof, R.K = P.K, R.profile_sorted = P.profile_sorted;
+  for (int b = threadIdx.x; b < kMmBins; b += kFluxThreads) {
+    const double h = hist_mm[b], reff = (double)b / 1000.0;
+    if (h != 0.0 && !(reff >= boundary)) atomicAdd(&s_rows[profile_row(R, reff)], h);
+  }
+  __syncthreads();
+  double acc[kMaxTransitions + 1];
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
+  for (int k = threadIdx.x; k < P.K; k += kFluxThreads) {
+    const double h = s_rows[k];
+    if (h == 0.0) continue;
+    RowEval r;
+    eval_row(T, prof[3 * k + 2], prof[3 * k + 1], P.conc, r);
+#pragma unroll
+    for (int t = 0; t < kMaxTransitions; ++t)
+      if (t < nt) acc[t] += r.emis[t] * h;
+    acc[kMaxTransitions] += r.total * h;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t <= kMaxTransitions; ++t) {
+    double v = acc[t];
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= nt) {
+    const int slot = threadIdx.x == nt ? kMaxTransitions : threadIdx.x;
+    double v = 0.0;
+    for (int wq = 0; wq < kFluxThreads / 32; ++wq) v += s_red[wq][slot];
+    P.flux_out[((size_t)ch * P.n_slices + s) * P.n_out + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0 && s == 0 && P.boundary_out) P.boundary_out[ch] = boundary;
+}
+
 }  // namespace com
 
 // ---------------------------------------------------------------------------------------------------------
@@ -723,16 +797,59 @@ int com_emissivity_sweep(const ComTables* tables, const double* profiles, int32_
   return COM_OK;
 }
 
+int com_histograms_flux(int32_t n_channels, const ComTables* const* tables, const double* profiles, int32_t n_slices,
+                        int32_t K, int32_t profile_sorted, double profile_reff_max, double concentration,
+                        const double* hist_mm, double* flux_out, int32_t flux_stride, double* boundary_out,
+                        com_stream_t stream) {
+  if (n_channels < 1 || n_channels > com::kMaxChannels || !tables || !profiles || n_slices < 1 || K < 1 || !hist_mm ||
+      !flux_out) {
+    com::set_error("com_histograms_flux: bad arguments (1..%d channels)", com::kMaxChannels);
+    return COM_E_BADARG;
+  }
+  com::FluxParams P{};
+  int n_out = 0;
+  for (int c = 0; c < n_channels; ++c) {
+    if (!tables[c]) {
+      com::set_error("com_histograms_flux: null tables handle for channel %d", c);
+      return COM_E_BADARG;
+    }
+    P.tab[c] = tables[c]->dev;
+    n_out = std::max(n_out, tables[c]->n_trans + 1);
+  }
+  if (flux_stride < n_out) {
+    com::set_error("com_histograms_flux: flux_stride %d < transitions + 1 = %d", flux_stride, n_out);
+    return COM_E_BADARG;
+  }
+  const size_t smem = sizeof(double) * (size_t)K;
+  if (smem > 160 * 1024) {
+    com::set_error("com_histograms_flux: at most %d profile rows", 160 * 1024 / 8);
+    return COM_E_BADARG;
+  }
+  P.profiles = profiles, P.hist_mm = hist_mm, P.K = K, P.n_slices = n_slices, P.profile_sorted = profile_sorted;
+  P.profile_reff_max = profile_reff_max, P.conc = concentration;
+  P.flux_out = flux_out, P.boundary_out = boundary_out, P.n_out = flux_stride;
+  if (smem > 40 * 1024)
+    COM_CUDA(cudaFuncSetAttribute(com::histogram_flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  com::histogram_flux_kernel<<<dim3(n_channels, n_slices), com::kFluxThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
 }  // extern "C"
 
 // reff_h (n values), or reff_table_h + reff_index_h: voxel i has Reff reff_table_h[reff_index_h[i]] - the join of
 // Emissivity.get_plas_coords_with_rad_frac (reader.py:161-197), done while the inputs are staged for the upload.
-static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_h, int32_t K, double concentration,
+namespace com {
+int host_call_wait(cudaStream_t s);  // volume.cu
+}
+
+static int emissivity_host(const ComTables* tables_handle, const ComTablesDesc* tables_h, const double* profile_h, int32_t K,
+                           double concentration,
                            const double* reff_h, const double* reff_table_h, int64_t n_table, const int64_t* reff_index_h,
                            const double* w_h, int64_t n, double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
                            double* boundary_out_h) {
-  if (!tables_h || !profile_h || (!reff_h && !(reff_table_h && reff_index_h && n_table > 0)) || !w_h || !flux_out_h || n < 0 ||
-      K < 1) {
+  if ((!tables_h && !tables_handle) || !profile_h || (!reff_h && !(reff_table_h && reff_index_h && n_table > 0)) || !w_h ||
+      !flux_out_h || n < 0 || K < 1) {
     com::set_error("com_emissivity_integrate_host: bad arguments");
     return COM_E_BADARG;
   }
@@ -744,10 +861,15 @@ static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_
         return COM_E_BADARG;
       }
   std::vector<double> blob;
-  ComTables T;  // tables live in the shared host-call arena: nothing to free
-  int rc = build_tables_blob(tables_h, blob, T.dev);
-  if (rc) return rc;
-  T.n_trans = tables_h->n_transitions;
+  ComTables T;  // description given instead of a handle: tables live in the host-call arena, nothing to free
+  int rc = COM_OK;
+  if (tables_handle) {
+    T.dev = tables_handle->dev, T.n_trans = tables_handle->n_trans;
+  } else {
+    rc = build_tables_blob(tables_h, blob, T.dev);
+    if (rc) return rc;
+    T.n_trans = tables_h->n_transitions;
+  }
   const int nt = T.n_trans, ncol = 4 + 2 * nt + 1;
   const int sorted = non_decreasing(profile_h, K, 3) ? 1 : 0;
   double pmax = profile_h[0];
@@ -772,7 +894,7 @@ static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_
   std::memcpy(pin + b_tab + b_prof + b_n, w_h, sizeof(double) * (size_t)n);
   cudaStream_t s = cudaStreamPerThread;
   COM_CUDA(cudaMemcpyAsync(d, pin, up, cudaMemcpyHostToDevice, s));
-  bind_tables(T.dev, d);
+  if (!tables_handle) bind_tables(T.dev, d);
   double* d_prof = reinterpret_cast<double*>(d + b_tab);
   double* d_reff = reinterpret_cast<double*>(d + b_tab + b_prof);
   double* d_w = reinterpret_cast<double*>(d + b_tab + b_prof + b_n);
@@ -788,7 +910,8 @@ static int emissivity_host(const ComTablesDesc* tables_h, const double* profile_
   COM_CUDA(cudaMemcpyAsync(pin_out + 128, d_ws + 256 + 8, sizeof(double), cudaMemcpyDeviceToHost, s));
   if (d_pv) COM_CUDA(cudaMemcpyAsync(per_voxel_out_h, d_pv, sizeof(double) * (size_t)n * ncol, cudaMemcpyDeviceToHost, s));
   if (d_valid) COM_CUDA(cudaMemcpyAsync(valid_out_h, d_valid, (size_t)n, cudaMemcpyDeviceToHost, s));
-  COM_CUDA(cudaStreamSynchronize(s));
+  rc = com::host_call_wait(s);
+  if (rc) return rc;
   std::memcpy(flux_out_h, pin_out, sizeof(double) * (nt + 1));
   if (boundary_out_h) std::memcpy(boundary_out_h, pin_out + 128, sizeof(double));
   return COM_OK;
@@ -804,7 +927,7 @@ int com_emissivity_integrate_host(const ComTablesDesc* tables_h, const double* p
     com::set_error("com_emissivity_integrate_host: bad arguments");
     return COM_E_BADARG;
   }
-  return emissivity_host(tables_h, profile_h, K, concentration, reff_h, nullptr, 0, nullptr, w_h, n, flux_out_h,
+  return emissivity_host(nullptr, tables_h, profile_h, K, concentration, reff_h, nullptr, 0, nullptr, w_h, n, flux_out_h,
                          per_voxel_out_h, valid_out_h, boundary_out_h);
 }
 
@@ -816,7 +939,20 @@ int com_emissivity_integrate_indexed_host(const ComTablesDesc* tables_h, const d
     com::set_error("com_emissivity_integrate_indexed_host: bad arguments");
     return COM_E_BADARG;
   }
-  return emissivity_host(tables_h, profile_h, K, concentration, nullptr, reff_table_h, n_table, reff_index_h, w_h, n,
+  return emissivity_host(nullptr, tables_h, profile_h, K, concentration, nullptr, reff_table_h, n_table, reff_index_h, w_h, n,
+                         flux_out_h, per_voxel_out_h, valid_out_h, boundary_out_h);
+}
+
+int com_emissivity_integrate_indexed_host_tables(const ComTables* tables, const double* profile_h, int32_t K,
+                                                 double concentration, const double* reff_table_h, int64_t n_table,
+                                                 const int64_t* reff_index_h, const double* w_h, int64_t n,
+                                                 double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                                                 double* boundary_out_h) {
+  if (!tables || !reff_table_h || !reff_index_h) {
+    com::set_error("com_emissivity_integrate_indexed_host_tables: bad arguments");
+    return COM_E_BADARG;
+  }
+  return emissivity_host(tables, nullptr, profile_h, K, concentration, nullptr, reff_table_h, n_table, reff_index_h, w_h, n,
                          flux_out_h, per_voxel_out_h, valid_out_h, boundary_out_h);
 }
 

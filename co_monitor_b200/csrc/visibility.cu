@@ -59,6 +59,7 @@ struct K1Params {
   const uint16_t* reff_bin;
   double* hist_out;
   int n_bins;
+  int accumulate_stats;  // 1: add this launch's counters to *stats instead of overwriting them (whole-volume runs)
   ComStats* stats;
 };
 
@@ -516,11 +517,17 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const unsigned long long n_front = overflow ? 0ull : P.counters[0];
   const unsigned long long n = overflow ? 0ull : total;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    P.stats->candidates = total;
-    P.stats->certain_candidates = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
-    P.stats->candidate_capacity = P.cand_capacity;
-    P.stats->overflow = overflow ? 1 : 0;
-    P.stats->tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
+    const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
+    const unsigned long long tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
+    if (P.accumulate_stats) {  // launches of one stream run one after the other: plain read-modify-write
+      P.stats->candidates += total, P.stats->certain_candidates += certain, P.stats->tests += tests;
+      P.stats->candidate_capacity = max((unsigned long long)P.stats->candidate_capacity, P.cand_capacity);
+      P.stats->overflow |= overflow ? 1 : 0;
+    } else {
+      P.stats->candidates = total, P.stats->certain_candidates = certain, P.stats->tests = tests;
+      P.stats->candidate_capacity = P.cand_capacity;
+      P.stats->overflow = overflow ? 1 : 0;
+    }
   }
   if ((unsigned long long)blockIdx.x * kExactThreads >= n) return;
   // apertures + edge pool -> shared memory (a few kB)
@@ -686,6 +693,9 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------------
 // Optional per-kernel timing (bench.py's roofline leg): events on the launching stream around K1a / K1b.
+static thread_local bool g_accumulate_stats = false;
+void visibility_accumulate_stats(bool on) { g_accumulate_stats = on; }
+
 static bool g_timing_on = false;
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 static double g_ms_accum[2] = {0, 0};
@@ -818,6 +828,7 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   P.hist_out = hist_out;
   P.n_bins = n_bins;
   P.stats = stats_out;
+  P.accumulate_stats = g_accumulate_stats ? 1 : 0;
 
   cudaError_t e;
 #define COM_CUDA(x)                                                        \
@@ -832,7 +843,7 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     return COM_E_BADARG;
   }
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
-  COM_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(ComStats), stream));
+  if (!g_accumulate_stats) COM_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(ComStats), stream));
   if (n_vox) COM_CUDA(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)n_vox, stream));
   if (nrays_out && n_vox) COM_CUDA(cudaMemsetAsync(nrays_out, 0, sizeof(unsigned int) * (size_t)n_vox, stream));
   if (rays_count_out) COM_CUDA(cudaMemsetAsync(rays_count_out, 0, sizeof(unsigned long long), stream));

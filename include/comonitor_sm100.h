@@ -273,6 +273,17 @@ int com_visible_weights_host(const ComSceneDesc* desc_h, const ComLattice* latti
                              int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
                              int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h);
 
+/* The same two calls for a caller that keeps the ComScene handle (com_scene_create) across calls - e.g. one Simulation
+ * per voxel range, or a sweep over lattices: the scene is neither rebuilt nor uploaded again, the compacted result is
+ * written straight into pinned host memory by the device, and the call waits once (blocking, not spinning). */
+int com_visibility_weights_host_scene(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                      int64_t vox_begin, int64_t vox_end, double* w_out_h, uint32_t* nrays_out_h,
+                                      ComRayRecord* rays_out_h, int64_t rays_capacity, uint64_t* rays_count_out_h,
+                                      ComStats* stats_out_h);
+int com_visible_weights_host_scene(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz_h,
+                                   int64_t vox_begin, int64_t vox_end, int64_t* idx_out_h, double* w_out_h,
+                                   int64_t capacity, uint64_t* count_out_h, ComStats* stats_out_h);
+
 /* (No counterpart in the reference.)  The *_host calls keep one grow-only device block and one pinned staging block per calling thread between calls
  * (cudaMalloc and cudaFree synchronise the device) and run on the per-thread CUDA stream: they may be called
  * concurrently from several host threads (e.g. one channel per thread).  This frees the calling thread's blocks. */
@@ -402,6 +413,60 @@ int com_emissivity_integrate_indexed_host(const ComTablesDesc* tables_h, const d
                                           double concentration, const double* reff_table_h, int64_t n_table,
                                           const int64_t* reff_index_h, const double* w_h, int64_t n, double* flux_out_h,
                                           double* per_voxel_out_h, uint8_t* valid_out_h, double* boundary_out_h);
+
+/* Same as com_emissivity_integrate_indexed_host for a caller that keeps the ComTables handle (com_tables_create) across
+ * calls - the loop over time slices of co_monitor/emissivity/main.py:39-60 builds one Emissivity per slice with the same
+ * tables: they are then neither rebuilt nor uploaded again. */
+int com_emissivity_integrate_indexed_host_tables(const ComTables* tables, const double* profile_h, int32_t K,
+                                                 double concentration, const double* reff_table_h, int64_t n_table,
+                                                 const int64_t* reff_index_h, const double* w_h, int64_t n,
+                                                 double* flux_out_h, double* per_voxel_out_h, uint8_t* valid_out_h,
+                                                 double* boundary_out_h);
+
+/* ---- whole-volume runs (fused Stage 1 -> Stage 2; BASELINE config 5) ----------------
+ * The reference writes a per-voxel table (Simulation.save_to_file, simulation.py:616-630) that Emissivity reads back
+ * (reader.py:136-197).  For a lattice of 1e8-1e9 voxels that table is never built here: a ComVolume holds the Reff
+ * millimetre bins of the voxels of one (shard of a) lattice on the device (2 B per voxel) and runs Stage 1 launch by
+ * launch, each launch followed by the 10 B/voxel pass that folds its weights into the channel's millimetre histogram
+ * (the only thing reader.py:199-401 needs of the voxels).  Per-rank histograms add: ranks all-reduce(SUM) the packed
+ * (n_channels, COM_MM_BINS) buffer once, then every rank evaluates Stage 2 from the global histograms.
+ *   chunk_voxels        voxels per Stage-1 launch (<= 0: 2^26), rounded up to a multiple of 8
+ *   candidate_fraction  capacity of the per-launch candidate list as a fraction of the launch's rays (<= 0: 2 %) */
+#define COM_MAX_CHANNELS 8
+typedef struct ComVolume ComVolume;
+int com_volume_create(const ComLattice* lattice_h, int64_t chunk_voxels, double candidate_fraction, ComVolume** out);
+int com_volume_destroy(ComVolume* volume);
+int64_t com_volume_voxels(const ComVolume* volume);
+int64_t com_volume_chunk(const ComVolume* volume);
+const uint16_t* com_volume_reff_mm(const ComVolume* volume); /* DEVICE (voxels) uint16, 0xFFFF outside the LCFS */
+/* Reff bins of the volume's voxels (replaces reff_VMEC.py:85-136 like com_reff_resample / com_reff_quadratic).
+ * src_reff: (src_ny, src_nx, src_nz) fp64 grid, HOST when src_is_host != 0 (copied up on the stream) else DEVICE. */
+int com_volume_set_reff_resampled(ComVolume* volume, const double* src_reff, int32_t src_is_host, int64_t src_nx,
+                                  int64_t src_ny, int64_t src_nz, com_stream_t stream);
+int com_volume_set_reff_quadratic(ComVolume* volume, const double* coef_h, double reff_max, com_stream_t stream);
+/* Stage 1 of every voxel of the volume for n_channels scenes (what n_channels Simulation runs would compute,
+ * simulation.py:50-72) reduced to  hist_mm[c][mm] = sum of total_intensity_fraction over the voxels with that Reff
+ * millimetre  (DEVICE (n_channels, COM_MM_BINS) fp64, overwritten) and the counters summed over the launches
+ * (stats DEVICE (n_channels) ComStats, overwritten).  Stream-ordered, no host synchronisation. */
+int com_volume_histograms(ComVolume* volume, int32_t n_channels, const ComScene* const* scenes, double* hist_mm,
+                          ComStats* stats, com_stream_t stream);
+/* Host-buffer form: hist_mm_h / stats_h are HOST arrays; src_reff_h != NULL also (re)builds the Reff bins from that
+ * host grid first.  One device wait.  COM_E_OVERFLOW when a launch overflowed its candidate list. */
+int com_volume_histograms_host(ComVolume* volume, int32_t n_channels, const ComScene* const* scenes,
+                               const double* src_reff_h, int64_t src_nx, int64_t src_ny, int64_t src_nz,
+                               double* hist_mm_h, ComStats* stats_h);
+/* Stage 2 from (global) millimetre histograms in one launch - what n_channels x n_slices Emissivity runs would return
+ * as total_emissivity (reader.py:199-401): per channel the Reff cut at min(largest non-empty bin / 1000,
+ * profile_reff_max) (:210-217), bins -> nearest profile rows (:220-238), rows -> emissivities (:282-378), flux sums
+ * (:380-401).  profiles (n_slices, K, 3) [Reff, T_e, n_e] share their Reff column; flux_out[(c * n_slices + s) *
+ * flux_stride + t], t < transitions(c) + 1 (EXCIT.., then TOTAL); boundary_out (n_channels) nullable. */
+int com_histograms_flux(int32_t n_channels, const ComTables* const* tables, const double* profiles, int32_t n_slices,
+                        int32_t K, int32_t profile_sorted, double profile_reff_max, double concentration,
+                        const double* hist_mm, double* flux_out, int32_t flux_stride, double* boundary_out,
+                        com_stream_t stream);
+int com_histograms_flux_host(int32_t n_channels, const ComTables* const* tables, const double* profiles_h,
+                             int32_t n_slices, int32_t K, double concentration, const double* hist_mm_h,
+                             double* flux_out_h, int32_t flux_stride, double* boundary_out_h);
 
 /* ---- Reff provider ------------------------------------------------------------
  * Replaces the VMEC web-service step (co_monitor/geometry/reff_VMEC.py:85-136) and its 3-decimal file
