@@ -320,7 +320,9 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   // Inner rectangles: the bounding rectangle shrunk until its four corners (hence, by convexity, all of it) are at
   // least `safe` inside every edge of the polygon.  FP32 evaluation of the in-plane coordinates is good to ~1e-4 mm
   //  and the slit polygons agree with slit 0's to 1e-4 mm (checked above): 2e-2 mm is ample.
-  const double safe = std::max(2e-2, 2.0 * dv.near_edge_mm);
+  // A ray the filter calls "certain" skips the fp64 aperture tests altogether, so the extensions that add tests of their
+  // own (segment check, shields) and the detector image (which needs the fp64 detector hit) switch the shortcut off.
+  const double safe = std::max(5e-3, 2.0 * dv.near_band_mm);
   dv.certain_mm = (float)safe;
   auto inner_of = [&](const ComAperture& ap, double& ixlo, double& ixhi, double& iylo, double& iyhi) {
     rect_of(ap, -safe, ixlo, ixhi, iylo, iyhi);
@@ -352,16 +354,51 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
           for (int c = 0; c < 4; ++c)
             if (!(ak.edge[e][0] * cx[c] + ak.edge[e][1] * cy[c] + ak.edge[e][2] >= 0.5 * safe)) okc = false;
       }
-    if (!okc || !okp) dv.inner_crys = dv.inner_plasma = SlitRect{1.f, -1.f, 1.f, -1.f};
+    if (!okc || !okp || dv.physics_flags != 0 || dv.n_shields > 0)
+      dv.inner_crys = dv.inner_plasma = SlitRect{1.f, -1.f, 1.f, -1.f};
   }
 
   const int Cp = dv.n_crystal_padded;
   hs.det_forms.assign((size_t)4 * 3 * Cp, 0.f);
   hs.slit_forms.assign((size_t)4 * 6 * Cp, 0.f);
+  hs.port_forms.assign((size_t)4 * 3 * Cp, 0.f);
   const ComAperture& det = hs.apertures[2 * S + 1];
+  const ComAperture& port = hs.apertures[2 * S];
   double dxlo, dxhi, dylo, dyhi;
   rect_of(det, eps, dxlo, dxhi, dylo, dyhi);
   const double xc = 0.5 * (dxlo + dxhi), yc = 0.5 * (dylo + dyhi), hw = 0.5 * (dxhi - dxlo), hh = 0.5 * (dyhi - dylo);
+  {  // certain regions of detector and port, and whether the column-interval filter applies
+    double a, b, c2, d2;
+    const bool okd = inner_of(det, a, b, c2, d2);
+    dv.det_inner = okd ? SlitRect{(float)((a - xc) / hw), (float)((b - xc) / hw), (float)((c2 - yc) / hh), (float)((d2 - yc) / hh)}
+                       : SlitRect{1.f, -1.f, 1.f, -1.f};
+    rect_of(port, eps, a, b, c2, d2);
+    dv.port_outer = SlitRect{(float)a, (float)b, (float)c2, (float)d2};
+    // the port is a wide 14-gon: its certain region is the bounding rectangle scaled about its centre until the four
+    // corners are inside by `safe`
+    auto inner_scaled = [&](const ComAperture& ap, double& ixlo, double& ixhi, double& iylo, double& iyhi) {
+      double bxlo, bxhi, bylo, byhi;
+      rect_of(ap, 0.0, bxlo, bxhi, bylo, byhi);
+      const double cx = 0.5 * (bxlo + bxhi), cy = 0.5 * (bylo + byhi), hx = 0.5 * (bxhi - bxlo), hy = 0.5 * (byhi - bylo);
+      for (double f = 0.99; f > 0.02; f -= 0.01) {
+        ixlo = cx - f * hx, ixhi = cx + f * hx, iylo = cy - f * hy, iyhi = cy + f * hy;
+        bool inside = true;
+        const double qx[4] = {ixlo, ixhi, ixhi, ixlo}, qy[4] = {iylo, iylo, iyhi, iyhi};
+        for (int k = 0; k < ap.n_edges && inside; ++k)
+          for (int c = 0; c < 4 && inside; ++c) inside = ap.edge[k][0] * qx[c] + ap.edge[k][1] * qy[c] + ap.edge[k][2] >= safe;
+        if (inside) return true;
+      }
+      return false;
+    };
+    const bool okq = inner_scaled(port, a, b, c2, d2);
+    dv.port_inner = okq ? SlitRect{(float)a, (float)b, (float)c2, (float)d2} : SlitRect{1.f, -1.f, 1.f, -1.f};
+    // the interval filter visits every slit a column can reach and emits the rays of each: adjacent slit rectangles
+    // must not overlap (a ray in two of them would be emitted twice)
+    const bool disjoint = S == 1 || (dv.rect_crys.xhi < dv.slit_period + dv.rect_crys.xlo &&
+                                     dv.rect_plasma.xhi < dv.slit_period + dv.rect_plasma.xlo);
+    dv.interval_filter = (periodic && dv.slit_same_w && disjoint && !dv.filter_disabled) ? 1 : 0;
+    if (d.filter_flags & (COM_FILTER_NO_RUN_CULL | COM_FILTER_NO_INTERVALS)) dv.interval_filter = 0;
+  }
   const V3 O = load(d.origin);
   auto unit_normal = [&](const ComAperture& ap) {
     V3 N = load(ap.normal);
@@ -401,6 +438,13 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
       put_slit(3 * side + 0, c, a * load(ap.e1) - cx0 * nh, cl);
       put_slit(3 * side + 1, c, a * load(ap.e2) - cy0 * nh, cl);
       put_slit(3 * side + 2, c, nh, cl);
+    }
+    {  // port plane, same construction: hit of the line voxel -> crystal point at x = X'/W, y = Y'/W (mm, port frame)
+      const V3 nh = unit_normal(port), q = load(port.p1) - cp;
+      const double a = dot(nh, q), cx0 = dot(load(port.e1), q), cy0 = dot(load(port.e2), q);
+      put_at(&hs.port_forms[((size_t)c * 3 + 0) * 4], a * load(port.e1) - cx0 * nh, cl);
+      put_at(&hs.port_forms[((size_t)c * 3 + 1) * 4], a * load(port.e2) - cy0 * nh, cl);
+      put_at(&hs.port_forms[((size_t)c * 3 + 2) * 4], nh, cl);
     }
   }
   return COM_OK;

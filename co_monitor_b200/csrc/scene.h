@@ -62,6 +62,13 @@ struct DeviceScene {
   int pix_nx, pix_ny;
   double pix_mm, pix_x0, pix_y0;
   const float4* slit_forms;      // [Cp][6]: X', Y', W on the crystal-side slit plane, then on the plasma side
+  // Column-interval filter (lattice kernel): along a z-column every aperture test is a linear inequality in the voxel
+  // index, so the passing voxels of a (column, crystal point) pair form a few intervals.
+  int interval_filter;           // 1: the geometry allows it (periodic collimator, disjoint slit rectangles, ...)
+  SlitRect det_inner;            // inner rectangle of the detector polygon in the SCALED frame of det_forms (|x|,|y| <= 1
+                                 // is the grown bounding rectangle); xlo > xhi: no certain region
+  SlitRect port_outer, port_inner;  // bounding / inner rectangle of the port polygon in its aperture frame (mm)
+  const float4* port_forms;      // [Cp][3]: X', Y', W on the port plane
 };
 
 // Host-side result of analysing a ComSceneDesc (pure CPU, no CUDA).
@@ -72,6 +79,7 @@ struct HostScene {
   std::vector<double> edges;
   std::vector<float> det_forms;       // 4 * 3 * Cp
   std::vector<float> slit_forms;      // 4 * 6 * Cp
+  std::vector<float> port_forms;      // 4 * 3 * Cp
   std::vector<double> crystal_xyz, crystal_normal;
 };
 

@@ -85,7 +85,8 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, ~1 ulp: amp
 constexpr int kSlitUnknown = 15;  // candidate records carry the slit the FP32 filter saw in 4 bits; 15 = not known
 constexpr int kSlitCertain = 0x100;  // stage_b: the ray is inside the inner rectangle of that slit on both sides
 constexpr unsigned int kCandCertain = 1u << 27;  // candidate record: the slit tests cannot fail (the exact kernel skips them)
-constexpr unsigned int kCandCrystalMask = kCandCertain - 1u;
+constexpr unsigned int kCandCertainAll = 1u << 26;  // ... nor can the port and detector tests: only the weight is left
+constexpr unsigned int kCandCrystalMask = kCandCertainAll - 1u;
 
 // Returns -1 when the ray misses every slit (band included), else the index of the slit it goes through on both
 // sides, or kSlitUnknown when that is ambiguous / not evaluated.  The exact kernel tries the hinted slit first.
@@ -441,6 +442,240 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
 }
 
 // ------------------------------------------------------------------------------------------------------
+// K1a, column-interval form (the production lattice kernel).
+//
+// Along a z-column the recentred voxel position is p0 + k * dz, so every linear form is f0 + k * df and every aperture
+// test of the filter - a bound on a ratio of two forms whose denominator keeps its sign - is a linear inequality in
+// the voxel index k.  The voxels of a (column, crystal point) pair that can reach the detector are therefore one
+// interval [d_lo, d_hi] (four inequalities), the voxels that also go through slit j on both sides another interval
+// (eight more), and only the slits the column can reach are visited (the slit coordinate at the two ends of the
+// detector interval names them).  What costs ~15 instructions per ray when every ray is evaluated costs ~150 per
+// (column, crystal point) pair here, whatever the column length.
+//
+// Two nested sets of bounds are intersected: the OUTER ones (bounding rectangles grown by eps - the same superset the
+// per-ray kernel accepts) give the candidates, the INNER ones (rectangles at least `certain_mm` inside every polygon
+// edge; for the slit length and the port they are checked at the two ends of the interval, which by convexity
+// covers what lies between) give the rays whose aperture tests cannot fail: the fp64 stage only computes their
+// weight.  Candidates outside the inner interval - the ends of each interval - are decided in fp64 as before.
+// A column on which a denominator changes sign or comes close to zero is handed to the fp64 stage whole.
+constexpr int kColsPerItem = 32;
+
+// intersect [lo, hi] with { k : c0 + k * dc >= 0 }
+__device__ __forceinline__ void clip_halfline(float& lo, float& hi, float c0, float dc) {
+  const float t = -c0 * rcp_approx(dc);
+  if (dc > 0.f) lo = fmaxf(lo, t);
+  else if (dc < 0.f) hi = fminf(hi, t);
+  else if (c0 < 0.f) lo = 1.f, hi = 0.f;
+}
+
+// bounds lo_b <= N/W <= hi_b with sign(W) = s, as two half-lines in k (N, W linear in k)
+__device__ __forceinline__ void clip_ratio(float& lo, float& hi, float s, float n0, float dn, float w0, float dw, float lo_b,
+                                           float hi_b) {
+  clip_halfline(lo, hi, s * fmaf(-lo_b, w0, n0), s * fmaf(-lo_b, dw, dn));
+  clip_halfline(lo, hi, s * fmaf(hi_b, w0, -n0), s * fmaf(hi_b, dw, -dn));
+}
+
+__device__ __forceinline__ bool ratio_inside(float s, float n, float w, float lo_b, float hi_b) {
+  return s * fmaf(-lo_b, w, n) >= 0.f && s * fmaf(hi_b, w, -n) >= 0.f;
+}
+
+__device__ __forceinline__ float dz_dot(const float4 g, const float* dz) {
+  return fmaf(g.x, dz[0], fmaf(g.y, dz[1], g.z * dz[2]));
+}
+
+__global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(const __grid_constant__ K1Params P) {
+  __shared__ float4 s_base[kLatticeWarps][kColsPerItem];  // column base positions (recentred FP32, w = 1)
+  __shared__ uint2 s_out[kLatticeWarps][64];             // candidates waiting for a 32-wide flush
+
+  const DeviceScene& sc = P.sc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Cp = sc.n_crystal_padded, n_cgroups = Cp >> 5;
+  const unsigned int nz = (unsigned int)P.vox.lat.nz;
+  const unsigned int flat_lo = (unsigned int)P.vox_begin, flat_hi = (unsigned int)(P.vox_begin + P.n_vox);
+  const unsigned int colA = flat_lo / nz, colB = (flat_hi - 1u) / nz;
+  uint2* outq = s_out[warp];
+  float4* base = s_base[warp];
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  int on = 0;  // warp-uniform number of pending candidates
+  auto flush = [&](int count) {  // certain candidates to the front of the list, the others to its back
+    __syncwarp();
+    const uint2 mine = outq[min(lane, 63)];
+    const bool is_c = lane < count && (mine.y & kCandCertain) != 0u;
+    const unsigned int bc = __ballot_sync(0xffffffffu, is_c);
+    const int nc = __popc(bc), nu = count - nc;
+    unsigned long long posc = 0, posu = 0;
+    if (lane == 0) {
+      if (nc) posc = atomicAdd(&P.counters[0], (unsigned long long)nc);
+      if (nu) posu = atomicAdd(&P.counters[2], (unsigned long long)nu);
+    }
+    posc = __shfl_sync(0xffffffffu, posc, 0);
+    posu = __shfl_sync(0xffffffffu, posu, 0);
+    if (lane < count) {
+      if (is_c) {
+        const unsigned long long pos = posc + __popc(bc & lt_mask);
+        if (pos < P.cand_capacity) P.cand[pos] = mine;
+      } else {
+        const unsigned long long pos = posu + (lane - __popc(bc & lt_mask));
+        if (pos < P.cand_capacity) P.cand[P.cand_capacity - 1ull - pos] = mine;
+      }
+    }
+    const uint2 carry = outq[min(lane + count, 63)];
+    __syncwarp();
+    if (lane + count < on) outq[lane] = carry;
+    on -= count;
+    __syncwarp();
+  };
+  // every lane offers the rays [a, b] of its column (certain where ci_lo <= k <= ci_hi); the warp emits them side by side
+  auto emit = [&](unsigned int col, int a, int b, int ci_lo, int ci_hi, int ci, int slit) {
+    const int trips = __reduce_max_sync(0xffffffffu, b - a + 1);
+    const unsigned int v0 = col * nz - flat_lo;  // launch-local index of the column's voxel 0 (wraps for a clipped first column)
+    for (int i = 0; i < trips; ++i) {
+      const int k = a + i;
+      const bool have = k <= b;
+      const unsigned int bal = __ballot_sync(0xffffffffu, have);
+      if (have)
+        outq[on + __popc(bal & lt_mask)] = make_uint2(
+            v0 + (unsigned int)k,
+            (unsigned int)ci | ((k >= ci_lo && k <= ci_hi) ? (kCandCertain | kCandCertainAll) : 0u) | ((unsigned int)slit << 28));
+      on += __popc(bal);
+      if (on >= 32) flush(32);
+    }
+  };
+
+  const float nz1 = (float)(nz - 1u);
+  const float T = sc.slit_period, invT = sc.slit_inv_period;
+  const long long n_items = (long long)P.n_tiles * n_cgroups;
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&P.counters[1], 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((long long)item >= n_items) break;
+    const unsigned int cb = (unsigned int)(item / n_cgroups);
+    const int cg = (int)(item - (unsigned long long)cb * n_cgroups);
+    const int ci = cg * 32 + lane;
+    const bool real = ci < sc.n_crystal;
+
+    __syncwarp();
+    const unsigned int col_first = colA + cb * kColsPerItem;
+    {
+      const unsigned int col = col_first + (unsigned int)lane;
+      if (col <= colB) {
+        const D3 p = lattice_position_u32(P.vox.lat, col * nz);
+        base[lane] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 1.f);
+      }
+    }
+    const int ncols = (int)min((unsigned int)kColsPerItem, colB - col_first + 1u);
+    // per-lane constants of this crystal point: detector and slit forms with their z-derivatives
+    const float4 gx = __ldg(&sc.det_forms[ci]), gy = __ldg(&sc.det_forms[Cp + ci]), gw = __ldg(&sc.det_forms[2 * Cp + ci]);
+    const float dxs = dz_dot(gx, P.dz), dys = dz_dot(gy, P.dz), dws = dz_dot(gw, P.dz);
+    const float4* sf = sc.slit_forms + 6 * ci;
+    const float4 fXc = __ldg(sf), fYc = __ldg(sf + 1), fWc = __ldg(sf + 2), fXp = __ldg(sf + 3), fYp = __ldg(sf + 4);
+    const float dXc = dz_dot(fXc, P.dz), dYc = dz_dot(fYc, P.dz), dWc = dz_dot(fWc, P.dz), dXp = dz_dot(fXp, P.dz),
+                dYp = dz_dot(fYp, P.dz);
+    __syncwarp();
+
+#pragma unroll 1
+    for (int j = 0; j < ncols; ++j) {
+      const unsigned int col = col_first + (unsigned int)j;
+      const float4 p0 = base[j];
+      // launch range inside this column
+      const int k_first = col == colA ? (int)(flat_lo - colA * nz) : 0;
+      const int k_last = col == colB ? (int)(flat_hi - 1u - colB * nz) : (int)nz - 1;
+      // ---- mirrored detector: one interval ----
+      const float xs0 = form(gx, p0), ys0 = form(gy, p0), w0 = form(gw, p0);
+      const float w1 = fmaf(nz1, dws, w0);
+      bool weird = real && (!(w0 * w1 > 0.f) || fminf(fabsf(w0), fabsf(w1)) < 1e-3f);
+      const float s = w0 < 0.f ? -1.f : 1.f;
+      float lo = (float)k_first, hi = (float)k_last;
+      clip_ratio(lo, hi, s, xs0, dxs, w0, dws, -1.f, 1.f);
+      clip_ratio(lo, hi, s, ys0, dys, w0, dws, -1.f, 1.f);
+      int d_lo = (int)ceilf(lo - 1e-3f), d_hi = (int)floorf(hi + 1e-3f);
+      d_lo = max(d_lo, k_first), d_hi = min(d_hi, k_last);
+      if (!real || !(lo <= hi + 2e-3f)) d_lo = 1, d_hi = 0;  // (NaN bounds compare false: empty)
+      if (weird) d_lo = k_first, d_hi = k_last;
+      if (!__any_sync(0xffffffffu, d_lo <= d_hi)) continue;
+      // certain part of the detector interval
+      float li = lo, hi_i = hi;
+      clip_ratio(li, hi_i, s, xs0, dxs, w0, dws, sc.det_inner.xlo, sc.det_inner.xhi);
+      clip_ratio(li, hi_i, s, ys0, dys, w0, dws, sc.det_inner.ylo, sc.det_inner.yhi);
+      if (!(sc.det_inner.xlo <= sc.det_inner.xhi)) li = 1.f, hi_i = 0.f;
+
+      // ---- collimator: which slits can the detector interval reach ----
+      const float Xc0 = form(fXc, p0), Yc0 = form(fYc, p0), Wc0 = form(fWc, p0), Xp0 = form(fXp, p0), Yp0 = form(fYp, p0);
+      const float Wc1 = fmaf(nz1, dWc, Wc0);
+      if (d_lo <= d_hi && (!(Wc0 * Wc1 > 0.f) || fminf(fabsf(Wc0), fabsf(Wc1)) < 1e-3f)) weird = true;
+      const bool active = d_lo <= d_hi && !weird;
+      const float sq = Wc0 < 0.f ? -1.f : 1.f;
+      int j_lo = 1, j_hi = 0;
+      if (active) {
+        const float ka = (float)d_lo, kb = (float)d_hi;
+        const float xa = fmaf(ka, dXc, Xc0) * rcp_approx(fmaf(ka, dWc, Wc0));
+        const float xb = fmaf(kb, dXc, Xc0) * rcp_approx(fmaf(kb, dWc, Wc0));
+        j_lo = max(0, (int)ceilf((fminf(xa, xb) - sc.rect_crys.xhi) * invT - 1e-3f));
+        j_hi = min(sc.n_slits - 1, (int)floorf((fmaxf(xa, xb) - sc.rect_crys.xlo) * invT + 1e-3f));
+      }
+      if (weird) {  // a denominator changes sign or vanishes on this column: every voxel of it goes to the fp64 stage
+        j_lo = 0, j_hi = 0;
+      }
+      const int slit_trips = __reduce_max_sync(0xffffffffu, j_hi - j_lo + 1);
+      // port forms of this crystal point at the column base (only needed where something survives)
+      float Xq0 = 0.f, Yq0 = 0.f, Wq0 = 1.f, dXq = 0.f, dYq = 0.f, dWq = 0.f;
+      bool port_loaded = false;
+      for (int t = 0; t < slit_trips; ++t) {
+        const int js = j_lo + t;
+        int a = 1, b = 0, ci_lo = 1, ci_hi = 0, hint = kSlitUnknown;
+        if (weird && t == 0) {
+          a = d_lo, b = d_hi;
+        } else if (active && js <= j_hi) {
+          const float off = (float)js * T;
+          float lo_j = (float)d_lo, hi_j = (float)d_hi;
+          clip_ratio(lo_j, hi_j, sq, Xc0, dXc, Wc0, dWc, off + sc.rect_crys.xlo, off + sc.rect_crys.xhi);
+          clip_ratio(lo_j, hi_j, sq, Xp0, dXp, Wc0, dWc, off + sc.rect_plasma.xlo, off + sc.rect_plasma.xhi);
+          clip_ratio(lo_j, hi_j, sq, Yc0, dYc, Wc0, dWc, sc.rect_crys.ylo, sc.rect_crys.yhi);
+          clip_ratio(lo_j, hi_j, sq, Yp0, dYp, Wc0, dWc, sc.rect_plasma.ylo, sc.rect_plasma.yhi);
+          if (lo_j <= hi_j + 2e-3f) {
+            a = max(d_lo, (int)ceilf(lo_j - 1e-3f)), b = min(d_hi, (int)floorf(hi_j + 1e-3f));
+            hint = min(js, kSlitUnknown);
+          }
+          if (a <= b && sc.inner_crys.xlo <= sc.inner_crys.xhi) {
+            // certain part: inner bounds across the slits and on the detector, the slit length and the port at both ends
+            float l2 = fmaxf(li, (float)a), h2 = fminf(hi_i, (float)b);
+            clip_ratio(l2, h2, sq, Xc0, dXc, Wc0, dWc, off + sc.inner_crys.xlo, off + sc.inner_crys.xhi);
+            clip_ratio(l2, h2, sq, Xp0, dXp, Wc0, dWc, off + sc.inner_plasma.xlo, off + sc.inner_plasma.xhi);
+            if (l2 <= h2) ci_lo = (int)ceilf(l2 + 1e-3f), ci_hi = (int)floorf(h2 - 1e-3f);
+            if (ci_lo <= ci_hi) {
+              if (!port_loaded) {
+                const float4* pf = sc.port_forms + 3 * ci;
+                const float4 fXq = __ldg(pf), fYq = __ldg(pf + 1), fWq = __ldg(pf + 2);
+                Xq0 = form(fXq, p0), Yq0 = form(fYq, p0), Wq0 = form(fWq, p0);
+                dXq = dz_dot(fXq, P.dz), dYq = dz_dot(fYq, P.dz), dWq = dz_dot(fWq, P.dz);
+                port_loaded = true;
+              }
+              bool ok = sc.port_inner.xlo <= sc.port_inner.xhi;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float k = (float)(e ? ci_hi : ci_lo);
+                const float wc = fmaf(k, dWc, Wc0), wq = fmaf(k, dWq, Wq0);
+                const float sp = wq < 0.f ? -1.f : 1.f;
+                ok = ok && fabsf(wq) > 1e-3f && ratio_inside(sq, fmaf(k, dYc, Yc0), wc, sc.inner_crys.ylo, sc.inner_crys.yhi) &&
+                     ratio_inside(sq, fmaf(k, dYp, Yp0), wc, sc.inner_plasma.ylo, sc.inner_plasma.yhi) &&
+                     ratio_inside(sp, fmaf(k, dXq, Xq0), wq, sc.port_inner.xlo, sc.port_inner.xhi) &&
+                     ratio_inside(sp, fmaf(k, dYq, Yq0), wq, sc.port_inner.ylo, sc.port_inner.yhi);
+              }
+              // the port denominator must keep its sign between the two ends
+              ok = ok && fmaf((float)ci_lo, dWq, Wq0) * fmaf((float)ci_hi, dWq, Wq0) > 0.f;
+              if (!ok) ci_lo = 1, ci_hi = 0;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, a <= b)) emit(col, a, b, ci_lo, ci_hi, ci, hint);
+      }
+    }
+  }
+  if (on > 0) flush(on);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K1b: the reference arithmetic, one candidate ray per thread (grid-stride over the candidate list).
 struct HitResult {
   bool pass;
@@ -559,6 +794,8 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
     const bool certain = (e.y & kCandCertain) != 0u;  // K1a found the ray >= certain_mm inside one slit on both sides
+    // ... and inside port and detector: nothing is left to test (the detector image still needs the detector hit)
+    const bool certain_all = (e.y & kCandCertainAll) != 0u && sc.pix_out == nullptr;
     const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
     const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
     // simulation.py:309-321
@@ -569,8 +806,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     double near = 1e300;      // smallest |margin| over the apertures this ray was tested on
     bool seg_ok = true;       // every accepted hit lies on the physical part of its line (extension)
     auto note = [&](const HitResult& h) { near = fmin(near, fabs(h.margin)); };
-    HitResult h = aperture_hit(s_ap[2 * S], s_edges, s_edges_f, tau, plasma, crystal);  // port :372-384
-    note(h);
+    HitResult h{true, 1e300, 0.0, 0.0, 0.5};
+    if (!certain_all) {
+      h = aperture_hit(s_ap[2 * S], s_edges, s_edges_f, tau, plasma, crystal);  // port :372-384
+      note(h);
+    }
     bool ok = h.pass;
     seg_ok = seg_ok && h.s >= 0.0 && h.s <= 1.0;
     if (ok && !certain) {  // collimator :344-369, the same slit on both sides
@@ -610,7 +850,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
         }
       }
     }
-    if (ok) {
+    if (ok && !certain_all) {
       h = aperture_hit(s_ap[2 * S + 1], s_edges, s_edges_f, tau, reflected, crystal);  // detector :387-400
       note(h);
       ok = h.pass;
@@ -797,7 +1037,16 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   const bool lattice_kernel = lattice_h != nullptr && lattice_h->nz >= 1 &&
                               lattice_h->nx * lattice_h->ny * lattice_h->nz < (1ll << 32);
   const int n_groups = P.sc.n_crystal_padded / 32;
-  if (lattice_kernel) {
+  const bool interval_kernel = lattice_kernel && P.sc.interval_filter != 0;
+  if (interval_kernel) {
+    for (int i = 0; i < 3; ++i) P.dz[i] = (float)(lattice_h->step[2] * lattice_h->rotation[6 + i]);
+    const long long nz = lattice_h->nz;
+    const long long n_cols = n_vox > 0 ? (vox_end - 1) / nz - vox_begin / nz + 1 : 0;
+    P.n_tiles = (int)((n_cols + kColsPerItem - 1) / kColsPerItem);  // column blocks
+    P.tile_voxels = 0;
+    P.warps_per_cta = kLatticeWarps;
+    P.n_super = n_groups;
+  } else if (lattice_kernel) {
     // recentred position step along z: step_z * (row 2 of R), mesh_calculation.py:150
     for (int i = 0; i < 3; ++i) P.dz[i] = (float)(lattice_h->step[2] * lattice_h->rotation[6 + i]);
     const long long nz = lattice_h->nz, cpc = (nz + kSegmentMax - 1) / kSegmentMax;
@@ -852,7 +1101,9 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   COM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int threads = P.warps_per_cta * 32;
   int occ = 0;
-  if (lattice_kernel) {
+  if (interval_kernel) {
+    COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, interval_kernel_lattice, threads, 0));
+  } else if (lattice_kernel) {
     COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel_lattice, threads, 0));
   } else {
     COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, threads, 0));
@@ -865,7 +1116,9 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     timing_collect();
     cudaEventRecord(g_ev[0], stream);
   }
-  if (lattice_kernel)
+  if (interval_kernel)
+    interval_kernel_lattice<<<grid, threads, 0, stream>>>(P);
+  else if (lattice_kernel)
     filter_kernel_lattice<<<grid, threads, 0, stream>>>(P);
   else
     filter_kernel<<<grid, threads, 0, stream>>>(P);

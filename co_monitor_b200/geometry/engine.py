@@ -65,8 +65,10 @@ class ChannelScene:
     def __init__(self, crystal_points, normals, slit_crys, slit_plasma, vector_front_back, port_vertices,
                  port_ov, det_vertices, det_ov, origin, area_pt, refl_max, aoi0, refl_sigma=2.2,
                  voxel_corners=None, filter_eps_mm=DEFAULT_FILTER_EPS_MM, calibrate_apertures=True,
-                 near_edge_mm=0.0, host_only=False, run_cull=True, near_band_mm=0.0, segment_check=False, shields=None):
+                 near_edge_mm=0.0, host_only=False, run_cull=True, near_band_mm=0.0, segment_check=False, shields=None,
+                 intervals=True):
         """*near_edge_mm* / *near_band_mm*: widths of the two near-edge counters (defaults 1e-9 and 1e-4 mm).
+        *run_cull* / *intervals*: measurement and test aids selecting the per-ray forms of the lattice filter.
         Extensions, off by default (not reference behaviour): *segment_check* accepts an aperture hit only on the
         physical part of the ray's line; *shields* is a list of ``ComShield``-like dicts (see ``ecrh_shields``) every
         ray must also pass."""
@@ -98,7 +100,9 @@ class ChannelScene:
         d.area_pt, d.refl_max, d.aoi0, d.refl_sigma = float(area_pt), float(refl_max), float(aoi0), float(refl_sigma)
         d.filter_eps_mm = float(filter_eps_mm)
         d.near_edge_mm = float(near_edge_mm)
-        d.filter_flags = 0 if run_cull else 1  # COM_FILTER_NO_RUN_CULL: every ray's detector test evaluated on its own
+        # COM_FILTER_NO_RUN_CULL (1): every ray's detector test evaluated on its own; COM_FILTER_NO_INTERVALS (2): the
+        # per-ray lattice kernel with its run-level cull instead of the column-interval kernel
+        d.filter_flags = (0 if run_cull else 1) | (0 if intervals else 2)
         d.near_band_mm = float(near_band_mm)
         d.physics_flags = _lib.COM_PHYS_SEGMENT_CHECK if segment_check else 0
         if shields:

@@ -51,6 +51,7 @@ typedef void* com_stream_t; /* cudaStream_t */
 
 #define COM_MAX_EDGES 32
 #define COM_FILTER_NO_RUN_CULL 1
+#define COM_FILTER_NO_INTERVALS 2
 #define COM_MAX_SHIELDS 4
 /* ComSceneDesc.physics_flags - optional physics the reference does not compute; 0 = parity path */
 #define COM_PHYS_SEGMENT_CHECK 1 /* an aperture only counts where the physical ray meets it: on the segment voxel ->
