@@ -109,23 +109,23 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Scene tables as one blob; offsets[i] are the section starts (256-byte aligned).
 struct SceneBlob {
   std::vector<char> bytes;
-  size_t offset[7];
+  size_t offset[8];
 };
 
 void make_scene_blob(const com::HostScene& hs, SceneBlob& b) {
-  const void* src[7] = {hs.crystal_xyz.data(), hs.crystal_normal.data(), hs.dev_apertures.data(), hs.edges.data(),
-                        hs.det_forms.data(),   hs.slit_forms.data(),     hs.port_forms.data()};
-  const size_t bytes[7] = {hs.crystal_xyz.size() * sizeof(double),       hs.crystal_normal.size() * sizeof(double),
+  const void* src[8] = {hs.crystal_xyz.data(), hs.crystal_normal.data(), hs.dev_apertures.data(), hs.edges.data(),
+                        hs.det_forms.data(),   hs.slit_forms.data(),     hs.port_forms.data(),    hs.refl_table.data()};
+  const size_t bytes[8] = {hs.crystal_xyz.size() * sizeof(double),       hs.crystal_normal.size() * sizeof(double),
                            hs.dev_apertures.size() * sizeof(com::DevAperture), hs.edges.size() * sizeof(double),
                            hs.det_forms.size() * sizeof(float),          hs.slit_forms.size() * sizeof(float),
-                           hs.port_forms.size() * sizeof(float)};
+                           hs.port_forms.size() * sizeof(float),         hs.refl_table.size() * sizeof(double)};
   size_t total = 0;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < 8; ++i) {
     b.offset[i] = total;
     total += align_up(bytes[i], 256);
   }
   b.bytes.assign(total, 0);
-  for (int i = 0; i < 7; ++i) std::memcpy(b.bytes.data() + b.offset[i], src[i], bytes[i]);
+  for (int i = 0; i < 8; ++i) std::memcpy(b.bytes.data() + b.offset[i], src[i], bytes[i]);
 }
 
 void bind_scene(com::DeviceScene& dev, char* d, const SceneBlob& b) {
@@ -136,6 +136,7 @@ void bind_scene(com::DeviceScene& dev, char* d, const SceneBlob& b) {
   dev.det_forms = reinterpret_cast<const float4*>(d + b.offset[4]);
   dev.slit_forms = reinterpret_cast<const float4*>(d + b.offset[5]);
   dev.port_forms = reinterpret_cast<const float4*>(d + b.offset[6]);
+  dev.refl_table = reinterpret_cast<const double*>(d + b.offset[7]);
 }
 
 // ---- visible-voxel compaction: count per 1024-block, scan the block counts, scatter -------------------

@@ -358,6 +358,12 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
       dv.inner_crys = dv.inner_plasma = SlitRect{1.f, -1.f, 1.f, -1.f};
   }
 
+  hs.refl_table.resize(18001);
+  for (int m = 0; m <= 18000; ++m) {  // the expressions of the fp64 kernel, operation by operation
+    const double aoi = (180.0 - (double)m / 100.0) / 2.0;
+    const double da = aoi - dv.aoi0;
+    hs.refl_table[m] = dv.refl_max * std::exp(-(da * da) / (2.0 * (dv.refl_sigma * dv.refl_sigma)));
+  }
   const int Cp = dv.n_crystal_padded;
   hs.det_forms.assign((size_t)4 * 3 * Cp, 0.f);
   hs.slit_forms.assign((size_t)4 * 6 * Cp, 0.f);

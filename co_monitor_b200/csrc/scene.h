@@ -69,6 +69,9 @@ struct DeviceScene {
                                  // is the grown bounding rectangle); xlo > xhi: no certain region
   SlitRect port_outer, port_inner;  // bounding / inner rectangle of the port polygon in its aperture frame (mm)
   const float4* port_forms;      // [Cp][3]: X', Y', W on the port plane
+  // reflectivity profile at every value the rounded angle can take: refl_table[m] = refl_max * exp(-(aoi - aoi0)^2 /
+  // (2 sigma^2)) with aoi = (180 - m / 100) / 2, m = rint(deg * 100) in 0..18000 (simulation.py:520-531, 564-577)
+  const double* refl_table;
 };
 
 // Host-side result of analysing a ComSceneDesc (pure CPU, no CUDA).
@@ -80,6 +83,7 @@ struct HostScene {
   std::vector<float> det_forms;       // 4 * 3 * Cp
   std::vector<float> slit_forms;      // 4 * 6 * Cp
   std::vector<float> port_forms;      // 4 * 3 * Cp
+  std::vector<double> refl_table;     // 18001
   std::vector<double> crystal_xyz, crystal_normal;
 };
 

@@ -59,6 +59,8 @@ struct K1Params {
   const uint16_t* reff_bin;
   double* hist_out;
   int n_bins;
+  int front_weight_only;  // 1: the front region of the list was produced by the column-interval kernel and is handled by
+                          // weight_kernel (the exact kernel then takes the back region only)
   int accumulate_stats;  // 1: add this launch's counters to *stats instead of overwriting them (whole-volume runs)
   ComStats* stats;
 };
@@ -751,6 +753,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const bool overflow = total > P.cand_capacity;  // the two regions collided: nothing of this launch can be trusted
   const unsigned long long n_front = overflow ? 0ull : P.counters[0];
   const unsigned long long n = overflow ? 0ull : total;
+  const unsigned long long i_first = P.front_weight_only ? n_front : 0ull;  // weight_kernel owns the front region
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
     const unsigned long long tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
       P.stats->overflow = overflow ? 1 : 0;
     }
   }
-  if ((unsigned long long)blockIdx.x * kExactThreads >= n) return;
+  if (i_first + (unsigned long long)blockIdx.x * kExactThreads >= n) return;
   // apertures + edge pool -> shared memory (a few kB)
   DevAperture* s_ap = reinterpret_cast<DevAperture*>(s_raw);
   double* s_edges = reinterpret_cast<double*>(s_raw + sizeof(DevAperture) * sc.n_apertures);
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const bool seg_check = (sc.physics_flags & COM_PHYS_SEGMENT_CHECK) != 0;
   // FP32 edge distances decide beyond this; twice the near-edge radii so that the near-edge counts stay exact
   const float tau = fmaxf(2.0e-3f, 2.f * (float)sc.near_band_mm);
-  for (unsigned long long i = (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x; i < n;
+  for (unsigned long long i = i_first + (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kExactThreads) {
     const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
     const long long vloc = e.x;
@@ -928,6 +931,76 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
                                        (unsigned long long*)&P.stats->segment_rejected_rays};
     for (int q = 0; q < kStats; ++q)
       if (s_acc[q]) atomicAdd(out[q], (unsigned long long)s_acc[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1w: the weight of a ray no aperture test can fail (the front region of the column-interval kernel's list): the
+// reference's distance, angle of incidence with round(deg, 2) and weight (simulation.py:309-321, 494-497, 516-531,
+// 564-577), nothing else.  The reflectivity profile is read from a table over the 18001 values the rounded angle can
+// take.
+constexpr int kWeightThreads = 256;
+
+__global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_constant__ K1Params P) {
+  const DeviceScene& sc = P.sc;
+  const unsigned long long total = P.counters[0] + P.counters[2];
+  const unsigned long long n = total > P.cand_capacity ? 0ull : P.counters[0];  // overflow: the exact kernel reports it
+  unsigned int n_pass = 0, n_vis = 0;
+  const double* __restrict__ table = sc.refl_table;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kWeightThreads + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * kWeightThreads) {
+    const uint2 e = P.cand[i];
+    const long long vloc = e.x;
+    const int ci = (int)(e.y & kCandCrystalMask);
+    const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
+    const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
+    const D3 d = c - p;
+    const D3 r = d - (2.0 * dot(d, nrm)) * nrm;
+    const D3 reflected = c + r, plasma = c - d, crystal = p + d;
+    const D3 v = plasma - crystal, rc = reflected - crystal;
+    const double vv = dot(v, v), dist = sqrt(vv);
+    const double cosang = dot(v, rc) / (sqrt(vv) * sqrt(dot(rc, rc)));
+    const double deg = acos(cosang) * (180.0 / 3.141592653589793);
+    const double m = rint(deg * 100.0);
+    const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * (dist * dist));
+    double prof;
+    if (m >= 0.0 && m <= 18000.0) {
+      prof = table[(int)m];
+    } else {  // NaN angle (cosine rounded beyond 1): what the formula gives
+      const double aoi = (180.0 - m / 100.0) / 2.0, da = aoi - sc.aoi0;
+      prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
+    }
+    const double w = fraction * prof;
+    ++n_pass;
+    atomicAdd(&P.w_out[vloc], w);
+    if (P.nrays_out) {
+      if (atomicAdd(&P.nrays_out[vloc], 1u) == 0u) ++n_vis;
+    }
+    if (P.hist_out) {
+      const int bin = P.reff_bin[P.vox_begin + vloc];
+      if (bin < P.n_bins) atomicAdd(&P.hist_out[bin], w);
+    }
+    if (P.rays_out) {
+      const unsigned long long pos = atomicAdd(P.rays_count, 1ull);
+      if ((long long)pos < P.rays_capacity)
+        P.rays_out[pos] = ComRayRecord{(P.vox_begin + vloc) * (long long)sc.n_crystal + ci, dist, (180.0 - m / 100.0) / 2.0, w};
+    }
+  }
+  __shared__ unsigned int s_acc[2];
+  if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int off = 16; off; off >>= 1) {
+    n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);
+    n_vis += __shfl_down_sync(0xffffffffu, n_vis, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_pass) atomicAdd(&s_acc[0], n_pass);
+    if (n_vis) atomicAdd(&s_acc[1], n_vis);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
+    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[1]);
   }
 }
 
@@ -1134,6 +1207,15 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
     const unsigned int blocks = (unsigned int)std::max<unsigned long long>(
         1, std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, (unsigned long long)sms * occ_x * 4ull));
+    P.front_weight_only = (interval_kernel && P.sc.pix_out == nullptr) ? 1 : 0;
+    if (P.front_weight_only) {
+      int occ_w = 0;
+      COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, weight_kernel, kWeightThreads, 0));
+      if (occ_w < 1) occ_w = 1;
+      const unsigned int wblocks = (unsigned int)std::max<unsigned long long>(
+          1, std::min<unsigned long long>((slots + kWeightThreads - 1) / kWeightThreads, (unsigned long long)sms * occ_w * 4ull));
+      weight_kernel<<<wblocks, kWeightThreads, 0, stream>>>(P);
+    }
     exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
   }
   COM_CUDA(cudaGetLastError());
