@@ -343,6 +343,24 @@ int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9) {
   return COM_OK;
 }
 
+int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, int32_t* interval_filter,
+                                   float* port_forms_out) {
+  if (!desc_h) {
+    com::set_error("com_scene_interval_tables_host: null argument");
+    return COM_E_BADARG;
+  }
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  if (rects12) {
+    const com::SlitRect r[3] = {hs.dev.det_inner, hs.dev.port_outer, hs.dev.port_inner};
+    std::memcpy(rects12, r, sizeof(r));
+  }
+  if (interval_filter) *interval_filter = hs.dev.interval_filter;
+  if (port_forms_out) std::memcpy(port_forms_out, hs.port_forms.data(), hs.port_forms.size() * sizeof(float));
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

@@ -597,7 +597,8 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
       if (weird) d_lo = k_first, d_hi = k_last;
       if (!__any_sync(0xffffffffu, d_lo <= d_hi)) continue;
       // certain part of the detector interval
-      float li = lo, hi_i = hi;
+      // (inner bounds start unbounded: only thresholds that really clip are moved inwards by 1e-3 voxel below)
+      float li = -1e9f, hi_i = 1e9f;
       clip_ratio(li, hi_i, s, xs0, dxs, w0, dws, sc.det_inner.xlo, sc.det_inner.xhi);
       clip_ratio(li, hi_i, s, ys0, dys, w0, dws, sc.det_inner.ylo, sc.det_inner.yhi);
       if (!(sc.det_inner.xlo <= sc.det_inner.xhi)) li = 1.f, hi_i = 0.f;
@@ -641,10 +642,10 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
           }
           if (a <= b && sc.inner_crys.xlo <= sc.inner_crys.xhi) {
             // certain part: inner bounds across the slits and on the detector, the slit length and the port at both ends
-            float l2 = fmaxf(li, (float)a), h2 = fminf(hi_i, (float)b);
+            float l2 = li, h2 = hi_i;
             clip_ratio(l2, h2, sq, Xc0, dXc, Wc0, dWc, off + sc.inner_crys.xlo, off + sc.inner_crys.xhi);
             clip_ratio(l2, h2, sq, Xp0, dXp, Wc0, dWc, off + sc.inner_plasma.xlo, off + sc.inner_plasma.xhi);
-            if (l2 <= h2) ci_lo = (int)ceilf(l2 + 1e-3f), ci_hi = (int)floorf(h2 - 1e-3f);
+            if (l2 <= h2) ci_lo = max(a, (int)ceilf(fmaxf(l2, -1e6f) + 1e-3f)), ci_hi = min(b, (int)floorf(fminf(h2, 1e6f) - 1e-3f));
             if (ci_lo <= ci_hi) {
               if (!port_loaded) {
                 const float4* pf = sc.port_forms + 3 * ci;

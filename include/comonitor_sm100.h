@@ -178,6 +178,15 @@ int com_scene_filter_tables_host(const ComSceneDesc* desc_h, int32_t* n_crystal_
  * (check_ray_transmission, simulation.py:344-369, would find it in that slit); port and detector are still tested. */
 int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9);
 
+/* Host-only (no CUDA): the extra tables of the column-interval form of the lattice filter.  rects12 = xlo, xhi, ylo, yhi of
+ * the detector's certain rectangle in the scaled frame of det_forms (the grown bounding rectangle is |x|, |y| <= 1), of
+ * the port's bounding rectangle (band included) and of the port's certain rectangle, both in the port aperture's frame
+ * (mm); *interval_filter = 1 when the geometry allows the interval form (periodic collimator with one shared normal,
+ * disjoint slit rectangles, filter enabled, no COM_FILTER_NO_* flag); port_forms_out [Cp][3][4] floats: X', Y', W on
+ * the port plane.  Any output pointer may be NULL. */
+int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, int32_t* interval_filter,
+                                   float* port_forms_out);
+
 /* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
  * are tested one by one, simulation.py:344-369): whether the collimator was found periodic
  * (stage B of the filter active), whether the filter is disabled, the slit pitch and the band in mm */
