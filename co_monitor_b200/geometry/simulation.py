@@ -57,6 +57,12 @@ class ComputedFrame(pd.DataFrame):
 
 
 @timer
+def _ecrh_shields(element):
+    from .radiation_shield import ecrh_shields
+
+    return ecrh_shields(element)
+
+
 class Simulation:
     def __init__(
         self,
@@ -75,7 +81,14 @@ class Simulation:
         verbose=True,
         stage1_chunk=1 << 26,
         closing_side="top closing side",
+        ecrh_shields=False,
+        segment_check=False,
     ):
+        """Keyword-only extras (none changes the reference's results at its default): *closing_side* selects the
+        collimator position (the reference hard-codes the top one); *ecrh_shields* adds the two ECRH stray-radiation
+        shields of the channel's chamber as circular stops (the reference only draws them, radiation_shield.py:52-101);
+        *segment_check* accepts an aperture hit only on the physical part of the ray's line (the reference intersects
+        infinite lines, simulation.py:143-173).  ``stats`` reports how many rays the last two stopped."""
         self._say = print if verbose else (lambda *a, **k: None)
         self._say(f"\nInitializing element {element}.")
         self.element = element
@@ -102,7 +115,8 @@ class Simulation:
             self.detector_vertices_coordinates, self.detector_orientation_vector,
             origin=self._crystal_central_point, area_pt=self.crystal_point_area, refl_max=self.max_reflectivity,
             aoi0=float(self.AOI), voxel_corners=self.mesh.lattice.bounding_corners(),
-            filter_eps_mm=filter_eps_mm, calibrate_apertures=calibrate_apertures,
+            filter_eps_mm=filter_eps_mm, calibrate_apertures=calibrate_apertures, segment_check=bool(segment_check),
+            shields=_ecrh_shields(element) if ecrh_shields else None,
         )
         self._say("\n--- Calculating photon transmission ---")
         self._visible_idx, self._visible_w, self.stats = self._run_stage1(int(stage1_chunk))

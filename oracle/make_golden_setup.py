@@ -26,6 +26,7 @@ from co_monitor.geometry.detector import Detector  # noqa: E402
 from co_monitor.geometry.dispersive_element import DispersiveElement  # noqa: E402
 from co_monitor.geometry.mesh_calculation import CuboidMesh  # noqa: E402
 from co_monitor.geometry.port import Port  # noqa: E402
+from co_monitor.geometry.radiation_shield import RadiationShield  # noqa: E402
 from co_monitor.geometry.rotation_matrix import rotation_matrix  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "setup_reference.npz")
@@ -66,6 +67,11 @@ def main() -> None:
             out[f"mesh_{s}_n"] = np.array([len(m)])
             out[f"mesh_{s}_idx"] = idx
             out[f"mesh_{s}_pts"] = m[idx]
+        RadiationShield.make_shield = lambda self: None  # the PolyData member is plot-only (pyvista is stubbed)
+        for chamber in ("upper chamber", "bottom chamber"):
+            for shield in ("1st shield", "2nd shield"):
+                rs = RadiationShield(chamber, shield)
+                out[f"shield_{chamber.split()[0]}_{shield[:3]}"] = rs.vertices_coordinates
         out["rot_1rad_z"] = rotation_matrix(1, [0, 0, 1])
         out["rot_odd"] = rotation_matrix(0.3, [0.2, -1.0, 0.5])
     np.savez_compressed(OUT, **out)

@@ -109,3 +109,21 @@ def test_mesh_bit_exact(gold, capsys):
 def test_mesh_rejects_coarse_spacing():
     with pytest.raises(AssertionError):
         CuboidMesh(200)
+
+
+def test_radiation_shield_vertices_bit_exact(gold):
+    """The ECRH shields (plot-only in the reference, an optional stop here) are built like the reference builds them."""
+    from co_monitor_b200.geometry.radiation_shield import RadiationShield, ecrh_shields
+
+    for chamber in ("upper chamber", "bottom chamber"):
+        for shield in ("1st shield", "2nd shield"):
+            rs = RadiationShield(chamber, shield)
+            ref = gold[f"shield_{chamber.split()[0]}_{shield[:3]}"]
+            assert ref.shape == (720, 3) and np.array_equal(rs.vertices_coordinates, ref)
+            st = rs.as_stop()
+            # the stop's frame addresses the same rim: vertex k of the near rim at centre - axis/2 + r (cos u + sin v)
+            k = np.arange(360)
+            rim = st["centre"] - 0.5 * st["axis"] + st["radius"] * (np.cos(np.radians(k))[:, None] * st["u"] + np.sin(np.radians(k))[:, None] * st["v"])
+            np.testing.assert_allclose(rim, ref[0::2], rtol=0, atol=1e-9)
+    assert [round(float(s["centre"][2])) for s in ecrh_shields("C")] == [-80, -97]
+    assert [round(float(s["centre"][2])) for s in ecrh_shields("N")] == [-526, -541]
