@@ -195,7 +195,7 @@ def _declare(lib):
     lib.com_scene_get_aperture.argtypes = [vp, i32, C.POINTER(ComAperture)]
     lib.com_scene_set_detector_image.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, C.c_double]
     lib.com_scene_filter_tables_host.argtypes = [C.POINTER(ComSceneDesc), C.POINTER(i32), vp, vp, vp, vp, vp]
-    lib.com_scene_interval_tables_host.argtypes = [C.POINTER(ComSceneDesc), vp, C.POINTER(i32), vp]
+    lib.com_scene_interval_tables_host.argtypes = [C.POINTER(ComSceneDesc), vp, C.POINTER(i32), vp, vp, vp, C.POINTER(i32)]
     lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), dp, dp]
     lib.com_visibility_workspace_bytes.restype = C.c_size_t
     lib.com_visibility_workspace_bytes.argtypes = [vp, i64, C.c_double]

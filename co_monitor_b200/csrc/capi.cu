@@ -344,7 +344,8 @@ int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9) {
 }
 
 int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, int32_t* interval_filter,
-                                   float* port_forms_out) {
+                                   float* port_forms_out, float* slit_edges_out, int32_t* n_slit_edges_out,
+                                   int32_t* certain_off_out) {
   if (!desc_h) {
     com::set_error("com_scene_interval_tables_host: null argument");
     return COM_E_BADARG;
@@ -358,6 +359,9 @@ int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, i
   }
   if (interval_filter) *interval_filter = hs.dev.interval_filter;
   if (port_forms_out) std::memcpy(port_forms_out, hs.port_forms.data(), hs.port_forms.size() * sizeof(float));
+  if (slit_edges_out) std::memcpy(slit_edges_out, hs.dev.slit_edge, sizeof(hs.dev.slit_edge));
+  if (n_slit_edges_out) n_slit_edges_out[0] = hs.dev.n_slit_edge[0], n_slit_edges_out[1] = hs.dev.n_slit_edge[1];
+  if (certain_off_out) *certain_off_out = hs.dev.certain_off;
   return COM_OK;
 }
 

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_runtime.h>
+
 #include "scene.h"
 
 namespace com {
@@ -324,6 +326,7 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
   // own (segment check, shields) and the detector image (which needs the fp64 detector hit) switch the shortcut off.
   const double safe = std::max(5e-3, 2.0 * dv.near_band_mm);
   dv.certain_mm = (float)safe;
+  bool okc_slits = false;
   auto inner_of = [&](const ComAperture& ap, double& ixlo, double& ixhi, double& iylo, double& iyhi) {
     rect_of(ap, -safe, ixlo, ixhi, iylo, iyhi);
     for (int it = 0; it < 4000 && ixlo < ixhi && iylo < iyhi; ++it) {
@@ -356,6 +359,7 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
       }
     if (!okc || !okp || dv.physics_flags != 0 || dv.n_shields > 0)
       dv.inner_crys = dv.inner_plasma = SlitRect{1.f, -1.f, 1.f, -1.f};
+    okc_slits = okc && okp;
   }
 
   hs.refl_table.resize(18001);
@@ -400,9 +404,18 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
     dv.port_inner = okq ? SlitRect{(float)a, (float)b, (float)c2, (float)d2} : SlitRect{1.f, -1.f, 1.f, -1.f};
     // the interval filter visits every slit a column can reach and emits the rays of each: adjacent slit rectangles
     // must not overlap (a ray in two of them would be emitted twice)
+    for (int side = 0; side < 2; ++side) {
+      const ComAperture& ap = hs.apertures[side];
+      dv.n_slit_edge[side] = std::min(ap.n_edges, 8);
+      for (int k = 0; k < dv.n_slit_edge[side]; ++k)
+        dv.slit_edge[side][k] = make_float4((float)ap.edge[k][0], (float)ap.edge[k][1], (float)(ap.edge[k][2] + eps),
+                                            (float)(ap.edge[k][2] - safe));
+    }
+    const bool few_edges = c0.n_edges <= 8 && p0.n_edges <= 8;
     const bool disjoint = S == 1 || (dv.rect_crys.xhi < dv.slit_period + dv.rect_crys.xlo &&
                                      dv.rect_plasma.xhi < dv.slit_period + dv.rect_plasma.xlo);
-    dv.interval_filter = (periodic && dv.slit_same_w && disjoint && !dv.filter_disabled) ? 1 : 0;
+    dv.interval_filter = (periodic && dv.slit_same_w && disjoint && few_edges && !dv.filter_disabled) ? 1 : 0;
+    dv.certain_off = (!okc_slits || dv.physics_flags != 0 || dv.n_shields > 0) ? 1 : 0;
     if (d.filter_flags & (COM_FILTER_NO_RUN_CULL | COM_FILTER_NO_INTERVALS)) dv.interval_filter = 0;
   }
   const V3 O = load(d.origin);

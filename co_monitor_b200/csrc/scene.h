@@ -1,5 +1,7 @@
 // Internal layout of a channel's device-resident tables (not part of the C ABI).
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstdint>
 #include <vector>
 
@@ -65,9 +67,14 @@ struct DeviceScene {
   // Column-interval filter (lattice kernel): along a z-column every aperture test is a linear inequality in the voxel
   // index, so the passing voxels of a (column, crystal point) pair form a few intervals.
   int interval_filter;           // 1: the geometry allows it (periodic collimator, disjoint slit rectangles, ...)
+  int certain_off;               // 1: no ray is vouched for (extensions that add fp64 tests of their own)
   SlitRect det_inner;            // inner rectangle of the detector polygon in the SCALED frame of det_forms (|x|,|y| <= 1
                                  // is the grown bounding rectangle); xlo > xhi: no certain region
   SlitRect port_outer, port_inner;  // bounding / inner rectangle of the port polygon in its aperture frame (mm)
+  // edges of slit 0's polygon on the crystal side [0] and on the plasma side [1]: a x + b y + c >= 0 inside, (a, b) unit;
+  // .z = c + eps (outer: candidates), .w = c - certain_mm (inner: certain).  Slit j: x -> x - j * period.
+  float4 slit_edge[2][8];
+  int n_slit_edge[2];
   const float4* port_forms;      // [Cp][3]: X', Y', W on the port plane
   // reflectivity profile at every value the rounded angle can take: refl_table[m] = refl_max * exp(-(aoi - aoi0)^2 /
   // (2 sigma^2)) with aoi = (180 - m / 100) / 2, m = rint(deg * 100) in 0..18000 (simulation.py:520-531, 564-577)

@@ -50,7 +50,8 @@ struct K1Params {
   float dz[3];       // lattice kernel: recentred position step between z-consecutive voxels (FP32)
   uint2* cand;       // (voxel_local, crystal) pairs
   unsigned long long cand_capacity;
-  unsigned long long* counters;  // [0] candidates (lattice kernel: the certain ones), [1] next work item, [2] uncertain candidates
+  unsigned long long* counters;  // [0] slots used at the front (certain), [1] next work item, [2] slots used at the back,
+                                 // [3], [4] candidates written front / back when the list is filled in chunks
   double* w_out;
   unsigned int* nrays_out;
   ComRayRecord* rays_out;
@@ -59,6 +60,8 @@ struct K1Params {
   const uint16_t* reff_bin;
   double* hist_out;
   int n_bins;
+  int cand_chunk;         // column-interval kernel: slots a warp reserves at a time (the list then has invalid entries and
+                          // counters[3] / [4] hold the numbers of certain / other candidates really written)
   int front_weight_only;  // 1: the front region of the list was produced by the column-interval kernel and is handled by
                           // weight_kernel (the exact kernel then takes the back region only)
   int accumulate_stats;  // 1: add this launch's counters to *stats instead of overwriting them (whole-volume runs)
@@ -499,27 +502,41 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
   float4* base = s_base[warp];
   const unsigned int lt_mask = (1u << lane) - 1u;
   int on = 0;  // warp-uniform number of pending candidates
-  auto flush = [&](int count) {  // certain candidates to the front of the list, the others to its back
+  // The list is filled in per-warp chunks: a warp reserves P.cand_chunk slots of a region with one atomic and fills
+  // them by itself (one atomic per 32 candidates serialises the whole grid on two L2 addresses).  Slots a warp leaves
+  // unused are marked invalid; the fp64 kernels skip them.  Certain candidates fill the list from the front, the
+  // others from its back, so that the fp64 stage runs warps of one kind.
+  unsigned long long cur_c = 0, cur_u = 0, n_c = 0, n_u = 0;  // warp-uniform: next slot of the open chunks, candidates written
+  int left_c = 0, left_u = 0;
+  const uint2 kInvalid = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+  auto slot = [&](unsigned long long pos, bool back) -> uint2* {
+    return pos < P.cand_capacity ? &P.cand[back ? P.cand_capacity - 1ull - pos : pos] : nullptr;
+  };
+  auto reserve = [&](unsigned long long& cur, int& left, int need, bool back) {  // returns the first slot for `need` entries
+    if (need > left) {
+      if (lane < left)
+        if (uint2* q = slot(cur + lane, back)) *q = kInvalid;  // give up the tail of the open chunk (< 32 slots)
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&P.counters[back ? 2 : 0], (unsigned long long)P.cand_chunk);
+      cur = __shfl_sync(0xffffffffu, base, 0);
+      left = P.cand_chunk;
+    }
+    const unsigned long long first = cur;
+    cur += need, left -= need;
+    return first;
+  };
+  auto flush = [&](int count) {
     __syncwarp();
     const uint2 mine = outq[min(lane, 63)];
     const bool is_c = lane < count && (mine.y & kCandCertain) != 0u;
     const unsigned int bc = __ballot_sync(0xffffffffu, is_c);
     const int nc = __popc(bc), nu = count - nc;
-    unsigned long long posc = 0, posu = 0;
-    if (lane == 0) {
-      if (nc) posc = atomicAdd(&P.counters[0], (unsigned long long)nc);
-      if (nu) posu = atomicAdd(&P.counters[2], (unsigned long long)nu);
-    }
-    posc = __shfl_sync(0xffffffffu, posc, 0);
-    posu = __shfl_sync(0xffffffffu, posu, 0);
+    const unsigned long long posc = nc ? reserve(cur_c, left_c, nc, false) : 0ull;
+    const unsigned long long posu = nu ? reserve(cur_u, left_u, nu, true) : 0ull;
+    n_c += nc, n_u += nu;
     if (lane < count) {
-      if (is_c) {
-        const unsigned long long pos = posc + __popc(bc & lt_mask);
-        if (pos < P.cand_capacity) P.cand[pos] = mine;
-      } else {
-        const unsigned long long pos = posu + (lane - __popc(bc & lt_mask));
-        if (pos < P.cand_capacity) P.cand[P.cand_capacity - 1ull - pos] = mine;
-      }
+      uint2* q = is_c ? slot(posc + __popc(bc & lt_mask), false) : slot(posu + (lane - __popc(bc & lt_mask)), true);
+      if (q) *q = mine;
     }
     const uint2 carry = outq[min(lane + count, 63)];
     __syncwarp();
@@ -630,21 +647,26 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
         if (weird && t == 0) {
           a = d_lo, b = d_hi;
         } else if (active && js <= j_hi) {
+          // the polygon of slit js on both sides, edge by edge: s (a X + b Y + (c - a js T) W) >= 0, outer and inner offsets
           const float off = (float)js * T;
-          float lo_j = (float)d_lo, hi_j = (float)d_hi;
-          clip_ratio(lo_j, hi_j, sq, Xc0, dXc, Wc0, dWc, off + sc.rect_crys.xlo, off + sc.rect_crys.xhi);
-          clip_ratio(lo_j, hi_j, sq, Xp0, dXp, Wc0, dWc, off + sc.rect_plasma.xlo, off + sc.rect_plasma.xhi);
-          clip_ratio(lo_j, hi_j, sq, Yc0, dYc, Wc0, dWc, sc.rect_crys.ylo, sc.rect_crys.yhi);
-          clip_ratio(lo_j, hi_j, sq, Yp0, dYp, Wc0, dWc, sc.rect_plasma.ylo, sc.rect_plasma.yhi);
+          float lo_j = (float)d_lo, hi_j = (float)d_hi, l2 = li, h2 = hi_i;
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const float X0 = side ? Xp0 : Xc0, Y0 = side ? Yp0 : Yc0, dX = side ? dXp : dXc, dY = side ? dYp : dYc;
+            for (int q = 0; q < sc.n_slit_edge[side]; ++q) {
+              const float4 ed = sc.slit_edge[side][q];
+              const float base0 = fmaf(ed.x, X0, ed.y * Y0), based = fmaf(ed.x, dX, ed.y * dY);
+              const float co = fmaf(-ed.x, off, ed.z), cin = fmaf(-ed.x, off, ed.w);
+              clip_halfline(lo_j, hi_j, sq * fmaf(co, Wc0, base0), sq * fmaf(co, dWc, based));
+              clip_halfline(l2, h2, sq * fmaf(cin, Wc0, base0), sq * fmaf(cin, dWc, based));
+            }
+          }
           if (lo_j <= hi_j + 2e-3f) {
             a = max(d_lo, (int)ceilf(lo_j - 1e-3f)), b = min(d_hi, (int)floorf(hi_j + 1e-3f));
             hint = min(js, kSlitUnknown);
           }
-          if (a <= b && sc.inner_crys.xlo <= sc.inner_crys.xhi) {
-            // certain part: inner bounds across the slits and on the detector, the slit length and the port at both ends
-            float l2 = li, h2 = hi_i;
-            clip_ratio(l2, h2, sq, Xc0, dXc, Wc0, dWc, off + sc.inner_crys.xlo, off + sc.inner_crys.xhi);
-            clip_ratio(l2, h2, sq, Xp0, dXp, Wc0, dWc, off + sc.inner_plasma.xlo, off + sc.inner_plasma.xhi);
+          if (a <= b && !sc.certain_off) {
+            // certain part: inner offsets of the slit edges and of the detector rectangle; the port at both ends
             if (l2 <= h2) ci_lo = max(a, (int)ceilf(fmaxf(l2, -1e6f) + 1e-3f)), ci_hi = min(b, (int)floorf(fminf(h2, 1e6f) - 1e-3f));
             if (ci_lo <= ci_hi) {
               if (!port_loaded) {
@@ -658,11 +680,9 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float k = (float)(e ? ci_hi : ci_lo);
-                const float wc = fmaf(k, dWc, Wc0), wq = fmaf(k, dWq, Wq0);
+                const float wq = fmaf(k, dWq, Wq0);
                 const float sp = wq < 0.f ? -1.f : 1.f;
-                ok = ok && fabsf(wq) > 1e-3f && ratio_inside(sq, fmaf(k, dYc, Yc0), wc, sc.inner_crys.ylo, sc.inner_crys.yhi) &&
-                     ratio_inside(sq, fmaf(k, dYp, Yp0), wc, sc.inner_plasma.ylo, sc.inner_plasma.yhi) &&
-                     ratio_inside(sp, fmaf(k, dXq, Xq0), wq, sc.port_inner.xlo, sc.port_inner.xhi) &&
+                ok = ok && fabsf(wq) > 1e-3f && ratio_inside(sp, fmaf(k, dXq, Xq0), wq, sc.port_inner.xlo, sc.port_inner.xhi) &&
                      ratio_inside(sp, fmaf(k, dYq, Yq0), wq, sc.port_inner.ylo, sc.port_inner.yhi);
               }
               // the port denominator must keep its sign between the two ends
@@ -676,6 +696,15 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
     }
   }
   if (on > 0) flush(on);
+  // close the open chunks and report what was really written
+  for (int i = lane; i < left_c; i += 32)
+    if (uint2* q = slot(cur_c + i, false)) *q = kInvalid;
+  for (int i = lane; i < left_u; i += 32)
+    if (uint2* q = slot(cur_u + i, true)) *q = kInvalid;
+  if (lane == 0) {
+    if (n_c) atomicAdd(&P.counters[3], n_c);
+    if (n_u) atomicAdd(&P.counters[4], n_u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -756,14 +785,16 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const unsigned long long n = overflow ? 0ull : total;
   const unsigned long long i_first = P.front_weight_only ? n_front : 0ull;  // weight_kernel owns the front region
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
+    const unsigned long long written = P.cand_chunk ? P.counters[3] + P.counters[4] : total;
+    const unsigned long long certain = P.cand_chunk ? P.counters[3]
+                                                    : ((sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total));
     const unsigned long long tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
     if (P.accumulate_stats) {  // launches of one stream run one after the other: plain read-modify-write
-      P.stats->candidates += total, P.stats->certain_candidates += certain, P.stats->tests += tests;
+      P.stats->candidates += written, P.stats->certain_candidates += certain, P.stats->tests += tests;
       P.stats->candidate_capacity = max((unsigned long long)P.stats->candidate_capacity, P.cand_capacity);
       P.stats->overflow |= overflow ? 1 : 0;
     } else {
-      P.stats->candidates = total, P.stats->certain_candidates = certain, P.stats->tests = tests;
+      P.stats->candidates = written, P.stats->certain_candidates = certain, P.stats->tests = tests;
       P.stats->candidate_capacity = P.cand_capacity;
       P.stats->overflow = overflow ? 1 : 0;
     }
@@ -795,6 +826,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   for (unsigned long long i = i_first + (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kExactThreads) {
     const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
+    if (e.y == 0xFFFFFFFFu) continue;  // a slot its warp left unused
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
     const bool certain = (e.y & kCandCertain) != 0u;  // K1a found the ray >= certain_mm inside one slit on both sides
@@ -951,6 +983,7 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
   for (unsigned long long i = (unsigned long long)blockIdx.x * kWeightThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kWeightThreads) {
     const uint2 e = P.cand[i];
+    if (e.y == 0xFFFFFFFFu) continue;  // a slot its warp left unused
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask);
     const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
@@ -1186,6 +1219,12 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
   const long long items = (long long)P.n_tiles * P.n_super;  // lattice kernel: warp-level items
   const long long ctas_wanted = lattice_kernel ? (items + kLatticeWarps - 1) / kLatticeWarps : items;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ctas_wanted, (long long)sms * occ));
+  if (interval_kernel) {
+    // every warp may leave most of two chunks unused: keep that below ~1/8 of the list
+    const unsigned long long warps = (unsigned long long)grid * kLatticeWarps;
+    const unsigned long long c = P.cand_capacity / (warps * 16ull);
+    P.cand_chunk = (int)std::max<unsigned long long>(32, std::min<unsigned long long>(2048, c / 32 * 32));
+  }
   if (g_timing_on) {
     timing_collect();
     cudaEventRecord(g_ev[0], stream);

@@ -157,10 +157,15 @@ class ChannelScene:
         r12 = np.zeros(12, np.float32)
         ivl = C.c_int32()
         port = np.zeros((Cp, 3, 4), np.float32)
-        _lib.check(self._lib.com_scene_interval_tables_host(C.byref(self.desc), C.c_void_p(r12.ctypes.data), C.byref(ivl),
-                                                            C.c_void_p(port.ctypes.data)), "com_scene_interval_tables_host")
+        edges = np.zeros((2, 8, 4), np.float32)
+        n_edges = np.zeros(2, np.int32)
+        coff = C.c_int32()
+        _lib.check(self._lib.com_scene_interval_tables_host(
+            C.byref(self.desc), C.c_void_p(r12.ctypes.data), C.byref(ivl), C.c_void_p(port.ctypes.data),
+            C.c_void_p(edges.ctypes.data), C.c_void_p(n_edges.ctypes.data), C.byref(coff)), "com_scene_interval_tables_host")
         return dict(det_forms=det, slit_forms=slit, rect_crys=rects[:4], rect_plasma=rects[4:], period=period.value,
                     det_inner=r12[:4], port_outer=r12[4:8], port_inner=r12[8:], interval_filter=bool(ivl.value), port_forms=port,
+                    slit_edges=[edges[0, :n_edges[0]], edges[1, :n_edges[1]]], certain_off=bool(coff.value),
                     inner_crys=cert[:4], inner_plasma=cert[4:8], certain_mm=float(cert[8]),
                     slit_filter=bool(flags[0]), same_w=bool(flags[1]), disabled=bool(flags[2]),
                     origin=np.array(list(self.desc.origin)))

@@ -183,9 +183,12 @@ int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9);
  * the port's bounding rectangle (band included) and of the port's certain rectangle, both in the port aperture's frame
  * (mm); *interval_filter = 1 when the geometry allows the interval form (periodic collimator with one shared normal,
  * disjoint slit rectangles, filter enabled, no COM_FILTER_NO_* flag); port_forms_out [Cp][3][4] floats: X', Y', W on
- * the port plane.  Any output pointer may be NULL. */
+ * the port plane; slit_edges_out [2][8][4] floats: per side (crystal, plasma) the edges of slit 0's polygon as
+ * (a, b, c + eps, c - certain_mm) with a x + b y + c >= 0 inside, n_slit_edges_out [2] how many are used; certain_off_out
+ * 1 when no ray is vouched for (extensions on).  Any output pointer may be NULL. */
 int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, int32_t* interval_filter,
-                                   float* port_forms_out);
+                                   float* port_forms_out, float* slit_edges_out, int32_t* n_slit_edges_out,
+                                   int32_t* certain_off_out);
 
 /* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
  * are tested one by one, simulation.py:344-369): whether the collimator was found periodic

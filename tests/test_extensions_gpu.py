@@ -50,7 +50,7 @@ def test_shipped_ecrh_shields_are_clear_of_the_beam(el, lo):
 
 @pytest.mark.parametrize("n_sides", [360, 0])
 def test_narrow_stops_against_the_oracle(n_sides):
-    """Stops narrowed to 24 mm do cut into the beam: per-voxel ray counts, weights and the number of stopped rays equal the
+    """Stops narrowed to 18 mm do cut into the beam: per-voxel ray counts, weights and the number of stopped rays equal the
     oracle's (regular 360-gon as the reference builds the shield; n_sides = 0 is a true circle and has no oracle hull)."""
     from co_monitor_b200.geometry.radiation_shield import ecrh_shields
     from oracle import extensions as ext
@@ -58,7 +58,7 @@ def test_narrow_stops_against_the_oracle(n_sides):
     from oracle import stage1 as o1
 
     el, lo, hi = "O", 131000, 131900
-    stops = [dict(s, radius=24.0, n_sides=n_sides) for s in ecrh_shields(el)]
+    stops = [dict(s, radius=18.0, n_sides=n_sides) for s in ecrh_shields(el)]
     mesh, scene = _setup(el, shields=stops)
     res = scene.visibility(lattice=mesh.lattice, begin=lo, end=hi)
     db = gs.load_db()
@@ -67,10 +67,10 @@ def test_narrow_stops_against_the_oracle(n_sides):
     if n_sides:
         verts = []
         for ch_sh in (("upper chamber", "1st shield"), ("upper chamber", "2nd shield")):
-            db2 = {"ECRH shield": {ch_sh[0]: {ch_sh[1]: dict(db["ECRH shield"][ch_sh[0]][ch_sh[1]], radius=24.0)}}}
+            db2 = {"ECRH shield": {ch_sh[0]: {ch_sh[1]: dict(db["ECRH shield"][ch_sh[0]][ch_sh[1]], radius=18.0)}}}
             verts.append(ext.shield_vertices(db2, *ch_sh))
         ref = ext.run_chunk_physical(osc, vox, verts)
-        assert ref.shield_blocked > 200 and ref.nrays.sum() > 200
+        assert ref.shield_blocked > 50 and ref.nrays.sum() > 200
         assert np.array_equal(res.nrays.cpu().numpy(), ref.nrays)
         np.testing.assert_allclose(res.weight.cpu().numpy(), ref.weight, rtol=1e-12, atol=1e-300)
         assert res.stats["shield_blocked_rays"] == ref.shield_blocked

@@ -83,11 +83,13 @@ def column_intervals(t, p0, dz, nz, n_slits, C):
         for j in range(j_lo, j_hi + 1):
             off = F(j) * T
             lo_j, hi_j = one(ka), one(kb)
-            args = (one(sq[c]),)
-            lo_j, hi_j = clip_ratio(lo_j, hi_j, *args, one(Xc0[c]), one(dXc[c]), one(Wc0[c]), one(dWc[c]), off + rc[0], off + rc[1])
-            lo_j, hi_j = clip_ratio(lo_j, hi_j, *args, one(Xp0[c]), one(dXp[c]), one(Wc0[c]), one(dWc[c]), off + rp[0], off + rp[1])
-            lo_j, hi_j = clip_ratio(lo_j, hi_j, *args, one(Yc0[c]), one(dYc[c]), one(Wc0[c]), one(dWc[c]), rc[2], rc[3])
-            lo_j, hi_j = clip_ratio(lo_j, hi_j, *args, one(Yp0[c]), one(dYp[c]), one(Wc0[c]), one(dWc[c]), rp[2], rp[3])
+            l2, h2 = one(li[c]), one(hi_i[c])
+            for side, (X0, Y0, dX, dY) in enumerate(((Xc0[c], Yc0[c], dXc[c], dYc[c]), (Xp0[c], Yp0[c], dXp[c], dYp[c]))):
+                for ea, eb, eo, ei in t["slit_edges"][side]:
+                    base0, based = F(ea * X0 + eb * Y0), F(ea * dX + eb * dY)
+                    co, cin = F(eo - ea * off), F(ei - ea * off)
+                    lo_j, hi_j = clip_halfline(lo_j, hi_j, one(sq[c] * (co * Wc0[c] + base0)), one(sq[c] * (co * dWc[c] + based)))
+                    l2, h2 = clip_halfline(l2, h2, one(sq[c] * (cin * Wc0[c] + base0)), one(sq[c] * (cin * dWc[c] + based)))
             if not lo_j[0] <= hi_j[0] + F(2e-3):
                 continue
             a = max(d_lo[c], int(np.ceil(lo_j[0] - F(1e-3))))
@@ -95,20 +97,15 @@ def column_intervals(t, p0, dz, nz, n_slits, C):
             if a > b:
                 continue
             ci_lo, ci_hi = 1, 0
-            l2, h2 = one(li[c]), one(hi_i[c])
-            l2, h2 = clip_ratio(l2, h2, *args, one(Xc0[c]), one(dXc[c]), one(Wc0[c]), one(dWc[c]), off + ic[0], off + ic[1])
-            l2, h2 = clip_ratio(l2, h2, *args, one(Xp0[c]), one(dXp[c]), one(Wc0[c]), one(dWc[c]), off + ip[0], off + ip[1])
-            if l2[0] <= h2[0]:
+            if l2[0] <= h2[0] and not t["certain_off"]:
                 ci_lo = max(a, int(np.ceil(max(l2[0], F(-1e6)) + F(1e-3))))
                 ci_hi = min(b, int(np.floor(min(h2[0], F(1e6)) - F(1e-3))))
             if ci_lo <= ci_hi:
                 ok = True
                 for k in (F(ci_lo), F(ci_hi)):
-                    wc, wq = Wc0[c] + k * dWc[c], Wq0[c] + k * dWq[c]
+                    wq = Wq0[c] + k * dWq[c]
                     sp = F(-1) if wq < 0 else F(1)
-                    ok = ok and abs(wq) > 1e-3 and bool(ratio_inside(sq[c], Yc0[c] + k * dYc[c], wc, ic[2], ic[3])) and \
-                        bool(ratio_inside(sq[c], Yp0[c] + k * dYp[c], wc, ip[2], ip[3])) and \
-                        bool(ratio_inside(sp, Xq0[c] + k * dXq[c], wq, pi[0], pi[1])) and \
+                    ok = ok and abs(wq) > 1e-3 and bool(ratio_inside(sp, Xq0[c] + k * dXq[c], wq, pi[0], pi[1])) and \
                         bool(ratio_inside(sp, Yq0[c] + k * dYq[c], wq, pi[2], pi[3]))
                 if not ok:
                     ci_lo, ci_hi = 1, 0
@@ -153,4 +150,4 @@ def test_intervals_cover_the_oracle_and_certain_rays_pass(el, spacing):
         emitted += int(cand.sum())
     assert accepted > 50
     assert emitted <= 1.3 * accepted + 50  # selective: few rays beyond the accepted ones
-    assert certain > (0.5 if spacing == 10 else 0.8) * accepted, (certain, accepted)
+    assert certain > (0.55 if spacing == 10 else 0.88) * accepted, (certain, accepted)
