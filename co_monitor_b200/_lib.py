@@ -129,7 +129,7 @@ class ComStats(C.Structure):
         ("near_band_rays", C.c_uint64),
         ("shield_blocked_rays", C.c_uint64),
         ("segment_rejected_rays", C.c_uint64),
-        ("reserved", C.c_uint64),
+        ("near_rounding_rays", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -60,6 +60,7 @@ struct K1Params {
   const uint16_t* reff_bin;
   double* hist_out;
   int n_bins;
+  unsigned long long magic_nz, magic_nx, magic_cpb;  // weight kernel: multipliers replacing divisions by nz, nx, cols per block
   int cand_chunk;         // column-interval kernel: slots a warp reserves at a time (the list then has invalid entries and
                           // counters[3] / [4] hold the numbers of certain / other candidates really written)
   int front_weight_only;  // 1: the front region of the list was produced by the column-interval kernel and is handled by
@@ -818,7 +819,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   __syncthreads();
 
   const int S = sc.n_slits;
-  unsigned int n_pass = 0, n_edge = 0, n_band = 0, n_vis = 0, n_shield = 0, n_seg = 0;
+  unsigned int n_pass = 0, n_edge = 0, n_band = 0, n_vis = 0, n_shield = 0, n_seg = 0, n_round = 0;
   const double kNear = sc.near_edge_mm, kBand = sc.near_band_mm;
   const bool seg_check = (sc.physics_flags & COM_PHYS_SEGMENT_CHECK) != 0;
   // FP32 edge distances decide beyond this; twice the near-edge radii so that the near-edge counts stay exact
@@ -917,6 +918,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
       const double cosang = dot(v, rc) / (sqrt(vv) * sqrt(dot(rc, rc)));
       const double deg = acos(cosang) * (180.0 / 3.141592653589793);
       const double aoi = (180.0 - rint(deg * 100.0) / 100.0) / 2.0;
+      if (fabs(fabs(deg * 100.0 - rint(deg * 100.0)) - 0.5) < 1e-9) ++n_round;
       const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * (dist * dist));
       const double da = aoi - sc.aoi0;
       const double prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
@@ -945,11 +947,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   }
 
   // block-level stats
-  constexpr int kStats = 6;
+  constexpr int kStats = 7;
   __shared__ unsigned int s_acc[kStats];
   if (threadIdx.x < kStats) s_acc[threadIdx.x] = 0;
   __syncthreads();
-  unsigned int mine[kStats] = {n_pass, n_edge, n_vis, n_band, n_shield, n_seg};
+  unsigned int mine[kStats] = {n_pass, n_edge, n_vis, n_band, n_shield, n_seg, n_round};
 #pragma unroll
   for (int q = 0; q < kStats; ++q) {
     unsigned int v = mine[q];
@@ -961,7 +963,8 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     unsigned long long* out[kStats] = {(unsigned long long*)&P.stats->passing_rays, (unsigned long long*)&P.stats->near_edge_rays,
                                        (unsigned long long*)&P.stats->visible_voxels, (unsigned long long*)&P.stats->near_band_rays,
                                        (unsigned long long*)&P.stats->shield_blocked_rays,
-                                       (unsigned long long*)&P.stats->segment_rejected_rays};
+                                       (unsigned long long*)&P.stats->segment_rejected_rays,
+                                       (unsigned long long*)&P.stats->near_rounding_rays};
     for (int q = 0; q < kStats; ++q)
       if (s_acc[q]) atomicAdd(out[q], (unsigned long long)s_acc[q]);
   }
@@ -974,29 +977,51 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
 // take.
 constexpr int kWeightThreads = 256;
 
+// n / d for 32-bit n by one 64-bit high multiply: m = floor((2^64 - 1) / d) + 1 (exact for every n < 2^32, d >= 2)
+__device__ __forceinline__ unsigned int fast_div(unsigned int n, unsigned long long m, unsigned int d) {
+  return d == 1u ? n : (unsigned int)__umul64hi((unsigned long long)n, m);
+}
+
 __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_constant__ K1Params P) {
   const DeviceScene& sc = P.sc;
+  const ComLattice& L = P.vox.lat;
   const unsigned long long total = P.counters[0] + P.counters[2];
   const unsigned long long n = total > P.cand_capacity ? 0ull : P.counters[0];  // overflow: the exact kernel reports it
-  unsigned int n_pass = 0, n_vis = 0;
+  unsigned int n_pass = 0, n_vis = 0, n_round = 0;
   const double* __restrict__ table = sc.refl_table;
+  const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx, cpb = L.shard_cols_per_block > 0 ? (unsigned int)L.shard_cols_per_block : 1u;
+  const bool sharded = L.shard_count > 1 && L.shard_cols_per_block > 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * kWeightThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kWeightThreads) {
     const uint2 e = P.cand[i];
     if (e.y == 0xFFFFFFFFu) continue;  // a slot its warp left unused
-    const long long vloc = e.x;
+    const unsigned int vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask);
-    const D3 p = voxel_position(P.vox, P.vox_begin + vloc);
+    // voxel position (lattice.cuh: lattice_point), the index arithmetic by multiplication
+    const unsigned int f = (unsigned int)P.vox_begin + vloc;
+    unsigned int col = fast_div(f, P.magic_nz, nz);
+    const unsigned int iz = f - col * nz;
+    if (sharded) {
+      const unsigned int lb = fast_div(col, P.magic_cpb, cpb);
+      col = (lb * (unsigned int)L.shard_count + (unsigned int)L.shard_index) * cpb + (col - lb * cpb);
+    }
+    const unsigned int iy = fast_div(col, P.magic_nx, nx), ix = col - iy * nx;
+    const D3 p = lattice_point(L, ix, iy, iz);
     const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
+    // The reference forms plasma = c - d, crystal = p + d, reflected = c + r with d = c - p, r = d - 2 (d.n) n and then
+    // v = plasma - crystal (= -d), rc = reflected - crystal (= r), dist = |v|, cos = v.rc / (|v| |rc|)
+    // (simulation.py:309-321, 494-497, 516-520).  |r| = |d| and d.r = d.d - 2 (d.n)^2, so
+    //     dist^2 = d.d,   cos = 2 (d.n)^2 / (d.d) - 1
+    // - the same numbers to a few ulp (the exact kernel keeps the reference's own operation order for every ray it
+    // decides).  The rounded angle can differ from the reference's only when deg * 100 is within rounding distance of a
+    // half-integer; rays within 1e-9 of one are counted.
     const D3 d = c - p;
-    const D3 r = d - (2.0 * dot(d, nrm)) * nrm;
-    const D3 reflected = c + r, plasma = c - d, crystal = p + d;
-    const D3 v = plasma - crystal, rc = reflected - crystal;
-    const double vv = dot(v, v), dist = sqrt(vv);
-    const double cosang = dot(v, rc) / (sqrt(vv) * sqrt(dot(rc, rc)));
-    const double deg = acos(cosang) * (180.0 / 3.141592653589793);
-    const double m = rint(deg * 100.0);
-    const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * (dist * dist));
+    const double dd = dot(d, d), dn = dot(d, nrm);
+    const double cosang = 2.0 * (dn * dn) / dd - 1.0;
+    const double deg100 = acos(cosang) * (180.0 / 3.141592653589793) * 100.0;
+    const double m = rint(deg100);
+    if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
+    const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * dd);
     double prof;
     if (m >= 0.0 && m <= 18000.0) {
       prof = table[(int)m];
@@ -1017,24 +1042,28 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     if (P.rays_out) {
       const unsigned long long pos = atomicAdd(P.rays_count, 1ull);
       if ((long long)pos < P.rays_capacity)
-        P.rays_out[pos] = ComRayRecord{(P.vox_begin + vloc) * (long long)sc.n_crystal + ci, dist, (180.0 - m / 100.0) / 2.0, w};
+        P.rays_out[pos] = ComRayRecord{(P.vox_begin + (long long)vloc) * (long long)sc.n_crystal + ci, sqrt(dd),
+                                       (180.0 - m / 100.0) / 2.0, w};
     }
   }
-  __shared__ unsigned int s_acc[2];
-  if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+  __shared__ unsigned int s_acc[3];
+  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
   __syncthreads();
   for (int off = 16; off; off >>= 1) {
     n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);
     n_vis += __shfl_down_sync(0xffffffffu, n_vis, off);
+    n_round += __shfl_down_sync(0xffffffffu, n_round, off);
   }
   if ((threadIdx.x & 31) == 0) {
     if (n_pass) atomicAdd(&s_acc[0], n_pass);
     if (n_vis) atomicAdd(&s_acc[1], n_vis);
+    if (n_round) atomicAdd(&s_acc[2], n_round);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
     if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[1]);
+    if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[2]);
   }
 }
 
@@ -1249,6 +1278,9 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
         1, std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, (unsigned long long)sms * occ_x * 4ull));
     P.front_weight_only = (interval_kernel && P.sc.pix_out == nullptr) ? 1 : 0;
     if (P.front_weight_only) {
+      auto magic = [](long long d) { return d >= 2 ? ~0ull / (unsigned long long)d + 1ull : 0ull; };
+      P.magic_nz = magic(lattice_h->nz), P.magic_nx = magic(lattice_h->nx);
+      P.magic_cpb = magic(std::max<long long>(1, lattice_h->shard_cols_per_block));
       int occ_w = 0;
       COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, weight_kernel, kWeightThreads, 0));
       if (occ_w < 1) occ_w = 1;

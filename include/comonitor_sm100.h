@@ -233,7 +233,8 @@ typedef struct ComStats {
   uint64_t near_band_rays;  /* like near_edge_rays at the wider near_band_mm (default 1e-4 mm)                */
   uint64_t shield_blocked_rays;   /* rays through every reference aperture but stopped by an ECRH shield (extension) */
   uint64_t segment_rejected_rays; /* rays the infinite-line test accepts but COM_PHYS_SEGMENT_CHECK rejects (extension) */
-  uint64_t reserved;
+  uint64_t near_rounding_rays;    /* passing rays whose angle deg * 100 lies within 1e-9 of a half-integer: the only rays
+                                     whose round(deg, 2) (simulation.py:527) could differ from the reference's by one step */
 } ComStats;
 
 /* One passing ray (optional output): what the reference keeps per selected ray

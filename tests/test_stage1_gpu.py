@@ -431,7 +431,8 @@ def test_the_three_lattice_filters_decide_alike(sims, el):
         assert torch.equal(a.nrays, other.nrays)
         torch.testing.assert_close(a.weight, other.weight, rtol=1e-13, atol=0)
         assert other.stats["passing_rays"] == PASSING_RAYS[el]
-        assert abs(a.stats["candidates"] - other.stats["candidates"]) <= 0.002 * other.stats["candidates"] + 16
+        # the interval kernel follows the slit polygons edge by edge, the per-ray kernels their bounding rectangles
+        assert PASSING_RAYS[el] <= a.stats["candidates"] <= other.stats["candidates"] + 16
     assert a.stats["passing_rays"] == PASSING_RAYS[el]
     # the interval kernel vouches for most passing rays (the fp64 stage then only computes their weight)
     assert a.stats["certain_candidates"] > 0.8 * a.stats["passing_rays"]
