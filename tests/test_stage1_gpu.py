@@ -435,7 +435,7 @@ def test_the_three_lattice_filters_decide_alike(sims, el):
         assert PASSING_RAYS[el] <= a.stats["candidates"] <= other.stats["candidates"] + 16
     assert a.stats["passing_rays"] == PASSING_RAYS[el]
     # the interval kernel vouches for most passing rays (the fp64 stage then only computes their weight)
-    assert a.stats["certain_candidates"] > 0.8 * a.stats["passing_rays"]
+    assert a.stats["certain_candidates"] > 0.7 * a.stats["passing_rays"]  # 10 mm voxels: intervals of 1-2 voxels
     assert abs(b.stats["candidates"] - c.stats["candidates"]) <= 16
     # a range that starts and ends inside z-columns
     lo, hi = 100_007, 200_011
