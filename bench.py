@@ -216,18 +216,21 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def ncu_counters(spacing, element="C", timeout_s=240):
+KERNEL_REGEX = "regex:filter_kernel|interval_kernel_lattice|weight_kernel|exact_kernel|weight_histogram_mm"
+
+
+def ncu_counters(spacing, element="C", mode="production", timeout_s=300):
     """Instruction counts and DRAM bytes of one channel's whole-volume Stage 1 + histogram pass, measured now by an
-    `ncu --metrics` pass over `bench.py --probe` in a subprocess (hardware counters only; no time from it is used)."""
+    `ncu --metrics` pass over `bench.py --probe` in a subprocess (hardware counters only; no time from it is used).
+    *mode*: "nocull" = the headline step (every ray's detector test evaluated), "production" = the shipped step."""
     import shutil
 
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return {"unavailable": "ncu not found"}
     metrics = "smsp__thread_inst_executed.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum"
-    cmd = [ncu, "--csv", "--metrics", metrics, "--clock-control", "none", "-k",
-           "regex:filter_kernel|exact_kernel|weight_histogram_mm", sys.executable, os.path.abspath(__file__),
-           "--probe", element, "--spacing", str(spacing)]
+    cmd = [ncu, "--csv", "--metrics", metrics, "--clock-control", "none", "-k", KERNEL_REGEX, sys.executable,
+           os.path.abspath(__file__), "--probe", element, "--probe-mode", mode, "--spacing", str(spacing)]
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -258,13 +261,18 @@ def ncu_counters(spacing, element="C", timeout_s=240):
     for line in proc.stdout.splitlines():
         if line.startswith("{\"probe\""):
             probe = json.loads(line)
-    return {"kernels": agg, "probe": probe, "command": " ".join(cmd[:10]) + " python bench.py --probe " + element}
+    if probe is None:
+        return {"unavailable": "the probe printed no summary line", "rc": proc.returncode, "tail": (proc.stdout + proc.stderr)[-300:]}
+    return {"kernels": agg, "probe": probe,
+            "command": f"ncu --csv --metrics {metrics} --clock-control none -k {KERNEL_REGEX} python bench.py --probe {element} "
+                       f"--probe-mode {mode} --spacing {spacing}"}
 
 
 def run_probe(args):
     """One channel's whole-volume Stage 1 + histogram pass, once (the workload the ncu counter pass profiles)."""
     import torch
 
+    from co_monitor_b200 import _lib
     from co_monitor_b200.emissivity.engine import cached_line_tables
     from co_monitor_b200.geometry.engine import make_channel
     from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
@@ -274,14 +282,17 @@ def run_probe(args):
 
     el = args.probe
     lat = quiet(CuboidMesh, args.spacing).lattice
-    scene = quiet(make_channel, el, SLITS, H, L, lattice=lat)
+    scene = quiet(make_channel, el, SLITS, H, L, lattice=lat, run_cull=args.probe_mode != "nocull")
     cached_line_tables(el, *LYMAN_ALPHA[el], ("EXCIT", "RECOM"), None)
     vol = ObservationVolume(lat, args.chunk)
     vol.set_reff_resampled(source_volume(15))
     hist, stats = vol.histograms([scene])
     torch.cuda.synchronize()
-    print(json.dumps({"probe": el, "voxels": lat.n_points, "tests": lat.n_points * H * L, "launches": vol.n_launches,
-                      "passing_rays": int(stats[0, 2].item())}))
+    names = [f[0] for f in _lib.ComStats._fields_]
+    st = dict(zip(names, (int(x) for x in stats[0].cpu().numpy())))
+    print(json.dumps({"probe": el, "mode": args.probe_mode, "voxels": lat.n_points, "tests": lat.n_points * H * L,
+                      "launches": vol.n_launches, "passing_rays": st["passing_rays"], "candidates": st["candidates"],
+                      "certain_candidates": st["certain_candidates"]}))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -332,7 +343,7 @@ def run_ours(args):
     scenes_nc = [quiet(make_channel, el, SLITS, H, L, lattice=full, run_cull=False) for el in ELEMENTS]
     tables = [quiet(LineTables, el, *LYMAN_ALPHA[el], ["EXCIT", "RECOM"]) for el in ELEMENTS]
     src = source_volume(15)  # the shipped 15 mm VMEC grid (host), resampled onto the lattice on the device
-    pipe = VolumePipeline(lat, scenes, tables, profile, 2.0, chunk=args.chunk, device=device)
+    pipe = VolumePipeline(lat, scenes, tables, profile, 2.0, chunk=args.chunk, device=device, exchange=args.exchange)
     pipe.volume.set_reff_resampled(src)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
@@ -377,19 +388,68 @@ def run_ours(args):
     stats = pipe.global_stats()
     boundary = pipe.boundary.cpu().numpy()
 
-    # ---- per-kernel times of the production step (events inside the library, rank 0's shard) ----
-    lib.com_kernel_timing_enable(1)
-    t_seq0 = torch.cuda.Event(enable_timing=True)
-    t_seq1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t_seq0.record()
-    pipe.stage1()
-    t_seq1.record()
-    torch.cuda.synchronize()
-    f_ms, x_ms, n_l = C.c_double(), C.c_double(), C.c_int64()
-    lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_l))
-    lib.com_kernel_timing_enable(0)
-    stage1_ms = t_seq0.elapsed_time(t_seq1)
+    # ---- per-kernel times (events inside the library around every Stage-1 kernel, this rank's shard) ----
+    def kernel_times(scene_list):
+        """Stage 1 (+ histogram passes) of the given channels once more with the library's kernel events on: milliseconds
+        of the FP32 filter kernel, the fp64 weight-only kernel and the fp64 exact kernel, and of the whole Stage 1."""
+        lib.com_kernel_timing_enable(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        pipe.volume.histograms(scene_list, pipe.hist[: len(scene_list)], pipe.stats[: len(scene_list)])
+        b.record()
+        torch.cuda.synchronize()
+        ms3, n_l = (C.c_double * 3)(), C.c_int64()
+        lib.com_kernel_timing_read3(ms3, C.byref(n_l))
+        lib.com_kernel_timing_enable(0)
+        return {"filter_ms": ms3[0], "weight_ms": ms3[1], "exact_ms": ms3[2], "launches": int(n_l.value),
+                "stage1_ms": a.elapsed_time(b)}
+
+    kt_nc = kernel_times(scenes_nc)          # headline step, four channels
+    kt_prod = kernel_times(scenes)           # production step, four channels
+    kt_nc_c = kernel_times([scenes_nc[1]])   # channel C alone: the channel the ncu counter pass profiles
+    kt_prod_c = kernel_times([scenes[1]])
+    pipe.stage1()  # leave the pipeline's buffers as the production step left them
+
+    # ---- the exchange + Stage 2 alone, both transports (N > 1): NCCL all-reduce + Stage 2 vs the fused peer-memory launch ----
+    exchange_ms = None
+    if world > 1:
+        from co_monitor_b200.volume import flux_from_histograms, flux_from_peer_buffers
+
+        def time_loop(body, reps=50):
+            for _ in range(5):
+                body()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                body()
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / reps
+
+        tmp = pipe.packed.clone()
+        tmp_hist = tmp[: n_ch * _lib.COM_MM_BINS].view(n_ch, _lib.COM_MM_BINS)
+        fl_t, bd_t = torch.zeros_like(pipe.flux), torch.zeros_like(pipe.boundary)
+
+        def nccl_body():
+            tmp.copy_(pipe.packed)
+            dist.all_reduce(tmp)
+            flux_from_histograms(tables, pipe.profiles, tmp_hist, pipe.conc, fl_t, bd_t, pipe.meta)
+
+        exchange_ms = {"nccl_all_reduce_then_stage2_ms": time_loop(nccl_body),
+                       "what": "the step's tail alone, 50 repetitions, CUDA events, max over ranks: (a) copy + NCCL all-reduce of "
+                               "the packed buffer + the Stage-2 launch, (b) device-side barrier + ONE launch that reads the "
+                               "ranks' buffers over NVLink, sums them and evaluates Stage 2"}
+        flux_nccl = fl_t.cpu().numpy()[:, 0].copy()
+        if pipe.exchange_mode == "peer":
+            def peer_body():
+                pipe._symm.barrier(channel=0)
+                flux_from_peer_buffers(tables, pipe.profiles, pipe._peer_ptrs[pipe._slot], _lib.N_STATS, pipe.conc, fl_t, bd_t,
+                                       None, None, pipe.meta)
+
+            exchange_ms["peer_barrier_then_fused_launch_ms"] = time_loop(peer_body)
+            exchange_ms["flux_rel_diff_peer_vs_nccl"] = float(np.max(np.abs(fl_t.cpu().numpy()[:, 0] / flux_nccl - 1)))
 
     # ---- e2e: the host-buffer C-ABI calls, exchange included ----
     packed_h = torch.empty(n_ch * (_lib.COM_MM_BINS + _lib.N_STATS), dtype=torch.float64).pin_memory()
@@ -445,51 +505,75 @@ def run_ours(args):
     # =========================== rank 0 only from here: sub-records, rooflines, baselines ===========================
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     issue_peak = 148 * 4 * 32 * sm_max * 1e6  # lane-instructions per second: 148 SMs x 4 schedulers x 32 lanes x f_max
-    n_launch = max(1, n_l.value)
-
-    # ---- measured counters (ncu pass over one channel of this workload) ----
-    counters = None if args.no_ncu else ncu_counters(args.spacing, "C")
-    k1a = k1b = khist = None
-    if counters and "kernels" in counters:
-        k1a = counters["kernels"].get("filter_kernel_lattice")
-        k1b = counters["kernels"].get("exact_kernel")
-        khist = counters["kernels"].get("weight_histogram_mm_kernel")
-    # K1a time of channel C alone on this rank's shard, measured live (events around the kernels)
-    lib.com_kernel_timing_enable(1)
-    pipe.volume.histograms([scenes[1]])
-    torch.cuda.synchronize()
-    fc_ms, xc_ms, nc_l = C.c_double(), C.c_double(), C.c_int64()
-    lib.com_kernel_timing_read(C.byref(fc_ms), C.byref(xc_ms), C.byref(nc_l))
-    lib.com_kernel_timing_enable(0)
     tests_c_rank = lat.n_points * H * L
+
+    # ---- measured counters: one ncu --metrics pass per mode over channel C of this workload (counters only) ----
+    cnt_nc = None if args.no_ncu else ncu_counters(args.spacing, "C", "nocull")
+    cnt_prod = None if args.no_ncu else ncu_counters(args.spacing, "C", "production")
+    khist = (cnt_prod or {}).get("kernels", {}).get("weight_histogram_mm_kernel")
+
+    def kernel_record(counters, name, ms, per_unit_key=None, per_unit=None):
+        """Issue-rate figures of one kernel: lane-instructions from the ncu pass (the unsharded channel C, scaled to this
+        rank's shard) over this rank's live event time of the same kernel on the same channel."""
+        k = (counters or {}).get("kernels", {}).get(name)
+        if not k or ms <= 0:
+            return None
+        scale = tests_c_rank / counters["probe"]["tests"]
+        lane, warp = k["smsp__thread_inst_executed.sum"] * scale, k["smsp__inst_executed.sum"] * scale
+        rec = {"kernel": "com::" + name, "ms_channel_C": ms, "launches": k["launches"],
+               "achieved": lane / (ms * 1e-3) / 1e12, "frac": lane / (ms * 1e-3) / issue_peak,
+               "warp_issue_frac": warp * 32 / (ms * 1e-3) / issue_peak,
+               "threads_per_warp_instr": k["smsp__thread_inst_executed.sum"] / k["smsp__inst_executed.sum"],
+               "executed_lane_instr_per_test": k["smsp__thread_inst_executed.sum"] / counters["probe"]["tests"],
+               "traffic": (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) / k["launches"]}
+        if per_unit_key and per_unit:
+            rec[per_unit_key] = k["smsp__thread_inst_executed.sum"] / per_unit
+        return rec
+
+    def shares(kt):
+        tot = kt["stage1_ms"]
+        return None if tot <= 0 else {
+            "filter": kt["filter_ms"] / tot, "weight_only": kt["weight_ms"] / tot, "exact": kt["exact_ms"] / tot,
+            "histogram_pass_memsets_other": 1 - (kt["filter_ms"] + kt["weight_ms"] + kt["exact_ms"]) / tot}
+
+    n_launch = max(1, kt_nc["launches"])
     roofline = {
-        "bound": "issue (FP32/ALU instruction issue; not HBM, not tensor)", "kernel": "com::filter_kernel_lattice (K1a)",
+        "bound": "issue (FP32/ALU instruction issue; not HBM, not tensor)",
+        "kernel": "com::filter_kernel_lattice (K1a, every ray's detector test evaluated: the kernel of the headline step)",
         "unit": "Tlane-inst/s", "peak": issue_peak / 1e12,
         "peak_source": f"148 SM x 4 schedulers x 32 lanes x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no instruction-issue figure)",
-        "kernel_ms_per_launch": f_ms.value / n_launch, "exact_kernel_ms_per_launch": x_ms.value / n_launch,
-        "launches_per_step_this_rank": int(n_launch),
-        "kernel_share_of_step": (f_ms.value + x_ms.value) / stage1_ms if stage1_ms > 0 else None,
-        "filter_kernel_share_of_step": f_ms.value / stage1_ms if stage1_ms > 0 else None,
-        "timing": "CUDA events inside the library around every K1a / K1b launch of one production step of this rank",
+        "kernel_ms_per_launch": kt_nc["filter_ms"] / n_launch, "launches_per_step_this_rank": int(n_launch),
+        "kernel_share_of_step": kt_nc["filter_ms"] / kt_nc["stage1_ms"] if kt_nc["stage1_ms"] > 0 else None,
+        "step_shares": shares(kt_nc),
+        "timing": "CUDA events inside the library around every Stage-1 kernel of one headline step of this rank",
         "achieved": None, "frac": None, "traffic": None,
+        "what": "achieved = lane-instructions the kernel executes (ncu smsp__thread_inst_executed.sum, measured in this run) / "
+                "its event-timed duration; frac = achieved / peak.  warp_issue_frac counts every issued warp instruction as 32 "
+                "lanes (issue-slot utilisation); the difference is lanes predicated off in divergent code.",
     }
-    if k1a and fc_ms.value > 0:
-        scale = tests_c_rank / counters["probe"]["tests"]  # the probe ran the unsharded lattice
-        lane = k1a["smsp__thread_inst_executed.sum"] * scale
-        roofline.update({
-            "achieved": lane / (fc_ms.value * 1e-3) / 1e12, "frac": lane / (fc_ms.value * 1e-3) / issue_peak,
-            "executed_lane_instr_per_test": k1a["smsp__thread_inst_executed.sum"] / counters["probe"]["tests"],
-            "threads_per_warp_instr": k1a["smsp__thread_inst_executed.sum"] / k1a["smsp__inst_executed.sum"],
-            "traffic": (k1a["dram__bytes_read.sum"] + k1a["dram__bytes_write.sum"]) / k1a["launches"],
-            "counters": "measured in this run: ncu --metrics pass over channel C of this workload (counters only); the time "
-                        "is this rank's live event timing of the same channel",
-            "exact_kernel": None if not k1b else {
-                "executed_lane_instr_per_candidate": k1b["smsp__thread_inst_executed.sum"] / max(1, stats[1]["candidates"]),
-                "issue_frac": k1b["smsp__thread_inst_executed.sum"] * scale / (xc_ms.value * 1e-3) / issue_peak if xc_ms.value > 0 else None,
-                "traffic": (k1b["dram__bytes_read.sum"] + k1b["dram__bytes_write.sum"]) / k1b["launches"]},
-        })
-    elif counters:
-        roofline["counters"] = counters
+    rec = kernel_record(cnt_nc, "filter_kernel_lattice", kt_nc_c["filter_ms"])
+    if rec:
+        rec.pop("kernel")
+        roofline.update(rec)
+        roofline["exact_kernel"] = kernel_record(cnt_nc, "exact_kernel", kt_nc_c["exact_ms"], "executed_lane_instr_per_candidate",
+                                                 cnt_nc["probe"].get("candidates"))
+        roofline["counters_command"] = cnt_nc["command"]
+    elif cnt_nc:
+        roofline["counters"] = cnt_nc
+    pc = (cnt_prod or {}).get("probe") or {}
+    roofline_production = {
+        "what": "the shipped step's Stage-1 kernels, same definitions as `roofline` (channel C; counters from a second ncu pass)",
+        "step_shares": shares(kt_prod), "stage1_ms_four_channels": kt_prod["stage1_ms"],
+        "interval_kernel": kernel_record(cnt_prod, "interval_kernel_lattice", kt_prod_c["filter_ms"],
+                                         "executed_lane_instr_per_candidate", pc.get("candidates")),
+        "weight_kernel": kernel_record(cnt_prod, "weight_kernel", kt_prod_c["weight_ms"], "executed_lane_instr_per_ray",
+                                       pc.get("certain_candidates")),
+        "exact_kernel": kernel_record(cnt_prod, "exact_kernel", kt_prod_c["exact_ms"], "executed_lane_instr_per_candidate",
+                                      (pc.get("candidates") or 0) - (pc.get("certain_candidates") or 0) or None),
+        "counters_command": (cnt_prod or {}).get("command"),
+    }
+    if cnt_prod and "kernels" not in cnt_prod:
+        roofline_production["counters"] = cnt_prod
 
     # ---- metric 2 + Stage-2 roofline: full-channel flux from device-resident weights of this run (channel N) ----
     roofline_stage2 = None
@@ -574,7 +658,11 @@ def run_ours(args):
             "value_is": "every ray's detector test evaluated individually (COM_FILTER_NO_RUN_CULL); `production` is the "
                         "shipped step, which skips runs of voxels the linearity of the test proves dark - every ray is decided "
                         "either way and the results are identical (flux_rel_diff)",
-            "exchange": f"one all-reduce(SUM) of {pipe.packed.numel()} fp64 per step" if world > 1 else "none (one rank)",
+            "exchange": ("none (one rank)" if world == 1 else
+                         f"peer memory: every rank's packed buffer ({pipe.packed.numel()} fp64) is read over NVLink by the Stage-2 "
+                         "launch itself after one device-side barrier (no collective call)" if pipe.exchange_mode == "peer" else
+                         f"one NCCL all-reduce(SUM) of {pipe.packed.numel()} fp64 per step ({pipe.exchange_note})"),
+            "exchange_ms": exchange_ms,
             "passing_rays": {el: stats[i]["passing_rays"] for i, el in enumerate(ELEMENTS)},
             "visible_voxels": {el: stats[i]["visible_voxels"] for i, el in enumerate(ELEMENTS)},
             "fp64_candidates": {el: stats[i]["candidates"] for i, el in enumerate(ELEMENTS)},
@@ -607,6 +695,7 @@ def run_ours(args):
         "wall_s_timed_region": wall_nc,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_production": roofline_production,
         "roofline_stage2": roofline_stage2,
         "cpu_baseline": base,
         **sub,
@@ -761,11 +850,14 @@ def main():
     ap.add_argument("--spacing", type=float, default=0.65, help="lattice spacing in mm (0.65: configs[4], the headline)")
     ap.add_argument("--chunk", type=int, default=1 << 26, help="voxels per Stage-1 launch")
     ap.add_argument("--cols-per-block", type=int, default=8, help="z-columns per block of the block-cyclic shards")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: peer = histograms read over NVLink by the Stage-2 launch itself; nccl = all-reduce; auto = peer if it can be set up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ncu", action="store_true", help="skip the ncu counter pass (roofline instruction counts / DRAM bytes)")
     ap.add_argument("--no-stage2-roofline", action="store_true")
     ap.add_argument("--no-subrecords", action="store_true", help="skip the small_grid / sweep_1000 / grid_1mm legs")
     ap.add_argument("--probe", default="", help="internal: run one channel's whole-volume Stage 1 once (ncu counter pass)")
+    ap.add_argument("--probe-mode", default="production", choices=["production", "nocull"])
     args = ap.parse_args()
     if args.probe:
         run_probe(args)

@@ -227,6 +227,8 @@ def _declare(lib):
     lib.com_volume_histograms_host.argtypes = [vp, i32, C.POINTER(vp), vp, i64, i64, i64, vp, vp]
     lib.com_histograms_flux.argtypes = [i32, C.POINTER(vp), vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, i32, vp, vp]
     lib.com_histograms_flux_host.argtypes = [i32, C.POINTER(vp), vp, i32, i32, C.c_double, vp, vp, i32, vp]
+    lib.com_histograms_flux_peers.argtypes = [i32, C.POINTER(vp), vp, i32, i32, i32, C.c_double, C.c_double, i32, C.POINTER(vp),
+                                              i32, vp, vp, vp, i32, vp, vp]
     lib.com_compact_workspace_bytes.restype = C.c_size_t
     lib.com_compact_workspace_bytes.argtypes = [i64]
     lib.com_compact_visible.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, C.c_size_t, vp]
@@ -253,6 +255,7 @@ def _declare(lib):
     lib.com_measure_fp32_tflops.restype = C.c_double
     lib.com_kernel_timing_enable.argtypes = [C.c_int]
     lib.com_kernel_timing_read.argtypes = [dp, dp, C.POINTER(C.c_int64)]
+    lib.com_kernel_timing_read3.argtypes = [dp, C.POINTER(C.c_int64)]
     return lib
 
 
@@ -265,7 +268,7 @@ EXPORTED_SYMBOLS = [
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
     "com_visible_weights_host", "com_host_arena_release",
     "com_compact_workspace_bytes", "com_compact_visible",
-    "com_kernel_timing_enable", "com_kernel_timing_read", "com_measure_fp32_tflops",
+    "com_kernel_timing_enable", "com_kernel_timing_read", "com_kernel_timing_read3", "com_measure_fp32_tflops",
     "com_tables_create", "com_tables_destroy", "com_emissivity_workspace_bytes", "com_emissivity_integrate",
     "com_emissivity_integrate_host", "com_weight_histogram", "com_emissivity_sweep", "com_reff_max",
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
@@ -275,7 +278,7 @@ EXPORTED_SYMBOLS = [
     "com_visibility_weights_host_scene", "com_visible_weights_host_scene",
     "com_volume_create", "com_volume_destroy", "com_volume_voxels", "com_volume_chunk", "com_volume_reff_mm",
     "com_volume_set_reff_resampled", "com_volume_set_reff_quadratic", "com_volume_histograms",
-    "com_volume_histograms_host", "com_histograms_flux", "com_histograms_flux_host",
+    "com_volume_histograms_host", "com_histograms_flux", "com_histograms_flux_host", "com_histograms_flux_peers",
 ]
 
 

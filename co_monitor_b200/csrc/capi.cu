@@ -18,6 +18,7 @@ size_t visibility_workspace_bytes(const DeviceScene&, long long, double);
 long long lattice_local_voxels(const ComLattice&);
 void kernel_timing_enable(int on);
 void kernel_timing_read(double*, double*, long long*);
+void kernel_timing_read3(double*, long long*);
 int host_call_wait(cudaStream_t s);  // blocking (non-spinning) wait for the stream, volume.cu
 }  // namespace com
 
@@ -588,6 +589,13 @@ int com_kernel_timing_enable(int on) {
 int com_kernel_timing_read(double* filter_ms, double* exact_ms, int64_t* launches) {
   long long n = 0;
   com::kernel_timing_read(filter_ms, exact_ms, &n);
+  if (launches) *launches = n;
+  return COM_OK;
+}
+
+int com_kernel_timing_read3(double* ms3, int64_t* launches) {
+  long long n = 0;
+  com::kernel_timing_read3(ms3, &n);
   if (launches) *launches = n;
   return COM_OK;
 }

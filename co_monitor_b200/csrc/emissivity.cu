@@ -451,10 +451,19 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams P) {
 constexpr int kMaxChannels = 8;
 constexpr int kFluxThreads = 1024;
 
+constexpr int kMaxPeers = 16;
+
 struct FluxParams {
   DevTables tab[kMaxChannels];
   const double* profiles;  // (n_slices, K, 3)
-  const double* hist_mm;   // (n_channels, kMmBins)
+  const double* hist_mm;   // (n_channels, kMmBins); unused when n_peers > 0
+  // The exchange fused into Stage 2 (n_peers > 0): rank r's packed buffer [n_channels x kMmBins | n_channels x
+  // n_counters] as mapped into this process (NVLink peer / symmetric memory).  The block sums the peers' bins in rank
+  // order - every rank gets bit-identical sums - into shared memory and carries on from there.
+  const double* peers[kMaxPeers];
+  int n_peers, n_channels, n_counters;
+  double* hist_sum_out;      // null, or (n_channels, kMmBins): the global histograms (written by the slice-0 blocks)
+  double* counters_sum_out;  // null, or (n_channels, n_counters)
   int K, n_slices, profile_sorted;
   double profile_reff_max, conc;
   double* flux_out;      // (n_channels, n_slices, n_trans + 1)
@@ -463,7 +472,7 @@ struct FluxParams {
 };
 
 __global__ void __launch_bounds__(kFluxThreads) histogram_flux_kernel(const __grid_constant__ FluxParams P) {
-  extern __shared__ double s_rows[];  // (K)
+  extern __shared__ double s_rows[];  // (K), then (kMmBins) summed bins when the peers are read here
   __shared__ int s_max;
   __shared__ double s_red[kFluxThreads / 32][kMaxTransitions + 1];
   const int ch = blockIdx.x, s = blockIdx.y;
@@ -473,6 +482,34 @@ __global__ void __launch_bounds__(kFluxThreads) histogram_flux_kernel(const __gr
   const double* prof = P.profiles + (size_t)s * P.K * 3;
   if (threadIdx.x == 0) s_max = -1;
   for (int k = threadIdx.x; k < P.K; k += kFluxThreads) s_rows[k] = 0.0;
+  if (P.n_peers > 0) {
+    double* s_hist = s_rows + P.K;
+    constexpr int kPer = kMmBins / kFluxThreads;  // bins per thread: all loads of a peer in flight together
+    double h[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) h[i] = 0.0;
+    for (int r = 0; r < P.n_peers; ++r) {
+      const double* src = P.peers[r] + (size_t)ch * kMmBins;
+      double v[kPer];
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) v[i] = __ldcg(src + threadIdx.x + i * kFluxThreads);
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) h[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int b = threadIdx.x + i * kFluxThreads;
+      s_hist[b] = h[i];
+      if (s == 0 && P.hist_sum_out) P.hist_sum_out[(size_t)ch * kMmBins + b] = h[i];
+    }
+    if (s == 0 && P.counters_sum_out && threadIdx.x < P.n_counters) {
+      double c = 0.0;
+      const size_t off = (size_t)P.n_channels * kMmBins + (size_t)ch * P.n_counters + threadIdx.x;
+      for (int r = 0; r < P.n_peers; ++r) c += __ldcg(P.peers[r] + off);
+      P.counters_sum_out[(size_t)ch * P.n_counters + threadIdx.x] = c;
+    }
+    hist_mm = s_hist;
+  }
   __syncthreads();
   int m = -1;
   for (int b = threadIdx.x; b < kMmBins; b += kFluxThreads)
@@ -832,6 +869,62 @@ int com_histograms_flux(int32_t n_channels, const ComTables* const* tables, cons
     COM_CUDA(cudaFuncSetAttribute(com::histogram_flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   com::histogram_flux_kernel<<<dim3(n_channels, n_slices), com::kFluxThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
   COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
+int com_histograms_flux_peers(int32_t n_channels, const ComTables* const* tables, const double* profiles,
+                              int32_t n_slices, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                              double concentration, int32_t n_peers, const double* const* peers_h, int32_t n_counters,
+                              double* hist_sum_out, double* counters_sum_out, double* flux_out, int32_t flux_stride,
+                              double* boundary_out, com_stream_t stream) {
+  if (n_channels < 1 || n_channels > com::kMaxChannels || !tables || !profiles || n_slices < 1 || K < 1 || n_peers < 1 ||
+      n_peers > com::kMaxPeers || !peers_h || n_counters < 0 || n_counters > com::kFluxThreads || !flux_out) {
+    com::set_error("com_histograms_flux_peers: bad arguments (1..%d channels, 1..%d peers)", com::kMaxChannels, com::kMaxPeers);
+    return COM_E_BADARG;
+  }
+  // many slices: sum the peers once (a one-slice launch that only keeps the sums), then sweep from the local copy
+  const bool two_phase = n_slices > 4;
+  if (two_phase && !hist_sum_out) {
+    com::set_error("com_histograms_flux_peers: more than 4 slices need hist_sum_out (the peers are summed once)");
+    return COM_E_BADARG;
+  }
+  com::FluxParams P{};
+  int n_out = 0;
+  for (int c = 0; c < n_channels; ++c) {
+    if (!tables[c]) {
+      com::set_error("com_histograms_flux_peers: null tables handle for channel %d", c);
+      return COM_E_BADARG;
+    }
+    P.tab[c] = tables[c]->dev;
+    n_out = std::max(n_out, tables[c]->n_trans + 1);
+  }
+  if (flux_stride < n_out) {
+    com::set_error("com_histograms_flux_peers: flux_stride %d < transitions + 1 = %d", flux_stride, n_out);
+    return COM_E_BADARG;
+  }
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peers_h[r]) {
+      com::set_error("com_histograms_flux_peers: null buffer for rank %d", r);
+      return COM_E_BADARG;
+    }
+    P.peers[r] = peers_h[r];
+  }
+  const size_t smem = sizeof(double) * ((size_t)K + com::kMmBins);
+  if (smem > 160 * 1024) {
+    com::set_error("com_histograms_flux_peers: at most %d profile rows", 160 * 1024 / 8 - com::kMmBins);
+    return COM_E_BADARG;
+  }
+  P.profiles = profiles, P.hist_mm = nullptr, P.K = K, P.n_slices = two_phase ? 1 : n_slices, P.profile_sorted = profile_sorted;
+  P.profile_reff_max = profile_reff_max, P.conc = concentration;
+  P.flux_out = flux_out, P.boundary_out = boundary_out, P.n_out = flux_stride;
+  P.n_peers = n_peers, P.n_channels = n_channels, P.n_counters = n_counters;
+  P.hist_sum_out = hist_sum_out, P.counters_sum_out = counters_sum_out;
+  COM_CUDA(cudaFuncSetAttribute(com::histogram_flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  com::histogram_flux_kernel<<<dim3(n_channels, P.n_slices), com::kFluxThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  COM_CUDA(cudaGetLastError());
+  if (two_phase)
+    return com_histograms_flux(n_channels, tables, profiles, n_slices, K, profile_sorted, profile_reff_max, concentration,
+                               hist_sum_out, flux_out, flux_stride, boundary_out, stream);
   return COM_OK;
 }
 

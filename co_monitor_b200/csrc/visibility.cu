@@ -1073,18 +1073,19 @@ static thread_local bool g_accumulate_stats = false;
 void visibility_accumulate_stats(bool on) { g_accumulate_stats = on; }
 
 static bool g_timing_on = false;
-static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
-static double g_ms_accum[2] = {0, 0};
+static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before K1a | after K1a | after K1w | after K1b
+static double g_ms_accum[3] = {0, 0, 0};                            // filter, weight-only, exact
 static long long g_ms_launches = 0;
 static bool g_ev_pending = false;
 
 static void timing_collect() {
   if (!g_ev_pending) return;
-  cudaEventSynchronize(g_ev[2]);
-  float a = 0, b = 0;
+  cudaEventSynchronize(g_ev[3]);
+  float a = 0, b = 0, c = 0;
   cudaEventElapsedTime(&a, g_ev[0], g_ev[1]);
   cudaEventElapsedTime(&b, g_ev[1], g_ev[2]);
-  g_ms_accum[0] += a, g_ms_accum[1] += b, ++g_ms_launches;
+  cudaEventElapsedTime(&c, g_ev[2], g_ev[3]);
+  g_ms_accum[0] += a, g_ms_accum[1] += b, g_ms_accum[2] += c, ++g_ms_launches;
   g_ev_pending = false;
 }
 
@@ -1093,14 +1094,20 @@ void kernel_timing_enable(int on) {
   g_timing_on = on != 0;
   if (g_timing_on && !g_ev[0])
     for (auto& e : g_ev) cudaEventCreate(&e);
-  g_ms_accum[0] = g_ms_accum[1] = 0;
+  g_ms_accum[0] = g_ms_accum[1] = g_ms_accum[2] = 0;
   g_ms_launches = 0;
 }
 
-void kernel_timing_read(double* filter_ms, double* exact_ms, long long* launches) {
+void kernel_timing_read(double* filter_ms, double* exact_ms, long long* launches) {  // exact_ms: both fp64 kernels
   timing_collect();
   if (filter_ms) *filter_ms = g_ms_accum[0];
-  if (exact_ms) *exact_ms = g_ms_accum[1];
+  if (exact_ms) *exact_ms = g_ms_accum[1] + g_ms_accum[2];
+  if (launches) *launches = g_ms_launches;
+}
+
+void kernel_timing_read3(double* ms3, long long* launches) {  // filter, weight-only, exact
+  timing_collect();
+  if (ms3) ms3[0] = g_ms_accum[0], ms3[1] = g_ms_accum[1], ms3[2] = g_ms_accum[2];
   if (launches) *launches = g_ms_launches;
 }
 
@@ -1288,11 +1295,12 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
           1, std::min<unsigned long long>((slots + kWeightThreads - 1) / kWeightThreads, (unsigned long long)sms * occ_w * 4ull));
       weight_kernel<<<wblocks, kWeightThreads, 0, stream>>>(P);
     }
+    if (g_timing_on) cudaEventRecord(g_ev[2], stream);
     exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
   }
   COM_CUDA(cudaGetLastError());
   if (g_timing_on) {
-    cudaEventRecord(g_ev[2], stream);
+    cudaEventRecord(g_ev[3], stream);
     g_ev_pending = true;
   }
 #undef COM_CUDA

@@ -181,6 +181,34 @@ def flux_from_histograms(tables, profiles, hist, concentration: float, flux=None
     return flux, boundary
 
 
+def flux_from_peer_buffers(tables, profiles, peer_ptrs, n_counters: int, concentration: float, flux, boundary, hist_sum=None,
+                           counters_sum=None, meta=None):
+    """The exchange fused into Stage 2 (``com_histograms_flux_peers``): *peer_ptrs* are the device addresses of every
+    rank's packed ``[n_channels * 4096 | n_channels * n_counters]`` float64 buffer as mapped into this process (peer /
+    symmetric memory; on one GPU any device buffers will do - that is how the kernel is tested).  The kernel sums them
+    in rank order and evaluates the flux; *hist_sum* / *counters_sum* receive the global sums.  Stream-ordered; the
+    caller orders the ranks (see ``VolumePipeline``)."""
+    import torch
+
+    lib = _lib.load()
+    dev = flux.device
+    n_ch = len(tables)
+    n_slices, K = int(profiles.shape[0]), int(profiles.shape[1])
+    if meta is None:
+        col = profiles[0, :, 0]
+        meta = (int(bool((col[1:] >= col[:-1]).all().item())), float(col.max().item()))
+    ptrs = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        rc = lib.com_histograms_flux_peers(
+            n_ch, _handles(tables), C.c_void_p(profiles.data_ptr()), n_slices, K, meta[0], meta[1], float(concentration),
+            len(peer_ptrs), ptrs, int(n_counters), C.c_void_p(hist_sum.data_ptr()) if hist_sum is not None else None,
+            C.c_void_p(counters_sum.data_ptr()) if counters_sum is not None else None, C.c_void_p(flux.data_ptr()),
+            int(flux.shape[-1]), C.c_void_p(boundary.data_ptr()) if boundary is not None else None,
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "com_histograms_flux_peers")
+    return flux, boundary
+
+
 def flux_from_histograms_host(tables, profiles: np.ndarray, hist: np.ndarray, concentration: float, device=None):
     """Host-buffer form of ``flux_from_histograms``: host arrays in, ``(flux (n_channels, n_slices, T+1), boundary)`` out."""
     import torch
@@ -206,11 +234,23 @@ class VolumePipeline:
     """Stage 1 -> exchange -> Stage 2 of one rank's shard, device-resident and free of host synchronisation.
 
     ``packed`` is the single buffer the ranks exchange: ``[n_channels * 4096 histogram bins | n_channels * N_STATS
-    counters]`` as float64 (counts < 2^53 are exact).  ``step()`` enqueues everything on the current stream."""
+    counters]`` as float64 (counts < 2^53 are exact).  ``step()`` enqueues everything on the current stream.
+
+    *exchange* (only matters with more than one rank):
+
+    ``"nccl"``  one ``all_reduce(SUM)`` of ``packed`` (NCCL), then Stage 2 from the reduced histograms;
+    ``"peer"``  ``packed`` lives in symmetric memory (``torch.distributed._symmetric_memory``: every rank's buffer is
+                mapped into every process of the box over NVLink); after a device-side barrier on the stream the Stage-2
+                kernel itself reads the peers' buffers, sums them in rank order and evaluates the flux - one launch, no
+                collective call, bit-identical results on every rank.  Two buffers alternate between steps so that one
+                barrier per step is enough (a rank can only be one step ahead of a peer that is still reading);
+    ``"auto"``  ``"peer"`` when symmetric memory can be set up, else ``"nccl"`` (``exchange_mode`` /
+                ``exchange_note`` say which and why)."""
 
     def __init__(self, lattice, scenes, tables, profile: np.ndarray, concentration_percent: float = 2.0, chunk: int = 1 << 26,
-                 candidate_fraction: float = 0.0, device=None, group=None):
+                 candidate_fraction: float = 0.0, device=None, group=None, exchange: str = "nccl"):
         import torch
+        import torch.distributed as dist
 
         self.volume = ObservationVolume(lattice, chunk, candidate_fraction, device)
         dev = self.volume.device
@@ -223,39 +263,85 @@ class VolumePipeline:
             prof = prof[None]
         self.meta = _profile_meta(prof)
         self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        n_packed = n_ch * (_lib.COM_MM_BINS + _lib.N_STATS)
+        self.exchange_mode, self.exchange_note, self._symm, self._peer_ptrs, self._slot = "none", "one rank", None, None, 0
+        if self.world > 1:
+            self.exchange_mode, self.exchange_note = "nccl", "requested"
+            if exchange in ("peer", "auto"):
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+
+                    with torch.cuda.device(dev):
+                        buf = symm_mem.empty(2 * n_packed, dtype=torch.float64, device=dev)
+                        buf.zero_()
+                        self._symm = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                    self._symm_buf = buf
+                    base = [int(p) for p in self._symm.buffer_ptrs]
+                    self._peer_ptrs = [[b + slot * n_packed * 8 for b in base] for slot in (0, 1)]
+                    self.exchange_mode, self.exchange_note = "peer", "symmetric memory over NVLink, reduction fused into Stage 2"
+                except Exception as exc:  # noqa: BLE001 - any failure of the optional transport falls back to NCCL, loudly
+                    if exchange == "peer":
+                        raise
+                    self.exchange_note = f"symmetric memory unavailable ({type(exc).__name__}: {str(exc)[:120]})"
         with torch.cuda.device(dev):
             self.profiles = torch.from_numpy(prof.copy()).to(dev)
-            self.packed = torch.zeros(n_ch * (_lib.COM_MM_BINS + _lib.N_STATS), dtype=torch.float64, device=dev)
-            self.hist = self.packed[: n_ch * _lib.COM_MM_BINS].view(n_ch, _lib.COM_MM_BINS)
-            self.counters = self.packed[n_ch * _lib.COM_MM_BINS:].view(n_ch, _lib.N_STATS)
+            if self.exchange_mode == "peer":
+                self._packed2 = [self._symm_buf[:n_packed], self._symm_buf[n_packed:]]
+                self.global_packed = torch.zeros(n_packed, dtype=torch.float64, device=dev)
+            else:
+                self._packed2 = [torch.zeros(n_packed, dtype=torch.float64, device=dev)]
+                self.global_packed = self._packed2[0]  # the all-reduce is in place
+            self._bind(0)
             self.stats = torch.zeros((n_ch, _lib.N_STATS), dtype=torch.int64, device=dev)
             self.flux = torch.zeros((n_ch, prof.shape[0], max(t.n_out for t in self.tables)), dtype=torch.float64, device=dev)
             self.boundary = torch.zeros(n_ch, dtype=torch.float64, device=dev)
+
+    def _bind(self, slot: int):
+        n_ch = self.n_channels
+        self._slot = slot
+        self.packed = self._packed2[slot]
+        self.hist = self.packed[: n_ch * _lib.COM_MM_BINS].view(n_ch, _lib.COM_MM_BINS)
+        self.counters = self.packed[n_ch * _lib.COM_MM_BINS:].view(n_ch, _lib.N_STATS)
+        g = self.global_packed
+        self.global_hist = g[: n_ch * _lib.COM_MM_BINS].view(n_ch, _lib.COM_MM_BINS)
+        self.global_counters = g[n_ch * _lib.COM_MM_BINS:].view(n_ch, _lib.N_STATS)
 
     def stage1(self):
         self.volume.histograms(self.scenes, self.hist, self.stats)
         self.counters.copy_(self.stats)  # int64 -> float64, exact below 2^53
 
     def exchange(self):
-        """The single exchange of the path: one all-reduce(SUM) of the packed buffer (NCCL over NVLink)."""
+        """NCCL form of the path's single exchange: one all-reduce(SUM) of the packed buffer."""
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self.exchange_mode == "nccl":
             dist.all_reduce(self.packed, group=self.group)
 
     def stage2(self):
-        flux_from_histograms(self.tables, self.profiles, self.hist, self.conc, self.flux, self.boundary, self.meta)
+        flux_from_histograms(self.tables, self.profiles, self.global_hist, self.conc, self.flux, self.boundary, self.meta)
+
+    def exchange_stage2_fused(self):
+        """Peer form: barrier on the stream, then ONE launch that reads every rank's buffer over NVLink, reduces and
+        evaluates; the next step fills the other buffer."""
+        self._symm.barrier(channel=0)
+        flux_from_peer_buffers(self.tables, self.profiles, self._peer_ptrs[self._slot], _lib.N_STATS, self.conc, self.flux,
+                               self.boundary, self.global_hist, self.global_counters, self.meta)
+        self._bind(1 - self._slot)
 
     def step(self):
         self.stage1()
-        self.exchange()
-        self.stage2()
+        if self.exchange_mode == "peer":
+            self.exchange_stage2_fused()
+        else:
+            self.exchange()
+            self.stage2()
         return self.flux
 
     def global_stats(self) -> list[dict]:
-        """Counters summed over the ranks (after ``exchange``); ``candidate_capacity`` and ``overflow`` are sums too -
+        """Counters summed over the ranks (after the exchange); ``candidate_capacity`` and ``overflow`` are sums too -
         overflow != 0 means some launch of some rank overflowed."""
-        raw = self.counters.cpu().numpy().round().astype(np.uint64)
+        raw = self.global_counters.cpu().numpy().round().astype(np.uint64)
         return _stats_dicts(raw)
 
     def close(self):

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define COM_ABI_VERSION 3
+#define COM_ABI_VERSION 4
 
 #define COM_OK 0
 #define COM_E_BADARG (-1)   /* null pointer, bad size, inconsistent description            */
@@ -481,6 +481,22 @@ int com_histograms_flux(int32_t n_channels, const ComTables* const* tables, cons
 int com_histograms_flux_host(int32_t n_channels, const ComTables* const* tables, const double* profiles_h,
                              int32_t n_slices, int32_t K, double concentration, const double* hist_mm_h,
                              double* flux_out_h, int32_t flux_stride, double* boundary_out_h);
+/* The path's single exchange FUSED into Stage 2 (N > 1 ranks on one NVLink/NVSwitch box; no reference counterpart - the
+ * reference is one process): instead of all-reducing the histograms and then calling com_histograms_flux, every rank
+ * keeps its packed buffer [n_channels x 4096 bins | n_channels x n_counters], fp64, in memory its peers can read
+ * (CUDA peer / symmetric memory) and the Stage-2 kernel itself loads the n_peers buffers over NVLink, sums them in rank
+ * order (bit-identical sums on every rank) in shared memory and carries on as com_histograms_flux does.
+ * peers_h: HOST array of n_peers DEVICE pointers (rank r's buffer as mapped into this process; entry `own rank` is the
+ * local one).  hist_sum_out (n_channels, 4096) / counters_sum_out (n_channels, n_counters): nullable, the global sums
+ * (hist_sum_out is required for more than 4 slices: the peers are then summed once and the sweep runs from the copy).
+ * The CALLER orders the ranks: every rank's buffer must be complete and visible before this launch reads it, and must
+ * not be overwritten until every peer's launch has finished (a device-side barrier on the stream before the call and
+ * double buffering - see co_monitor_b200/volume.py). */
+int com_histograms_flux_peers(int32_t n_channels, const ComTables* const* tables, const double* profiles,
+                              int32_t n_slices, int32_t K, int32_t profile_sorted, double profile_reff_max,
+                              double concentration, int32_t n_peers, const double* const* peers_h, int32_t n_counters,
+                              double* hist_sum_out, double* counters_sum_out, double* flux_out, int32_t flux_stride,
+                              double* boundary_out, com_stream_t stream);
 
 /* ---- Reff provider ------------------------------------------------------------
  * Replaces the VMEC web-service step (co_monitor/geometry/reff_VMEC.py:85-136) and its 3-decimal file
@@ -511,10 +527,12 @@ int com_format_float_repr(double value, char* out, int32_t out_bytes);
 
 /* Measurement aid (no counterpart in the reference; not thread-safe, one stream at a time): when enabled, every com_visibility_weights call
  * records CUDA events around its two kernels on the launching stream; com_kernel_timing_read waits for the
- * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 exact kernel
+ * last call and returns the accumulated milliseconds of the FP32 filter kernel and of the fp64 kernels (weight-only + exact)
  * and the number of calls since the last enable. */
 int com_kernel_timing_enable(int on);
 int com_kernel_timing_read(double* filter_ms, double* exact_ms, int64_t* launches);
+/* the same with the fp64 stage split: ms3 = {filter kernel, weight-only kernel, exact kernel} */
+int com_kernel_timing_read3(double* ms3, int64_t* launches);
 
 /* FP32 FMA throughput of the current device measured by a register-only probe kernel, TFLOP/s (FMA = 2);
  * the denominator bench.py reports next to the nominal 148 x 128 x 2 x f_max.  < 0 on error. */

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--image", action="store_true", help="also accumulate the 0.1 mm detector image (config 3 extension)")
     ap.add_argument("--kernel-times", action="store_true", help="per-chunk times of the FP32 filter kernel and of the fp64 kernels")
     ap.add_argument("--only-chunks", default="", help="comma-separated chunk indices to run (default: all)")
+    ap.add_argument("--mode", default="production", choices=["production", "percull", "nocull"],
+                    help="production: column-interval filter + weight-only kernel; percull: per-ray filter with its run-level "
+                         "cull; nocull: every ray's detector test evaluated individually (the headline of bench.py)")
     a = ap.parse_args()
     import ctypes as C
 
@@ -49,7 +52,8 @@ def main():
     P = lat.n_points
     for el in a.elements:
         with contextlib.redirect_stdout(io.StringIO()):
-            scene = make_channel(el, a.slits, a.h, a.l, lattice=lat)
+            scene = make_channel(el, a.slits, a.h, a.l, lattice=lat, intervals=a.mode == "production",
+                                 run_cull=a.mode != "nocull")
         best = None
         img = scene.enable_detector_image(0.1) if a.image else None
         for _ in range(a.repeat):
@@ -73,10 +77,10 @@ def main():
                     raise SystemExit(f"candidate overflow in chunk [{lo},{hi}): {st}")
                 ms = e0.elapsed_time(e1)
                 if a.kernel_times:
-                    f_ms, x_ms, n_l = C.c_double(), C.c_double(), C.c_int64()
-                    lib.com_kernel_timing_read(C.byref(f_ms), C.byref(x_ms), C.byref(n_l))
+                    ms3, n_l = (C.c_double * 3)(), C.c_int64()
+                    lib.com_kernel_timing_read3(ms3, C.byref(n_l))
                     lib.com_kernel_timing_enable(0)
-                    ktimes.append([round(f_ms.value, 3), round(x_ms.value, 3), st["candidates"], st["passing_rays"]])
+                    ktimes.append([round(ms3[0], 3), round(ms3[1], 3), round(ms3[2], 3), st["candidates"], st["passing_rays"]])
                 ms_total += ms
                 chunks.append(round(ms, 3))
                 sum_w += float(plan.weight.sum().item())
@@ -86,12 +90,12 @@ def main():
                 near += st["near_edge_rays"]
                 del plan
             tests = P * a.h * a.l
-            rec = {"element": el, "spacing_mm": a.spacing, "lattice": [lat.nx, lat.ny, lat.nz], "voxels": P, "tests": tests,
+            rec = {"element": el, "mode": a.mode, "spacing_mm": a.spacing, "lattice": [lat.nx, lat.ny, lat.nz], "voxels": P, "tests": tests,
                    "ms": ms_total, "tests_per_s": tests / (ms_total * 1e-3), "visible_voxels": vis, "passing_rays": rays,
                    "fp64_candidates": cand, "near_edge_rays": near, "sum_w": sum_w,
                    "sum_w_times_voxel_volume_mm3": sum_w * a.spacing**3, "chunk_ms": chunks}
             if a.kernel_times:
-                rec["chunk_filter_ms_exact_ms_candidates_passing"] = ktimes
+                rec["chunk_filter_ms_weight_ms_exact_ms_candidates_passing"] = ktimes
             if img is not None:
                 rec["detector_image"] = {"shape": list(img.shape), "pixel_mm": 0.1, "sum": float(img.sum().item()),
                                          "max_pixel": float(img.max().item()),

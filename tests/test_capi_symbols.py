@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "binding list and header disagree"
     declared = int(re.search(r"#define COM_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "comonitor_sm100.h")).read()).group(1))
-    assert lib.com_abi_version() == declared == 3
+    assert lib.com_abi_version() == declared == 4
 
 
 def test_struct_layouts_match_the_header(lib):

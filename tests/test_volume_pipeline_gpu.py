@@ -95,6 +95,48 @@ def test_three_shards_sum_to_the_unsharded_result(setup, gold):
     check_against_reference(flux.cpu().numpy(), bnd.cpu().numpy(), stats, gold)
 
 
+def test_exchange_fused_into_stage2_three_rank_buffers(setup, gold):
+    """com_histograms_flux_peers: the kernel that replaces all-reduce + Stage 2 at N > 1 reads every rank's packed buffer
+    itself.  Here the three ranks' buffers live on one GPU (same kernel, same pointers-per-rank interface): reference
+    flux and counters, sums bit-identical to adding the buffers in rank order, and the many-slice (two-phase) form."""
+    import torch
+
+    from co_monitor_b200 import _lib
+    from co_monitor_b200.volume import VolumePipeline, _stats_dicts, flux_from_histograms, flux_from_peer_buffers
+
+    lat, scenes, tables, prof, src = setup
+    n_ch = len(ELEMENTS)
+    bufs = []
+    for r in range(3):
+        pipe = VolumePipeline(lat.shard(3, r, cols_per_block=8), scenes, tables, prof, 2.0, chunk=40_000)
+        pipe.volume.set_reff_resampled(src)
+        pipe.stage1()
+        bufs.append(pipe.packed.clone())
+        pipe.close()
+    profiles = torch.from_numpy(prof[None].copy()).cuda()
+    flux = torch.zeros((n_ch, 1, 3), dtype=torch.float64, device="cuda")
+    bnd = torch.zeros(n_ch, dtype=torch.float64, device="cuda")
+    hsum = torch.zeros((n_ch, _lib.COM_MM_BINS), dtype=torch.float64, device="cuda")
+    csum = torch.zeros((n_ch, _lib.N_STATS), dtype=torch.float64, device="cuda")
+    flux_from_peer_buffers(tables, profiles, [b.data_ptr() for b in bufs], _lib.N_STATS, 0.02, flux, bnd, hsum, csum)
+    stats = _stats_dicts(csum.cpu().numpy().round().astype(np.uint64))
+    check_against_reference(flux.cpu().numpy(), bnd.cpu().numpy(), stats, gold)
+    total = (bufs[0] + bufs[1]) + bufs[2]  # rank order
+    assert torch.equal(hsum.ravel(), total[: n_ch * _lib.COM_MM_BINS])
+    assert torch.equal(csum.ravel(), total[n_ch * _lib.COM_MM_BINS:])
+    # the fused launch equals all-reduce + com_histograms_flux bit for bit
+    f2, b2 = flux_from_histograms(tables, profiles, hsum, 0.02)
+    assert torch.equal(f2, flux) and torch.equal(b2, bnd)
+    # more than four slices: the peers are summed once, then the sweep runs from the local copy
+    profs = torch.from_numpy(np.stack([prof * [1, 1 + 0.1 * i, 1 - 0.05 * i] for i in range(6)])).cuda()
+    f6 = torch.zeros((n_ch, 6, 3), dtype=torch.float64, device="cuda")
+    flux_from_peer_buffers(tables, profs, [b.data_ptr() for b in bufs], _lib.N_STATS, 0.02, f6, bnd, hsum, None)
+    g6, _ = flux_from_histograms(tables, profs, hsum, 0.02)
+    assert torch.equal(f6, g6) and torch.equal(f6[:, 0], flux[:, 0])
+    with pytest.raises(_lib.ComonitorError):  # the two-phase form needs somewhere to keep the sums
+        flux_from_peer_buffers(tables, profs, [b.data_ptr() for b in bufs], _lib.N_STATS, 0.02, f6, bnd, None, None)
+
+
 def test_host_buffer_forms(setup, gold):
     """com_volume_histograms_host + com_histograms_flux_host: host arrays in and out, Reff source uploaded in the call."""
     from co_monitor_b200.volume import ObservationVolume, flux_from_histograms_host
