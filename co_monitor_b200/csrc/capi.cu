@@ -366,6 +366,19 @@ int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, i
   return COM_OK;
 }
 
+int com_scene_port_edges_host(const ComSceneDesc* desc_h, float* edges_out64, int32_t* n_edges_out) {
+  if (!desc_h || !edges_out64 || !n_edges_out) {
+    com::set_error("com_scene_port_edges_host: null argument");
+    return COM_E_BADARG;
+  }
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  std::memcpy(edges_out64, hs.dev.port_edge, sizeof(hs.dev.port_edge));
+  *n_edges_out = hs.dev.n_port_edge;
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

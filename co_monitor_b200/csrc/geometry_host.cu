@@ -411,6 +411,10 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
         dv.slit_edge[side][k] = make_float4((float)ap.edge[k][0], (float)ap.edge[k][1], (float)(ap.edge[k][2] + eps),
                                             (float)(ap.edge[k][2] - safe));
     }
+    dv.n_port_edge = (okq && port.n_edges <= 16) ? port.n_edges : 0;
+    for (int k = 0; k < dv.n_port_edge; ++k)
+      dv.port_edge[k] = make_float4((float)port.edge[k][0], (float)port.edge[k][1], (float)(port.edge[k][2] + eps),
+                                    (float)(port.edge[k][2] - safe));
     const bool few_edges = c0.n_edges <= 8 && p0.n_edges <= 8;
     const bool disjoint = S == 1 || (dv.rect_crys.xhi < dv.slit_period + dv.rect_crys.xlo &&
                                      dv.rect_plasma.xhi < dv.slit_period + dv.rect_plasma.xlo);

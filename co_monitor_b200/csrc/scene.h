@@ -75,6 +75,11 @@ struct DeviceScene {
   // .z = c + eps (outer: candidates), .w = c - certain_mm (inner: certain).  Slit j: x -> x - j * period.
   float4 slit_edge[2][8];
   int n_slit_edge[2];
+  // edges of the port polygon in its aperture frame, same layout (.w = c - certain_mm: a point inside all of them is at
+  // least certain_mm inside the polygon).  n_port_edge = 0 (more than 16 edges): the certain test falls back to the
+  // inner rectangle port_inner, which vouches for fewer rays.
+  float4 port_edge[16];
+  int n_port_edge;
   const float4* port_forms;      // [Cp][3]: X', Y', W on the port plane
   // reflectivity profile at every value the rounded angle can take: refl_table[m] = refl_max * exp(-(aoi - aoi0)^2 /
   // (2 sigma^2)) with aoi = (180 - m / 100) / 2, m = rint(deg * 100) in 0..18000 (simulation.py:520-531, 564-577)

@@ -96,6 +96,10 @@ constexpr unsigned int kCandCrystalMask = kCandCertainAll - 1u;
 
 // Returns -1 when the ray misses every slit (band included), else the index of the slit it goes through on both
 // sides, or kSlitUnknown when that is ambiguous / not evaluated.  The exact kernel tries the hinted slit first.
+__device__ __forceinline__ bool ratio_inside(float s, float n, float w, float lo_b, float hi_b) {
+  return s * fmaf(-lo_b, w, n) >= 0.f && s * fmaf(hi_b, w, -n) >= 0.f;
+}
+
 __device__ __forceinline__ int stage_b(const DeviceScene& sc, const float4 p, int cj) {
   if (!sc.slit_filter) return kSlitUnknown;  // non-periodic collimator: decided in fp64 only
   const float4* f = sc.slit_forms + 6 * cj;  // six forms of one crystal point are contiguous (96 B)
@@ -125,6 +129,27 @@ __device__ __forceinline__ int stage_b(const DeviceScene& sc, const float4 p, in
   inner = inner && code != kSlitUnknown && yc >= sc.inner_crys.ylo && yc <= sc.inner_crys.yhi &&
           yp >= sc.inner_plasma.ylo && yp <= sc.inner_plasma.yhi;
   return inner ? (code | kSlitCertain) : code;
+}
+
+// Detector (scaled frame of det_forms) and port (edge by edge, inner offsets) for a ray stage B found well inside its
+// slit: when both hold too, no aperture test of the fp64 stage can fail and only the weight is left.
+__device__ __forceinline__ bool certain_everywhere(const DeviceScene& sc, const float4 p, int cj) {
+  const int Cp = sc.n_crystal_padded;
+  const float xs = form(__ldg(&sc.det_forms[cj]), p), ys = form(__ldg(&sc.det_forms[Cp + cj]), p);
+  const float wd = form(__ldg(&sc.det_forms[2 * Cp + cj]), p);
+  const float sd = wd < 0.f ? -1.f : 1.f;
+  if (!(fabsf(wd) > 1e-3f && ratio_inside(sd, xs, wd, sc.det_inner.xlo, sc.det_inner.xhi) &&
+        ratio_inside(sd, ys, wd, sc.det_inner.ylo, sc.det_inner.yhi)))
+    return false;
+  const float4* pf = sc.port_forms + 3 * cj;
+  const float Xq = form(__ldg(pf), p), Yq = form(__ldg(pf + 1), p), Wq = form(__ldg(pf + 2), p);
+  const float sp = Wq < 0.f ? -1.f : 1.f;
+  float m = fabsf(Wq) - 1e-3f;  // > 0 required
+  for (int q = 0; q < sc.n_port_edge; ++q) {
+    const float4 ed = sc.port_edge[q];
+    m = fminf(m, sp * fmaf(ed.x, Xq, fmaf(ed.y, Yq, ed.w * Wq)));
+  }
+  return m >= 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -265,6 +290,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   __shared__ int2 s_seg[kLatticeWarps][kSegsPerItemMax];     // (first launch-local voxel, length)
   __shared__ unsigned int s_queue[kLatticeWarps][kQueueCap];
   __shared__ uint2 s_out[kLatticeWarps][64];                 // survivors of stage B waiting for a 32-wide flush
+  __shared__ float4 s_outp[kLatticeWarps][64];               // ... and their recentred positions
 
   const DeviceScene& sc = P.sc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,15 +302,22 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
   const unsigned int colA = flat_lo / nz, gA = colA * cpc + (flat_lo - colA * nz) / kSegmentMax;
   unsigned int* queue = s_queue[warp];
   uint2* outq = s_out[warp];
+  float4* outp = s_outp[warp];
   const unsigned int lt_mask = (1u << lane) - 1u;
   int on = 0;  // warp-uniform number of pending survivors
+  // which candidates fill the list from the front: the ones that need no aperture test at all when the weight-only
+  // kernel takes the front region, else the ones that need no slit test
+  const unsigned int front_flag = P.front_weight_only ? kCandCertainAll : kCandCertain;
   // append `count` (<= 32) pending survivors to the global candidate list: one atomic, one coalesced store
   // certain candidates grow from the front of the list, the others from its back: the exact kernel then runs warps of
   // one kind (a warp with a single uncertain lane would execute the tests the certain lanes skip anyway)
   auto flush = [&](int count) {
     __syncwarp();
-    const uint2 mine = outq[min(lane, 63)];
-    const bool is_c = lane < count && (mine.y & kCandCertain) != 0u;
+    uint2 mine = outq[min(lane, 63)];
+    if (P.front_weight_only && lane < count && (mine.y & kCandCertain) != 0u &&
+        certain_everywhere(sc, outp[lane], (int)(mine.y & kCandCrystalMask)))
+      mine.y |= kCandCertainAll;  // decided here, 32 compacted survivors at a time, not in the sparse drain
+    const bool is_c = lane < count && (mine.y & front_flag) != 0u;
     const unsigned int bc = __ballot_sync(0xffffffffu, is_c);
     const int nc = __popc(bc), nu = count - nc;
     unsigned long long posc = 0, posu = 0;
@@ -304,8 +337,9 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       }
     }
     const uint2 carry = outq[min(lane + count, 63)];
+    const float4 carryp = outp[min(lane + count, 63)];
     __syncwarp();
-    if (lane + count < on) outq[lane] = carry;
+    if (lane + count < on) outq[lane] = carry, outp[lane] = carryp;
     on -= count;
     __syncwarp();
   };
@@ -357,6 +391,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
       bool keep = false, certain = false;
       unsigned int ent = 0;
       int vloc = 0, slit = -1;
+      float4 pos = make_float4(0.f, 0.f, 0.f, 1.f);
       if (lane < take) {
         ent = queue[qn - take + lane];
         const int seg = ent >> 11, k = (ent >> 5) & 63;
@@ -369,14 +404,17 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) filter_kernel_lattice(cons
         keep = slit >= 0;
         certain = keep && (slit & kSlitCertain) != 0;  // well inside its slit on both sides
         slit &= 0xF;
+        pos = p;
       }
       qn -= take;
       const unsigned int bal = __ballot_sync(0xffffffffu, keep);
       if (bal) {
-        if (keep)
-          outq[on + __popc(bal & lt_mask)] =
-              make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)) | (certain ? kCandCertain : 0u) |
-                                                 ((unsigned int)slit << 28));
+        if (keep) {
+          const int at = on + __popc(bal & lt_mask);
+          outq[at] = make_uint2((unsigned int)vloc, (unsigned int)(cg * 32 + (ent & 31)) | (certain ? kCandCertain : 0u) |
+                                                        ((unsigned int)slit << 28));
+          outp[at] = pos;
+        }
         on += __popc(bal);
         if (on >= 32) flush(32);
       }
@@ -479,10 +517,6 @@ __device__ __forceinline__ void clip_ratio(float& lo, float& hi, float s, float 
                                            float hi_b) {
   clip_halfline(lo, hi, s * fmaf(-lo_b, w0, n0), s * fmaf(-lo_b, dw, dn));
   clip_halfline(lo, hi, s * fmaf(hi_b, w0, -n0), s * fmaf(hi_b, dw, -dn));
-}
-
-__device__ __forceinline__ bool ratio_inside(float s, float n, float w, float lo_b, float hi_b) {
-  return s * fmaf(-lo_b, w, n) >= 0.f && s * fmaf(hi_b, w, -n) >= 0.f;
 }
 
 __device__ __forceinline__ float dz_dot(const float4 g, const float* dz) {
@@ -677,17 +711,33 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
                 dXq = dz_dot(fXq, P.dz), dYq = dz_dot(fYq, P.dz), dWq = dz_dot(fWq, P.dz);
                 port_loaded = true;
               }
-              bool ok = sc.port_inner.xlo <= sc.port_inner.xhi;
+              // the port denominator must keep its sign (and stay away from zero) between the two ends
+              const float wqa = fmaf((float)ci_lo, dWq, Wq0), wqb = fmaf((float)ci_hi, dWq, Wq0);
+              bool ok = sc.port_inner.xlo <= sc.port_inner.xhi && wqa * wqb > 0.f && fminf(fabsf(wqa), fabsf(wqb)) > 1e-3f;
+              const float sp = wqa < 0.f ? -1.f : 1.f;
+              bool in_rect = ok;  // both ends inside the inner rectangle: nothing more to do (convexity)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float k = (float)(e ? ci_hi : ci_lo);
-                const float wq = fmaf(k, dWq, Wq0);
-                const float sp = wq < 0.f ? -1.f : 1.f;
-                ok = ok && fabsf(wq) > 1e-3f && ratio_inside(sp, fmaf(k, dXq, Xq0), wq, sc.port_inner.xlo, sc.port_inner.xhi) &&
-                     ratio_inside(sp, fmaf(k, dYq, Yq0), wq, sc.port_inner.ylo, sc.port_inner.yhi);
+                const float wq = e ? wqb : wqa;
+                in_rect = in_rect && ratio_inside(sp, fmaf(k, dXq, Xq0), wq, sc.port_inner.xlo, sc.port_inner.xhi) &&
+                          ratio_inside(sp, fmaf(k, dYq, Yq0), wq, sc.port_inner.ylo, sc.port_inner.yhi);
               }
-              // the port denominator must keep its sign between the two ends
-              ok = ok && fmaf((float)ci_lo, dWq, Wq0) * fmaf((float)ci_hi, dWq, Wq0) > 0.f;
+              if (ok && !in_rect && sc.n_port_edge > 0) {
+                // the port polygon edge by edge, inner offsets: each is one more linear inequality in k
+                float l3 = -1e9f, h3 = 1e9f;
+                for (int q = 0; q < sc.n_port_edge; ++q) {
+                  const float4 ed = sc.port_edge[q];
+                  clip_halfline(l3, h3, sp * fmaf(ed.x, Xq0, fmaf(ed.y, Yq0, ed.w * Wq0)),
+                                sp * fmaf(ed.x, dXq, fmaf(ed.y, dYq, ed.w * dWq)));
+                }
+                if (l3 <= h3)
+                  ci_lo = max(ci_lo, (int)ceilf(fmaxf(l3, -1e6f) + 1e-3f)), ci_hi = min(ci_hi, (int)floorf(fminf(h3, 1e6f) - 1e-3f));
+                else
+                  ok = false;
+              } else {
+                ok = ok && in_rect;
+              }
               if (!ok) ci_lo = 1, ci_hi = 0;
             }
           }
@@ -1261,6 +1311,13 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     const unsigned long long c = P.cand_capacity / (warps * 16ull);
     P.cand_chunk = (int)std::max<unsigned long long>(32, std::min<unsigned long long>(2048, c / 32 * 32));
   }
+  // the weight-only kernel takes the front region of the list when the filter can vouch for whole rays: the interval
+  // kernel always, the per-ray lattice kernel when the scene has certain regions for every aperture (the detector image
+  // needs the fp64 detector hit: everything then goes through the exact kernel)
+  P.front_weight_only = (P.sc.pix_out == nullptr && !P.sc.filter_disabled &&
+                         (interval_kernel || (lattice_kernel && !P.sc.certain_off && P.sc.n_port_edge > 0 &&
+                                              P.sc.det_inner.xlo <= P.sc.det_inner.xhi && P.sc.inner_crys.xlo <= P.sc.inner_crys.xhi)))
+                            ? 1 : 0;
   if (g_timing_on) {
     timing_collect();
     cudaEventRecord(g_ev[0], stream);
@@ -1283,7 +1340,6 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
     const unsigned int blocks = (unsigned int)std::max<unsigned long long>(
         1, std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, (unsigned long long)sms * occ_x * 4ull));
-    P.front_weight_only = (interval_kernel && P.sc.pix_out == nullptr) ? 1 : 0;
     if (P.front_weight_only) {
       auto magic = [](long long d) { return d >= 2 ? ~0ull / (unsigned long long)d + 1ull : 0ull; };
       P.magic_nz = magic(lattice_h->nz), P.magic_nx = magic(lattice_h->nx);

@@ -189,6 +189,9 @@ int com_scene_filter_certain_host(const ComSceneDesc* desc_h, float* out9);
 int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, int32_t* interval_filter,
                                    float* port_forms_out, float* slit_edges_out, int32_t* n_slit_edges_out,
                                    int32_t* certain_off_out);
+/* The port polygon as the filters' certain test uses it: edges_out64 [16][4] = (a, b, c + eps, c - certain_mm) per edge
+ * with a x + b y + c >= 0 inside (aperture frame, mm), *n_edges_out how many are used (0: the inner rectangle is used). */
+int com_scene_port_edges_host(const ComSceneDesc* desc_h, float* edges_out64, int32_t* n_edges_out);
 
 /* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
  * are tested one by one, simulation.py:344-369): whether the collimator was found periodic
