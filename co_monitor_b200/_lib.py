@@ -203,6 +203,10 @@ def _declare(lib):
     lib.com_visibility_weights.argtypes = [
         vp, C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, C.c_size_t, vp,
     ]
+    lib.com_voxels_pack.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.com_visibility_weights_packed.argtypes = [
+        vp, vp, vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, C.c_size_t, vp,
+    ]
     lib.com_visibility_weights_host.argtypes = [
         C.POINTER(ComSceneDesc), C.POINTER(ComLattice), vp, i64, i64, vp, vp, vp, i64, u64p, C.POINTER(ComStats),
     ]
@@ -267,6 +271,7 @@ EXPORTED_SYMBOLS = [
     "com_scene_create", "com_scene_destroy", "com_scene_aperture_count", "com_scene_get_aperture",
     "com_scene_filter_info", "com_lattice_local_voxels", "com_scene_set_detector_image", "com_scene_filter_tables_host",
     "com_visibility_workspace_bytes", "com_visibility_weights", "com_visibility_weights_host",
+    "com_voxels_pack", "com_visibility_weights_packed",
     "com_visible_weights_host", "com_host_arena_release",
     "com_compact_workspace_bytes", "com_compact_visible",
     "com_kernel_timing_enable", "com_kernel_timing_read", "com_kernel_timing_read3", "com_measure_fp32_tflops",

@@ -11,6 +11,10 @@
 #include "scene.h"
 
 namespace com {
+int voxels_pack(const ComScene*, const double*, long long, long long, float4*, cudaStream_t);
+int visibility_launch_packed(const ComScene*, const ComLattice*, const double*, const float4*, long long, long long, double*,
+                             unsigned int*, ComRayRecord*, long long, unsigned long long*, const uint16_t*, double*, int,
+                             ComStats*, void*, size_t, cudaStream_t);
 int visibility_launch(const ComScene*, const ComLattice*, const double*, long long, long long, double*, unsigned int*,
                       ComRayRecord*, long long, unsigned long long*, const uint16_t*, double*, int, ComStats*, void*,
                       size_t, cudaStream_t);
@@ -394,6 +398,27 @@ size_t com_visibility_workspace_bytes(const ComScene* scene, int64_t n_voxels, d
   return com::visibility_workspace_bytes(scene->dev, n_voxels, candidate_fraction);
 }
 
+int com_voxels_pack(const ComScene* scene, const double* vox_xyz, int64_t vox_begin, int64_t vox_end, void* vox_packed_out,
+                    com_stream_t stream) {
+  return com::voxels_pack(scene, vox_xyz, vox_begin, vox_end, reinterpret_cast<float4*>(vox_packed_out),
+                          static_cast<cudaStream_t>(stream));
+}
+
+int com_visibility_weights_packed(const ComScene* scene, const double* vox_xyz, const void* vox_packed, int64_t vox_begin,
+                                  int64_t vox_end, double* w_out, uint32_t* nrays_out, ComRayRecord* rays_out,
+                                  int64_t rays_capacity, uint64_t* rays_count_out, const uint16_t* reff_bin,
+                                  double* hist_out, int32_t n_bins, ComStats* stats_out, void* workspace,
+                                  size_t workspace_bytes, com_stream_t stream) {
+  if (!vox_xyz || !vox_packed) {
+    com::set_error("com_visibility_weights_packed: both voxel arrays are needed (fp64 for the decision, packed for the filter)");
+    return COM_E_BADARG;
+  }
+  return com::visibility_launch_packed(scene, nullptr, vox_xyz, reinterpret_cast<const float4*>(vox_packed), vox_begin, vox_end,
+                                       w_out, nrays_out, rays_out, rays_capacity,
+                                       reinterpret_cast<unsigned long long*>(rays_count_out), reff_bin, hist_out, n_bins,
+                                       stats_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz,
                            int64_t vox_begin, int64_t vox_end, double* w_out, uint32_t* nrays_out,
                            ComRayRecord* rays_out, int64_t rays_capacity, uint64_t* rays_count_out,
@@ -437,10 +462,11 @@ static int visibility_host_impl(const ComScene* scene_h, const ComSceneDesc* des
   const size_t b_scene = align_up(blob.bytes.size(), 256);
   const size_t b_w = align_up(sizeof(double) * (size_t)n, 256), b_n = align_up(sizeof(uint32_t) * (size_t)n, 256);
   const size_t b_vox = (!lattice_h) ? align_up(sizeof(double) * 3 * (size_t)n, 256) : 0;
+  const size_t b_vox4 = (!lattice_h) ? align_up(16 * (size_t)n, 256) : 0;  // the same voxels packed for the filter
   const size_t b_rays = rays_out_h ? align_up(sizeof(ComRayRecord) * (size_t)rays_capacity, 256) : 0;
   const size_t b_misc = 512;
   const size_t b_cap = align_up(sizeof(int64_t) * (size_t)cap, 256);  // per compacted array, in pinned memory
-  const size_t total = b_scene + b_w + b_n + b_vox + b_rays + b_misc + align_up(cws_bytes, 256) + ws_bytes;
+  const size_t total = b_scene + b_w + b_n + b_vox + b_vox4 + b_rays + b_misc + align_up(cws_bytes, 256) + ws_bytes;
   char *d = nullptr, *pin = nullptr;
   rc = com::HostArena::reserve(total, b_scene + 512 + 2 * b_cap, &d, &pin);
   if (rc) return rc;
@@ -454,6 +480,7 @@ static int visibility_host_impl(const ComScene* scene_h, const ComSceneDesc* des
   double* d_w = reinterpret_cast<double*>(take(b_w));
   uint32_t* d_n = reinterpret_cast<uint32_t*>(take(b_n));
   double* d_vox = b_vox ? reinterpret_cast<double*>(take(b_vox)) : nullptr;
+  float4* d_vox4 = b_vox4 ? reinterpret_cast<float4*>(take(b_vox4)) : nullptr;
   ComRayRecord* d_rays = b_rays ? reinterpret_cast<ComRayRecord*>(take(b_rays)) : nullptr;
   char* d_misc = take(b_misc);
   ComStats* d_stats = reinterpret_cast<ComStats*>(d_misc);
@@ -472,13 +499,17 @@ static int visibility_host_impl(const ComScene* scene_h, const ComSceneDesc* des
     bind_scene(local.dev, d_scene, blob);
   }
   const double* d_vox_base = nullptr;
+  const float4* d_vox4_base = nullptr;
   if (d_vox) {  // explicit voxels: the caller passes rows [vox_begin, vox_end) only; shift so that flat indexing works
     COM_CUDA(cudaMemcpyAsync(d_vox, vox_xyz_h, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
     d_vox_base = d_vox - 3 * vox_begin;
+    rc = com::voxels_pack(scene, d_vox_base, vox_begin, vox_end, d_vox4 - vox_begin, s);
+    if (rc) return rc;
+    d_vox4_base = d_vox4 - vox_begin;
   }
-  rc = com::visibility_launch(scene, lattice_h, d_vox_base, vox_begin, vox_end, d_w, d_n, d_rays, rays_capacity,
-                              d_rays ? reinterpret_cast<unsigned long long*>(d_rcount) : nullptr, nullptr, nullptr, 0,
-                              d_stats, d_ws, ws_bytes, s);
+  rc = com::visibility_launch_packed(scene, lattice_h, d_vox_base, d_vox4_base, vox_begin, vox_end, d_w, d_n, d_rays,
+                                     rays_capacity, d_rays ? reinterpret_cast<unsigned long long*>(d_rcount) : nullptr,
+                                     nullptr, nullptr, 0, d_stats, d_ws, ws_bytes, s);
   if (rc) return rc;
   if (dense) {
     COM_CUDA(cudaMemcpyAsync(w_out_h, d_w, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));

@@ -34,7 +34,9 @@ constexpr int kQueueCap = 32 * kUnroll + 32;
 struct VoxelSource {
   int use_lattice;
   ComLattice lat;
-  const double* xyz;
+  const double* xyz;   // explicit voxels: (P,3) fp64, global mm (what the reference materialises, mesh_calculation.py:119-159)
+  const float4* f4;    // null, or the same voxels packed for the filter: (x - ox, y - oy, z - oz, 1) FP32, one 16-byte
+                       // element per voxel (com_voxels_pack); tiles of it are moved into shared memory by bulk copies
 };
 
 struct K1Params {
@@ -153,10 +155,42 @@ __device__ __forceinline__ bool certain_everywhere(const DeviceScene& sc, const 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Explicit voxels, packed for the filter: fp64 (P,3) -> recentred FP32 float4.  One pass, 24 B in + 16 B out per voxel.
+__global__ void __launch_bounds__(256) voxel_pack_kernel(const double* __restrict__ xyz, long long begin, long long end,
+                                                         double ox, double oy, double oz, float4* __restrict__ out) {
+  for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long long)gridDim.x * blockDim.x) {
+    const D3 p = ld3(xyz + 3 * i);
+    out[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), 1.f);
+  }
+}
+
+// Bulk asynchronous copy global -> shared (the TMA unit's 1-D form, cp.async.bulk) completing on an mbarrier.
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_constant__ K1Params P) {
-  __shared__ float4 s_tile[kTileVoxels];
+  __shared__ __align__(128) float4 s_tiles[2][kTileVoxels];  // [1] only with packed voxels (double buffering)
   __shared__ unsigned int s_queue[kMaxWarps][kQueueCap];
-  __shared__ int s_item;
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ int s_item, s_next;
 
   const DeviceScene& sc = P.sc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,20 +204,56 @@ __global__ void __launch_bounds__(kMaxWarps * 32) filter_kernel(const __grid_con
   int ci = 0;
   bool warp_active = false;
 
+  // Packed voxels: the tile of the NEXT work item is already on its way (one elected thread, one bulk copy of
+  // 16 B x nv into the other buffer, completion counted on an mbarrier) while this one is evaluated.
+  const bool packed = P.vox.f4 != nullptr;
+  unsigned int iter = 0;  // block-uniform: iteration i uses buffer i & 1, whose barrier is then in its (i >> 1)-th phase
+  auto issue = [&](int it, unsigned int b) {  // thread 0 only
+    const int t = it / P.n_super;
+    const long long tb = (long long)t * kTileVoxels;
+    const int nvt = (int)min((long long)kTileVoxels, P.n_vox - tb);
+    bulk_load(s_tiles[b], P.vox.f4 + P.vox_begin + tb, (unsigned int)nvt * 16u, &s_bar[b]);
+  };
+  if (packed) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar[0], 1), mbar_init(&s_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      s_next = (int)atomicAdd(&P.counters[1], 1ull);
+      if (s_next < n_items) issue(s_next, 0);
+    }
+  }
+
   for (;;) {
+    const unsigned int buf = packed ? (iter & 1u) : 0u, par = (iter >> 1) & 1u;
+    ++iter;
     __syncthreads();  // previous tile fully consumed, s_item free
-    if (threadIdx.x == 0) s_item = (int)atomicAdd(&P.counters[1], 1ull);
+    if (threadIdx.x == 0) {
+      if (packed) {
+        s_item = s_next;
+        if (s_item < n_items) {
+          s_next = (int)atomicAdd(&P.counters[1], 1ull);
+          if (s_next < n_items) issue(s_next, buf ^ 1u);
+        }
+      } else {
+        s_item = (int)atomicAdd(&P.counters[1], 1ull);
+      }
+    }
     __syncthreads();
     const int item = s_item;
     if (item >= n_items) break;
     const int tile = item / P.n_super, sup = item - tile * P.n_super;
     const long long tile_base = (long long)tile * kTileVoxels;
     const int nv = (int)min((long long)kTileVoxels, P.n_vox - tile_base);
+    const float4* s_tile = s_tiles[buf];
 
-    // stage the tile: fp64 position -> recentred FP32 (w = 1 so that a form is one dot4-like FFMA chain)
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-      D3 p = voxel_position(P.vox, P.vox_begin + tile_base + i);
-      s_tile[i] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 1.f);
+    if (packed) {
+      mbar_wait(&s_bar[buf], par);
+    } else {
+      // stage the tile: fp64 position -> recentred FP32 (w = 1 so that a form is one dot4-like FFMA chain)
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        D3 p = voxel_position(P.vox, P.vox_begin + tile_base + i);
+        s_tiles[0][i] = make_float4((float)(p.x - sc.origin[0]), (float)(p.y - sc.origin[1]), (float)(p.z - sc.origin[2]), 1.f);
+      }
     }
     if (sup != cur_super) {
       cur_super = sup;
@@ -1192,11 +1262,49 @@ size_t visibility_workspace_bytes(const DeviceScene& sc, long long n_vox, double
   return 256 + cap * sizeof(uint2);
 }
 
+int voxels_pack(const ComScene* scene, const double* vox_xyz, long long vox_begin, long long vox_end, float4* out,
+                cudaStream_t stream) {
+  if (!scene || !vox_xyz || !out || vox_end < vox_begin || vox_begin < 0) {
+    set_error("com_voxels_pack: bad arguments");
+    return COM_E_BADARG;
+  }
+  if (vox_end == vox_begin) return COM_OK;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) {
+    set_error("com_voxels_pack: the packed array must be 16-byte aligned");
+    return COM_E_BADARG;
+  }
+  const long long n = vox_end - vox_begin;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148ll * 16);
+  voxel_pack_kernel<<<blocks, 256, 0, stream>>>(vox_xyz, vox_begin, vox_end, scene->dev.origin[0], scene->dev.origin[1],
+                                                scene->dev.origin[2], out);
+  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+    set_error("voxel_pack_kernel failed: %s", cudaGetErrorString(e));
+    return COM_E_CUDA;
+  }
+  return COM_OK;
+}
+
+int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz, const float4* vox_f4,
+                             long long vox_begin, long long vox_end, double* w_out, unsigned int* nrays_out,
+                             ComRayRecord* rays_out, long long rays_capacity, unsigned long long* rays_count_out,
+                             const uint16_t* reff_bin, double* hist_out, int n_bins, ComStats* stats_out, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream);
+
 int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz, long long vox_begin,
                       long long vox_end, double* w_out, unsigned int* nrays_out, ComRayRecord* rays_out,
                       long long rays_capacity, unsigned long long* rays_count_out, const uint16_t* reff_bin,
                       double* hist_out, int n_bins, ComStats* stats_out, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream) {
+  return visibility_launch_packed(scene, lattice_h, vox_xyz, nullptr, vox_begin, vox_end, w_out, nrays_out, rays_out,
+                                  rays_capacity, rays_count_out, reff_bin, hist_out, n_bins, stats_out, workspace,
+                                  workspace_bytes, stream);
+}
+
+int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h, const double* vox_xyz, const float4* vox_f4,
+                             long long vox_begin, long long vox_end, double* w_out, unsigned int* nrays_out,
+                             ComRayRecord* rays_out, long long rays_capacity, unsigned long long* rays_count_out,
+                             const uint16_t* reff_bin, double* hist_out, int n_bins, ComStats* stats_out, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
   // an empty range has nothing to write: the output pointers may then be null (empty device tensors are)
   const bool empty = vox_end == vox_begin;
   if (!scene || (!lattice_h && !vox_xyz && !empty) || vox_end < vox_begin || (!w_out && !empty) || !stats_out ||
@@ -1224,6 +1332,11 @@ int visibility_launch(const ComScene* scene, const ComLattice* lattice_h, const 
     }
   }
   P.vox.xyz = vox_xyz;
+  P.vox.f4 = lattice_h ? nullptr : vox_f4;
+  if (P.vox.f4 && (reinterpret_cast<uintptr_t>(P.vox.f4) & 15u) != 0) {
+    set_error("com_visibility_weights_packed: the packed voxel array must be 16-byte aligned");
+    return COM_E_BADARG;
+  }
   P.vox_begin = vox_begin;
   P.n_vox = n_vox;
   // the lattice kernel indexes voxels with 32 bits

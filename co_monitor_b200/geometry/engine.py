@@ -233,12 +233,14 @@ class ChannelScene:
     # -- Stage 1 -------------------------------------------------------------------------
     def visibility(self, lattice: Lattice | None = None, voxels=None, begin: int = 0, end: int | None = None,
                    want_rays: bool = False, candidate_fraction: float = 0.0, reff_bin=None, hist=None,
-                   device=None, max_retries: int = 3) -> VisibilityResult:
+                   device=None, max_retries: int = 3, packed=None) -> VisibilityResult:
         """Run K1a/K1b over the voxels [begin, end).
 
         *lattice* selects the implicit CuboidMesh lattice; *voxels* is a torch.float64 CUDA tensor ``(P, 3)``
-        of explicit coordinates (global mm).  Returns device tensors; nothing is copied to the host except
-        the 64-byte statistics block (and the ray list when *want_rays*).
+        of explicit coordinates (global mm) - what the reference materialises (mesh_calculation.py:119-159); they are
+        packed once into the recentred float4 array the FP32 filter streams (``com_voxels_pack``; pass the result of
+        ``pack_voxels`` as *packed* to reuse it across calls).  Returns device tensors; nothing is copied to the host
+        except the statistics block (and the ray list when *want_rays*).
         """
         import torch
 
@@ -260,6 +262,10 @@ class ChannelScene:
             total = voxels.shape[0]
             vox_ptr = C.c_void_p(voxels.data_ptr())
             device = voxels.device
+            if packed is None:
+                packed = self.pack_voxels(voxels)
+            if packed.dtype != torch.float32 or tuple(packed.shape) != (total, 4) or packed.device != device:
+                raise ValueError("packed must be the float32 (P, 4) tensor pack_voxels returned for these voxels")
         end = total if end is None else end
         if not (0 <= begin <= end <= total):
             raise ValueError(f"voxel range [{begin},{end}) outside [0,{total})")
@@ -279,8 +285,7 @@ class ChannelScene:
                     rays_cap = rays_cap or max(1 << 16, (ws_bytes - 256) // 8)
                     rays_t = torch.empty(rays_cap * 4, dtype=torch.float64, device=device)
                     rays_cnt = torch.zeros(1, dtype=torch.int64, device=device)
-                rc = self._lib.com_visibility_weights(
-                    self.handle, C.byref(lat_struct) if lat_struct is not None else None, vox_ptr, begin, end,
+                out_args = (
                     C.c_void_p(w.data_ptr()), C.c_void_p(nr.data_ptr()),
                     C.c_void_p(rays_t.data_ptr()) if want_rays else None, rays_cap,
                     C.c_void_p(rays_cnt.data_ptr()) if want_rays else None,
@@ -288,6 +293,11 @@ class ChannelScene:
                     C.c_void_p(hist.data_ptr()) if hist is not None else None,
                     int(hist.numel()) if hist is not None else 0,
                     C.c_void_p(stats_t.data_ptr()), C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream))
+                if lat_struct is not None:
+                    rc = self._lib.com_visibility_weights(self.handle, C.byref(lat_struct), None, begin, end, *out_args)
+                else:
+                    rc = self._lib.com_visibility_weights_packed(self.handle, vox_ptr, C.c_void_p(packed.data_ptr()), begin, end,
+                                                                 *out_args)
                 _lib.check(rc, "com_visibility_weights")
                 stats = dict(zip([f[0] for f in _lib.ComStats._fields_], stats_t.cpu().tolist()))
                 if not stats["overflow"]:
@@ -307,6 +317,21 @@ class ChannelScene:
                                               f"{cnt} passing rays > ray-list capacity {rays_cap}")
                 rays = rays_t[: cnt * 4].cpu().numpy().view(_lib.RAY_RECORD_DTYPE).copy()
         return VisibilityResult(begin=begin, end=end, weight=w, nrays=nr, stats=stats, rays=rays)
+
+    def pack_voxels(self, voxels):
+        """``(P, 3)`` float64 CUDA coordinates -> the ``(P, 4)`` float32 array the FP32 filter streams: (x - ox, y - oy,
+        z - oz, 1) recentred on this scene's origin (``com_voxels_pack``; stream-ordered)."""
+        import torch
+
+        if voxels.dtype != torch.float64 or not voxels.is_cuda or voxels.dim() != 2 or voxels.shape[1] != 3:
+            raise ValueError("voxels must be a CUDA float64 tensor of shape (P, 3)")
+        voxels = voxels.contiguous()
+        with torch.cuda.device(voxels.device):
+            out = torch.empty((voxels.shape[0], 4), dtype=torch.float32, device=voxels.device)
+            rc = self._lib.com_voxels_pack(self.handle, C.c_void_p(voxels.data_ptr()), 0, voxels.shape[0],
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "com_voxels_pack")
+        return out
 
     def plan(self, lattice: Lattice, begin: int = 0, end: int | None = None, candidate_fraction: float = 0.0,
              device=None, **kwargs) -> "VisibilityPlan":

@@ -275,6 +275,23 @@ int com_visibility_weights(const ComScene* scene, const ComLattice* lattice_h, c
                            const uint16_t* reff_bin, double* hist_out, int32_t n_bins, ComStats* stats_out,
                            void* workspace, size_t workspace_bytes, com_stream_t stream);
 
+/* Explicit voxels the way the kernels want them (north-star: "voxel coordinates streamed from HBM as coalesced float4"):
+ * the reference materialises (P,3) fp64 coordinates (mesh_calculation.py:119-159); the fp64 decision kernel keeps reading
+ * those (only for the ~0.5 % of rays that reach it), the FP32 filter reads a packed copy - one 16-byte element
+ * (x - ox, y - oy, z - oz, 1) per voxel, recentred on the scene origin - whose 512-voxel tiles are moved into shared memory
+ * by bulk asynchronous copies (cp.async.bulk, double buffered).
+ *   com_voxels_pack                 vox_packed_out[v] for v in [vox_begin, vox_end) from vox_xyz (DEVICE, indexed by v);
+ *                                   vox_packed_out: DEVICE, 16 x P bytes, 16-byte aligned
+ *   com_visibility_weights_packed   com_visibility_weights for explicit voxels with the packed copy supplied (results are
+ *                                   identical to passing vox_xyz alone: the same FP32 values enter the filter) */
+int com_voxels_pack(const ComScene* scene, const double* vox_xyz, int64_t vox_begin, int64_t vox_end, void* vox_packed_out,
+                    com_stream_t stream);
+int com_visibility_weights_packed(const ComScene* scene, const double* vox_xyz, const void* vox_packed, int64_t vox_begin,
+                                  int64_t vox_end, double* w_out, uint32_t* nrays_out, ComRayRecord* rays_out,
+                                  int64_t rays_capacity, uint64_t* rays_count_out, const uint16_t* reff_bin,
+                                  double* hist_out, int32_t n_bins, ComStats* stats_out, void* workspace,
+                                  size_t workspace_bytes, com_stream_t stream);
+
 /* Host-buffer variant (the reference-facing call: everything Simulation.__init__ does after its _init_* methods,
  * simulation.py:50-72): host in, host out, device work inside; synchronous.
  * vox_xyz_h may be NULL when lattice_h is given.  rays_out_h may be NULL.  Returns COM_E_EMPTY when no

@@ -113,6 +113,58 @@ def test_explicit_voxels_match_lattice(sims):
     assert torch.allclose(a.weight, b.weight, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("el", ["C", "O"])
+def test_packed_explicit_voxels_ragged_ranges(sims, el):
+    """Explicit (P,3) fp64 voxels with the packed float4 copy the filter streams by bulk copies (com_voxels_pack +
+    com_visibility_weights_packed) against the lattice path (oracle-checked) and against the unpacked explicit call:
+    ranges that start and end off the 512-voxel tiles, a range shorter than one tile, a reused packed array."""
+    import ctypes as C
+
+    import torch
+
+    from co_monitor_b200 import _lib
+
+    sim = sims(el)
+    scene, lat = sim.scene, sim.mesh.lattice
+    hi_all = 150_003
+    pts = torch.from_numpy(sim.mesh.points_at(np.arange(0, hi_all))).cuda()
+    packed = scene.pack_voxels(pts)
+    ref_pack = (pts - torch.tensor(list(scene.desc.origin), dtype=torch.float64, device="cuda")).to(torch.float32)
+    assert torch.equal(packed[:, :3], ref_pack) and bool((packed[:, 3] == 1).all())
+    for lo, hi in [(100_001, 140_777), (120_000, 120_300), (0, 513), (149_000, hi_all)]:
+        a = scene.visibility(lattice=lat, begin=lo, end=hi)
+        b = scene.visibility(voxels=pts, begin=lo, end=hi, packed=packed)
+        assert torch.equal(a.nrays, b.nrays), (lo, hi)
+        assert torch.allclose(a.weight, b.weight, rtol=1e-12, atol=0)
+        assert a.stats["passing_rays"] == b.stats["passing_rays"]
+    # the unpacked explicit call (tiles converted from fp64 inside the kernel) gives the same candidates and results
+    lib = _lib.load()
+    lo, hi = 100_001, 140_777
+    n = hi - lo
+    ws_bytes = lib.com_visibility_workspace_bytes(scene.handle, n, 0.0)
+    outs = []
+    for use_packed in (False, True):
+        w = torch.empty(n, dtype=torch.float64, device="cuda")
+        nr = torch.empty(n, dtype=torch.int32, device="cuda")
+        st = torch.zeros(_lib.N_STATS, dtype=torch.int64, device="cuda")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        tail = (lo, hi, C.c_void_p(w.data_ptr()), C.c_void_p(nr.data_ptr()), None, 0, None, None, None, 0,
+                C.c_void_p(st.data_ptr()), C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if use_packed:
+            rc = lib.com_visibility_weights_packed(scene.handle, C.c_void_p(pts.data_ptr()), C.c_void_p(packed.data_ptr()), *tail)
+        else:
+            rc = lib.com_visibility_weights(scene.handle, None, C.c_void_p(pts.data_ptr()), *tail)
+        _lib.check(rc, "explicit voxels")
+        torch.cuda.synchronize()
+        outs.append((w, nr, st.cpu().tolist()))
+    assert torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-13, atol=0)
+    # misaligned packed array is refused, not read
+    with pytest.raises(_lib.ComonitorError):
+        bad = torch.empty(hi_all * 4 + 1, dtype=torch.float32, device="cuda")[1:].view(hi_all, 4)
+        scene.visibility(voxels=pts, begin=0, end=1000, packed=bad)
+
+
 def test_reference_attributes(sims):
     sim = sims("C")
     assert sim.crystal_point_area == 2.67
