@@ -246,13 +246,32 @@ __global__ void reff_max_kernel(const K2Params P) {
 
 constexpr int kK2Threads = 256;
 
+// kRowTable: everything a voxel's columns hold depends on its profile row alone (reader.py:282-378 work on n_e and T_e
+// of the row), so the block first evaluates every row once into shared memory - the profile, the fractional-abundance
+// grid and the PEC nodes are then touched K times per block instead of once per voxel - and the voxel loop is a row
+// search, a shared-memory gather and the weighted sums.  The same eval_row on the same inputs: identical numbers.
+// Used when the K x (4 + 2 T + 1) table fits in shared memory (K <= ~1300 rows); longer profiles evaluate per voxel.
+template <bool kRowTable>
 __global__ void __launch_bounds__(kK2Threads) emissivity_kernel(const K2Params P) {
+  extern __shared__ double s_rowtab[];  // kRowTable: (K, ncol) = n_e, T_e, FA ion, FA stripped, pec[T], emis[T], total
   const int nt = P.tab.n_trans, nout = nt + 1, ncol = 4 + 2 * nt + 1;
   const double boundary = cut_boundary(P);
   const long long n = voxel_count(P);
   double acc[kMaxTransitions + 1];
 #pragma unroll
   for (int t = 0; t <= kMaxTransitions; ++t) acc[t] = 0.0;
+  if (kRowTable) {
+    for (int k = threadIdx.x; k < P.K; k += kK2Threads) {
+      const double te = P.profile[3 * k + 1], ne = P.profile[3 * k + 2];
+      RowEval r;
+      eval_row(P.tab, ne, te, P.conc, r);
+      double* o = s_rowtab + (size_t)k * ncol;
+      o[0] = ne, o[1] = te, o[2] = r.fa_ion, o[3] = r.fa_last;
+      for (int t = 0; t < nt; ++t) o[4 + t] = r.pec[t], o[4 + nt + t] = r.emis[t];
+      o[4 + 2 * nt] = r.total;
+    }
+    __syncthreads();
+  }
 
   for (long long i = blockIdx.x * (long long)kK2Threads + threadIdx.x; i < n; i += (long long)gridDim.x * kK2Threads) {
     const double reff = voxel_reff(P, i);
@@ -260,10 +279,22 @@ __global__ void __launch_bounds__(kK2Threads) emissivity_kernel(const K2Params P
     if (P.valid_out) P.valid_out[i] = valid ? 1 : 0;
     if (!valid) continue;
     const int k = profile_row(P, reff);
+    const double w = P.w[i];
+    if (kRowTable) {
+      const double* r = s_rowtab + (size_t)k * ncol;
+#pragma unroll
+      for (int t = 0; t < kMaxTransitions; ++t)
+        if (t < nt) acc[t] += r[4 + nt + t] * w;
+      acc[kMaxTransitions] += r[4 + 2 * nt] * w;
+      if (P.per_voxel) {
+        double* o = P.per_voxel + (size_t)i * ncol;
+        for (int c = 0; c < ncol; ++c) o[c] = r[c];
+      }
+      continue;
+    }
     const double te = P.profile[3 * k + 1], ne = P.profile[3 * k + 2];
     RowEval r;
     eval_row(P.tab, ne, te, P.conc, r);
-    const double w = P.w[i];
 #pragma unroll
     for (int t = 0; t < kMaxTransitions; ++t)
       if (t < nt) acc[t] += r.emis[t] * w;
@@ -717,9 +748,20 @@ int com_emissivity_integrate(const ComTables* tables, const double* profile, int
   COM_CUDA(cudaMemsetAsync(workspace, 0, 256 + 64, s));
   COM_CUDA(cudaMemsetAsync(flux_out, 0, sizeof(double) * (tables->n_trans + 1), s));
   if (n == 0) return COM_OK;
-  const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * 2);
+  // row table in shared memory when it fits next to three resident blocks per SM; the rows are evaluated once per
+  // block, so small inputs get few blocks (a block's set-up is K row evaluations)
+  const size_t rowtab = sizeof(double) * (size_t)K * (4 + 2 * tables->n_trans + 1);
+  const bool use_rowtab = rowtab <= 72 * 1024 && n >= 4 * (long long)K;
+  const int per_sm = use_rowtab ? 3 : 2;
+  const int blocks = (int)std::min<long long>((n + com::kK2Threads - 1) / com::kK2Threads, 148 * per_sm);
   if (!mapped_reff_max) com::reff_max_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
-  com::emissivity_kernel<<<blocks, com::kK2Threads, 0, s>>>(P);
+  if (use_rowtab) {
+    const int rblocks = (int)std::min<long long>(blocks, std::max<long long>(1, n / (4 * (long long)K)));
+    COM_CUDA(cudaFuncSetAttribute(com::emissivity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowtab));
+    com::emissivity_kernel<true><<<rblocks, com::kK2Threads, rowtab, s>>>(P);
+  } else {
+    com::emissivity_kernel<false><<<blocks, com::kK2Threads, 0, s>>>(P);
+  }
   COM_CUDA(cudaGetLastError());
   return COM_OK;
 }
