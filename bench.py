@@ -216,7 +216,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-KERNEL_REGEX = "regex:filter_kernel|interval_kernel_lattice|weight_kernel|exact_kernel|weight_histogram_mm"
+KERNEL_REGEX = "regex:filter_kernel|interval_kernel_lattice|expand_kernel|weight_kernel|exact_kernel|weight_histogram_mm"
 
 
 def ncu_counters(spacing, element="C", mode="production", timeout_s=300):
@@ -562,10 +562,13 @@ def run_ours(args):
         roofline["counters"] = cnt_nc
     pc = (cnt_prod or {}).get("probe") or {}
     roofline_production = {
-        "what": "the shipped step's Stage-1 kernels, same definitions as `roofline` (channel C; counters from a second ncu pass)",
+        "what": "the shipped step's Stage-1 kernels, same definitions as `roofline` (channel C; counters from a second ncu pass); "
+                "the interval kernel's time includes expand_kernel (interval records -> per-ray list), its counters do not",
         "step_shares": shares(kt_prod), "stage1_ms_four_channels": kt_prod["stage1_ms"],
         "interval_kernel": kernel_record(cnt_prod, "interval_kernel_lattice", kt_prod_c["filter_ms"],
                                          "executed_lane_instr_per_candidate", pc.get("candidates")),
+        "expand_kernel_lane_instr_per_candidate": ((cnt_prod or {}).get("kernels", {}).get("expand_kernel", {}).get(
+            "smsp__thread_inst_executed.sum", 0.0) / pc["candidates"]) if pc.get("candidates") else None,
         "weight_kernel": kernel_record(cnt_prod, "weight_kernel", kt_prod_c["weight_ms"], "executed_lane_instr_per_ray",
                                        pc.get("certain_candidates")),
         "exact_kernel": kernel_record(cnt_prod, "exact_kernel", kt_prod_c["exact_ms"], "executed_lane_instr_per_candidate",
@@ -666,6 +669,7 @@ def run_ours(args):
             "passing_rays": {el: stats[i]["passing_rays"] for i, el in enumerate(ELEMENTS)},
             "visible_voxels": {el: stats[i]["visible_voxels"] for i, el in enumerate(ELEMENTS)},
             "fp64_candidates": {el: stats[i]["candidates"] for i, el in enumerate(ELEMENTS)},
+            "certain_candidates_weight_only": {el: stats[i]["certain_candidates"] for i, el in enumerate(ELEMENTS)},
             "near_edge_rays_1e-9mm": {el: stats[i]["near_edge_rays"] for i, el in enumerate(ELEMENTS)},
             "near_edge_rays_1e-4mm": {el: stats[i]["near_band_rays"] for i, el in enumerate(ELEMENTS)},
             "flux_excit_recom_total": {el: [float(x) for x in flux_prod[i]] for i, el in enumerate(ELEMENTS)},

@@ -53,7 +53,7 @@ struct K1Params {
   uint2* cand;       // (voxel_local, crystal) pairs
   unsigned long long cand_capacity;
   unsigned long long* counters;  // [0] slots used at the front (certain), [1] next work item, [2] slots used at the back,
-                                 // [3], [4] candidates written front / back when the list is filled in chunks
+                                 // [5] interval records reserved, [6] rays in all interval records
   double* w_out;
   unsigned int* nrays_out;
   ComRayRecord* rays_out;
@@ -63,8 +63,8 @@ struct K1Params {
   double* hist_out;
   int n_bins;
   unsigned long long magic_nz, magic_nx, magic_cpb;  // weight kernel: multipliers replacing divisions by nz, nx, cols per block
-  int cand_chunk;         // column-interval kernel: slots a warp reserves at a time (the list then has invalid entries and
-                          // counters[3] / [4] hold the numbers of certain / other candidates really written)
+  uint4* recs;            // column-interval kernel: one 16-byte record per interval (layout at the kernel's emit)
+  unsigned long long rec_capacity;
   int front_weight_only;  // 1: the front region of the list was produced by the column-interval kernel and is handled by
                           // weight_kernel (the exact kernel then takes the back region only)
   int accumulate_stats;  // 1: add this launch's counters to *stats instead of overwriting them (whole-volume runs)
@@ -595,7 +595,7 @@ __device__ __forceinline__ float dz_dot(const float4 g, const float* dz) {
 
 __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(const __grid_constant__ K1Params P) {
   __shared__ float4 s_base[kLatticeWarps][kColsPerItem];  // column base positions (recentred FP32, w = 1)
-  __shared__ uint2 s_out[kLatticeWarps][64];             // candidates waiting for a 32-wide flush
+  __shared__ uint4 s_out[kLatticeWarps][64];             // interval records waiting for a 32-wide flush
 
   const DeviceScene& sc = P.sc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -603,67 +603,43 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
   const unsigned int nz = (unsigned int)P.vox.lat.nz;
   const unsigned int flat_lo = (unsigned int)P.vox_begin, flat_hi = (unsigned int)(P.vox_begin + P.n_vox);
   const unsigned int colA = flat_lo / nz, colB = (flat_hi - 1u) / nz;
-  uint2* outq = s_out[warp];
+  uint4* outq = s_out[warp];
   float4* base = s_base[warp];
   const unsigned int lt_mask = (1u << lane) - 1u;
-  int on = 0;  // warp-uniform number of pending candidates
-  // The list is filled in per-warp chunks: a warp reserves P.cand_chunk slots of a region with one atomic and fills
-  // them by itself (one atomic per 32 candidates serialises the whole grid on two L2 addresses).  Slots a warp leaves
-  // unused are marked invalid; the fp64 kernels skip them.  Certain candidates fill the list from the front, the
-  // others from its back, so that the fp64 stage runs warps of one kind.
-  unsigned long long cur_c = 0, cur_u = 0, n_c = 0, n_u = 0;  // warp-uniform: next slot of the open chunks, candidates written
-  int left_c = 0, left_u = 0;
-  const uint2 kInvalid = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-  auto slot = [&](unsigned long long pos, bool back) -> uint2* {
-    return pos < P.cand_capacity ? &P.cand[back ? P.cand_capacity - 1ull - pos : pos] : nullptr;
-  };
-  auto reserve = [&](unsigned long long& cur, int& left, int need, bool back) {  // returns the first slot for `need` entries
-    if (need > left) {
-      if (lane < left)
-        if (uint2* q = slot(cur + lane, back)) *q = kInvalid;  // give up the tail of the open chunk (< 32 slots)
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&P.counters[back ? 2 : 0], (unsigned long long)P.cand_chunk);
-      cur = __shfl_sync(0xffffffffu, base, 0);
-      left = P.cand_chunk;
-    }
-    const unsigned long long first = cur;
-    cur += need, left -= need;
-    return first;
-  };
+  int on = 0;  // warp-uniform number of pending records
+  // One 16-byte record per interval (not one entry per ray: the intervals of a warp's 32 crystal points rarely line up,
+  // a per-ray emit loop runs with a handful of lanes): .x launch-local index of the interval's first voxel, .y crystal
+  // index | slit hint << 28, .z length | (offset of the certain part) << 16, .w length of the certain part (0: none).
+  // expand_kernel turns the records into the per-ray list the fp64 kernels read, with every lane busy.
+  unsigned long long n_rays = 0, n_certain = 0;  // per lane, for the statistics
   auto flush = [&](int count) {
     __syncwarp();
-    const uint2 mine = outq[min(lane, 63)];
-    const bool is_c = lane < count && (mine.y & kCandCertain) != 0u;
-    const unsigned int bc = __ballot_sync(0xffffffffu, is_c);
-    const int nc = __popc(bc), nu = count - nc;
-    const unsigned long long posc = nc ? reserve(cur_c, left_c, nc, false) : 0ull;
-    const unsigned long long posu = nu ? reserve(cur_u, left_u, nu, true) : 0ull;
-    n_c += nc, n_u += nu;
-    if (lane < count) {
-      uint2* q = is_c ? slot(posc + __popc(bc & lt_mask), false) : slot(posu + (lane - __popc(bc & lt_mask)), true);
-      if (q) *q = mine;
-    }
-    const uint2 carry = outq[min(lane + count, 63)];
+    const uint4 mine = outq[min(lane, 63)];
+    unsigned long long pos = 0;
+    if (lane == 0) pos = atomicAdd(&P.counters[5], (unsigned long long)count);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (lane < count && pos + lane < P.rec_capacity) P.recs[pos + lane] = mine;
+    const uint4 carry = outq[min(lane + count, 63)];
     __syncwarp();
     if (lane + count < on) outq[lane] = carry;
     on -= count;
     __syncwarp();
   };
-  // every lane offers the rays [a, b] of its column (certain where ci_lo <= k <= ci_hi); the warp emits them side by side
+  // every lane offers the interval [a, b] of its column (certain where ci_lo <= k <= ci_hi)
   auto emit = [&](unsigned int col, int a, int b, int ci_lo, int ci_hi, int ci, int slit) {
-    const int trips = __reduce_max_sync(0xffffffffu, b - a + 1);
-    const unsigned int v0 = col * nz - flat_lo;  // launch-local index of the column's voxel 0 (wraps for a clipped first column)
-    for (int i = 0; i < trips; ++i) {
-      const int k = a + i;
-      const bool have = k <= b;
-      const unsigned int bal = __ballot_sync(0xffffffffu, have);
-      if (have)
-        outq[on + __popc(bal & lt_mask)] = make_uint2(
-            v0 + (unsigned int)k,
-            (unsigned int)ci | ((k >= ci_lo && k <= ci_hi) ? (kCandCertain | kCandCertainAll) : 0u) | ((unsigned int)slit << 28));
-      on += __popc(bal);
-      if (on >= 32) flush(32);
+    const bool have = a <= b;
+    const unsigned int bal = __ballot_sync(0xffffffffu, have);
+    if (have) {
+      const unsigned int v0 = col * nz - flat_lo;  // launch-local index of the column's voxel 0 (wraps for a clipped first column)
+      const bool cert = ci_lo <= ci_hi;
+      const unsigned int len = (unsigned int)(b - a + 1), c_off = cert ? (unsigned int)(ci_lo - a) : 0u,
+                         c_len = cert ? (unsigned int)(ci_hi - ci_lo + 1) : 0u;
+      outq[on + __popc(bal & lt_mask)] = make_uint4(v0 + (unsigned int)a, (unsigned int)ci | ((unsigned int)slit << 28),
+                                                    len | (c_off << 16), c_len);
+      n_rays += len, n_certain += c_len;
     }
+    on += __popc(bal);
+    if (on >= 32) flush(32);
   };
 
   const float nz1 = (float)(nz - 1u);
@@ -817,14 +793,86 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
     }
   }
   if (on > 0) flush(on);
-  // close the open chunks and report what was really written
-  for (int i = lane; i < left_c; i += 32)
-    if (uint2* q = slot(cur_c + i, false)) *q = kInvalid;
-  for (int i = lane; i < left_u; i += 32)
-    if (uint2* q = slot(cur_u + i, true)) *q = kInvalid;
-  if (lane == 0) {
-    if (n_c) atomicAdd(&P.counters[3], n_c);
-    if (n_u) atomicAdd(&P.counters[4], n_u);
+  (void)n_certain;
+  n_rays = __reduce_add_sync(0xffffffffu, (unsigned int)min(n_rays, 0xFFFFFFFFull >> 5));  // per lane < 2^27 in any launch
+  if (lane == 0 && n_rays) atomicAdd(&P.counters[6], n_rays);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Interval records -> the per-ray candidate list.  A block takes 256 records, scans the lengths of their certain and
+// uncertain parts, reserves the two ranges of the list with one atomic each (certain rays fill the list from the front -
+// the weight-only kernel's region - the others from its back) and writes the rays with all lanes busy: ray r of the
+// block belongs to the record found by a binary search in the scanned lengths.
+constexpr int kExpandThreads = 256;
+
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ K1Params P) {
+  __shared__ uint4 s_rec[kExpandThreads];
+  __shared__ unsigned int s_c[kExpandThreads + 1], s_u[kExpandThreads + 1];  // exclusive scans of the two lengths
+  __shared__ unsigned int s_warp[2][kExpandThreads / 32];
+  __shared__ unsigned long long s_pos[2];
+  const unsigned long long reserved = P.counters[5];
+  if (reserved > P.rec_capacity) {
+    // The record list overflowed: make the ray list report it (exact_kernel checks), with a candidate count that sizes a
+    // workspace in which both lists fit - callers re-run with candidate_fraction = that count / tests.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned long long by_recs = (reserved * P.cand_capacity + P.rec_capacity - 1ull) / max(P.rec_capacity, 1ull);
+      P.counters[0] = max(max(P.counters[6], by_recs), P.cand_capacity) + 1ull;
+      P.counters[2] = 0ull;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned long long first = (unsigned long long)blockIdx.x * kExpandThreads; first < reserved;
+       first += (unsigned long long)gridDim.x * kExpandThreads) {
+    const unsigned long long i = first + threadIdx.x;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (i < reserved) rec = P.recs[i];
+    const unsigned int len = rec.z & 0xFFFFu, c_len = rec.w, u_len = len - c_len;
+    // block-wide exclusive scans of c_len and u_len
+    unsigned int ic = c_len, iu = u_len;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int a = __shfl_up_sync(0xffffffffu, ic, off), b = __shfl_up_sync(0xffffffffu, iu, off);
+      if (lane >= off) ic += a, iu += b;
+    }
+    if (lane == 31) s_warp[0][warp] = ic, s_warp[1][warp] = iu;
+    s_rec[threadIdx.x] = rec;
+    __syncthreads();
+    unsigned int bc = 0, bu = 0;
+    for (int q = 0; q < warp; ++q) bc += s_warp[0][q], bu += s_warp[1][q];
+    s_c[threadIdx.x + 1] = bc + ic, s_u[threadIdx.x + 1] = bu + iu;
+    if (threadIdx.x == 0) s_c[0] = 0u, s_u[0] = 0u;
+    __syncthreads();
+    const unsigned int Tc = s_c[kExpandThreads], Tu = s_u[kExpandThreads];
+    if (threadIdx.x == 0) {
+      s_pos[0] = Tc ? atomicAdd(&P.counters[0], (unsigned long long)Tc) : 0ull;
+      s_pos[1] = Tu ? atomicAdd(&P.counters[2], (unsigned long long)Tu) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long pc = s_pos[0], pu = s_pos[1];
+    auto owner = [](const unsigned int* scan, unsigned int r) {  // largest i with scan[i] <= r
+      int lo = 0, hi = kExpandThreads - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (scan[mid] <= r) lo = mid; else hi = mid - 1;
+      }
+      return lo;
+    };
+    for (unsigned int r = threadIdx.x; r < Tc; r += kExpandThreads) {
+      const int q = owner(s_c, r);
+      const uint4 e = s_rec[q];
+      const unsigned long long pos = pc + r;
+      if (pos < P.cand_capacity)
+        P.cand[pos] = make_uint2(e.x + (e.z >> 16) + (r - s_c[q]), e.y | kCandCertain | kCandCertainAll);
+    }
+    for (unsigned int r = threadIdx.x; r < Tu; r += kExpandThreads) {
+      const int q = owner(s_u, r);
+      const uint4 e = s_rec[q];
+      const unsigned int j = r - s_u[q], c_off = e.z >> 16;
+      const unsigned long long pos = pu + r;
+      if (pos < P.cand_capacity) P.cand[P.cand_capacity - 1ull - pos] = make_uint2(e.x + (j < c_off ? j : j + e.w), e.y);
+    }
+    __syncthreads();  // s_rec / scans are rewritten by the next batch
   }
 }
 
@@ -906,9 +954,8 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const unsigned long long n = overflow ? 0ull : total;
   const unsigned long long i_first = P.front_weight_only ? n_front : 0ull;  // weight_kernel owns the front region
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const unsigned long long written = P.cand_chunk ? P.counters[3] + P.counters[4] : total;
-    const unsigned long long certain = P.cand_chunk ? P.counters[3]
-                                                    : ((sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total));
+    const unsigned long long written = total;
+    const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
     const unsigned long long tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
     if (P.accumulate_stats) {  // launches of one stream run one after the other: plain read-modify-write
       P.stats->candidates += written, P.stats->certain_candidates += certain, P.stats->tests += tests;
@@ -947,7 +994,6 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   for (unsigned long long i = i_first + (unsigned long long)blockIdx.x * kExactThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kExactThreads) {
     const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
-    if (e.y == 0xFFFFFFFFu) continue;  // a slot its warp left unused
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
     const bool certain = (e.y & kCandCertain) != 0u;  // K1a found the ray >= certain_mm inside one slit on both sides
@@ -1114,7 +1160,6 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
   for (unsigned long long i = (unsigned long long)blockIdx.x * kWeightThreads + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * kWeightThreads) {
     const uint2 e = P.cand[i];
-    if (e.y == 0xFFFFFFFFu) continue;  // a slot its warp left unused
     const unsigned int vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask);
     // voxel position (lattice.cuh: lattice_point), the index arithmetic by multiplication
@@ -1259,7 +1304,16 @@ size_t visibility_workspace_bytes(const DeviceScene& sc, long long n_vox, double
   double rays = (double)n_vox * sc.n_crystal;
   unsigned long long cap = (unsigned long long)(rays * frac) + 1;
   if (!sc.filter_disabled) cap = std::max(cap, 1ull << 20);
-  return 256 + cap * sizeof(uint2);
+  // [256 B counters][ray list: cap x 8 B][interval records: cap x 16 B].  An interval holds at least one ray, so a
+  // record list as long as the ray list cannot overflow before the ray list does (coarse lattices: ~1.3 rays per interval).
+  return 256 + cap * (sizeof(uint2) + sizeof(uint4));
+}
+
+// the split of a workspace of `bytes` bytes into ray list and record list (the inverse of the sizing above)
+static void split_workspace(size_t bytes, unsigned long long& cap, unsigned long long& rec_cap) {
+  const size_t body = bytes - 256;
+  cap = std::max<size_t>(1, body / (sizeof(uint2) + sizeof(uint4)));
+  rec_cap = (body - cap * sizeof(uint2)) / sizeof(uint4);
 }
 
 int voxels_pack(const ComScene* scene, const double* vox_xyz, long long vox_begin, long long vox_end, float4* out,
@@ -1317,7 +1371,7 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
     set_error("com_visibility_weights: at most 2^32-1 voxels per call (got %lld); split the range", n_vox);
     return COM_E_BADARG;
   }
-  if (workspace_bytes < 256 + sizeof(uint2)) {
+  if (workspace_bytes < 256 + 64) {
     set_error("workspace too small");
     return COM_E_NOMEM;
   }
@@ -1343,7 +1397,7 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
   const bool lattice_kernel = lattice_h != nullptr && lattice_h->nz >= 1 &&
                               lattice_h->nx * lattice_h->ny * lattice_h->nz < (1ll << 32);
   const int n_groups = P.sc.n_crystal_padded / 32;
-  const bool interval_kernel = lattice_kernel && P.sc.interval_filter != 0;
+  const bool interval_kernel = lattice_kernel && P.sc.interval_filter != 0 && lattice_h->nz < 65536;  // 16-bit lengths
   if (interval_kernel) {
     for (int i = 0; i < 3; ++i) P.dz[i] = (float)(lattice_h->step[2] * lattice_h->rotation[6 + i]);
     const long long nz = lattice_h->nz;
@@ -1373,7 +1427,9 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
   }
   P.counters = reinterpret_cast<unsigned long long*>(workspace);
   P.cand = reinterpret_cast<uint2*>(static_cast<char*>(workspace) + 256);
-  P.cand_capacity = (workspace_bytes - 256) / sizeof(uint2);
+  split_workspace(workspace_bytes, P.cand_capacity, P.rec_capacity);
+  P.recs = reinterpret_cast<uint4*>(static_cast<char*>(workspace) + 256 + ((P.cand_capacity * sizeof(uint2) + 15) / 16) * 16);
+  if (reinterpret_cast<char*>(P.recs + P.rec_capacity) > static_cast<char*>(workspace) + workspace_bytes) --P.rec_capacity;
   P.w_out = w_out;
   P.nrays_out = nrays_out;
   P.rays_out = rays_out;
@@ -1418,12 +1474,6 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
   const long long items = (long long)P.n_tiles * P.n_super;  // lattice kernel: warp-level items
   const long long ctas_wanted = lattice_kernel ? (items + kLatticeWarps - 1) / kLatticeWarps : items;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ctas_wanted, (long long)sms * occ));
-  if (interval_kernel) {
-    // every warp may leave most of two chunks unused: keep that below ~1/8 of the list
-    const unsigned long long warps = (unsigned long long)grid * kLatticeWarps;
-    const unsigned long long c = P.cand_capacity / (warps * 16ull);
-    P.cand_chunk = (int)std::max<unsigned long long>(32, std::min<unsigned long long>(2048, c / 32 * 32));
-  }
   // the weight-only kernel takes the front region of the list when the filter can vouch for whole rays: the interval
   // kernel always, the per-ray lattice kernel when the scene has certain regions for every aperture (the detector image
   // needs the fp64 detector hit: everything then goes through the exact kernel)
@@ -1435,9 +1485,14 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
     timing_collect();
     cudaEventRecord(g_ev[0], stream);
   }
-  if (interval_kernel)
+  if (interval_kernel) {
     interval_kernel_lattice<<<grid, threads, 0, stream>>>(P);
-  else if (lattice_kernel)
+    // interval records -> per-ray list (grid-stride over batches of 256 records; the count is only known on the device)
+    const unsigned long long batches = (std::min<unsigned long long>(P.rec_capacity, (unsigned long long)n_vox * P.sc.n_crystal) +
+                                        kExpandThreads - 1) / kExpandThreads;
+    expand_kernel<<<(unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>(batches, (unsigned long long)sms * 8)),
+                    kExpandThreads, 0, stream>>>(P);
+  } else if (lattice_kernel)
     filter_kernel_lattice<<<grid, threads, 0, stream>>>(P);
   else
     filter_kernel<<<grid, threads, 0, stream>>>(P);

@@ -59,7 +59,7 @@ def main():
         for _ in range(a.repeat):
             if img is not None:
                 img.zero_()
-            sum_w, vis, rays, cand, near, ms_total, chunks, ktimes = 0.0, 0, 0, 0, 0, 0.0, [], []
+            sum_w, vis, rays, cand, near, ms_total, chunks, ktimes, cert = 0.0, 0, 0, 0, 0, 0.0, [], [], 0
             for j, lo in enumerate(range(0, P, a.chunk)):
                 if only and j not in only:
                     continue
@@ -87,12 +87,13 @@ def main():
                 vis += st["visible_voxels"]
                 rays += st["passing_rays"]
                 cand += st["candidates"]
+                cert += st["certain_candidates"]
                 near += st["near_edge_rays"]
                 del plan
             tests = P * a.h * a.l
             rec = {"element": el, "mode": a.mode, "spacing_mm": a.spacing, "lattice": [lat.nx, lat.ny, lat.nz], "voxels": P, "tests": tests,
                    "ms": ms_total, "tests_per_s": tests / (ms_total * 1e-3), "visible_voxels": vis, "passing_rays": rays,
-                   "fp64_candidates": cand, "near_edge_rays": near, "sum_w": sum_w,
+                   "fp64_candidates": cand, "certain_candidates": cert, "near_edge_rays": near, "sum_w": sum_w,
                    "sum_w_times_voxel_volume_mm3": sum_w * a.spacing**3, "chunk_ms": chunks}
             if a.kernel_times:
                 rec["chunk_filter_ms_weight_ms_exact_ms_candidates_passing"] = ktimes

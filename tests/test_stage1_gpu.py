@@ -409,7 +409,7 @@ def test_edge_cases_empty_range_overflow_and_bad_arguments(sims):
     w = torch.empty(n, dtype=torch.float64, device="cuda")
     nr = torch.empty(n, dtype=torch.int32, device="cuda")
     st = torch.zeros(_lib.N_STATS, dtype=torch.int64, device="cuda")
-    ws = torch.empty(256 + 8 * 100, dtype=torch.uint8, device="cuda")  # room for 100 candidates only
+    ws = torch.empty(256 + 24 * 100, dtype=torch.uint8, device="cuda")  # room for 100 candidates (and 100 interval records) only
     ls = lattice_struct(lat)
     rc = lib.com_visibility_weights(sim.scene.handle, C.byref(ls), None, lo, hi, C.c_void_p(w.data_ptr()),
                                     C.c_void_p(nr.data_ptr()), None, 0, None, None, None, 0, C.c_void_p(st.data_ptr()),
