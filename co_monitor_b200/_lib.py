@@ -197,6 +197,7 @@ def _declare(lib):
     lib.com_scene_filter_tables_host.argtypes = [C.POINTER(ComSceneDesc), C.POINTER(i32), vp, vp, vp, vp, vp]
     lib.com_scene_interval_tables_host.argtypes = [C.POINTER(ComSceneDesc), vp, C.POINTER(i32), vp, vp, vp, C.POINTER(i32)]
     lib.com_scene_port_edges_host.argtypes = [C.POINTER(ComSceneDesc), vp, C.POINTER(i32)]
+    lib.com_scene_detector_edges_host.argtypes = [C.POINTER(ComSceneDesc), vp, C.POINTER(i32)]
     lib.com_scene_filter_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), dp, dp]
     lib.com_visibility_workspace_bytes.restype = C.c_size_t
     lib.com_visibility_workspace_bytes.argtypes = [vp, i64, C.c_double]
@@ -280,7 +281,7 @@ EXPORTED_SYMBOLS = [
     "com_weight_histogram_mm", "com_histogram_rows", "com_reff_resample", "com_reff_quadratic",
     "com_write_stage1_csv", "com_format_float_repr", "com_scene_filter_certain_host",
     "com_emissivity_integrate_indexed_host", "com_emissivity_integrate_indexed_host_tables",
-    "com_scene_interval_tables_host", "com_scene_port_edges_host",
+    "com_scene_interval_tables_host", "com_scene_port_edges_host", "com_scene_detector_edges_host",
     "com_visibility_weights_host_scene", "com_visible_weights_host_scene",
     "com_volume_create", "com_volume_destroy", "com_volume_voxels", "com_volume_chunk", "com_volume_reff_mm",
     "com_volume_set_reff_resampled", "com_volume_set_reff_quadratic", "com_volume_histograms",

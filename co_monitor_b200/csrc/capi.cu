@@ -383,6 +383,19 @@ int com_scene_port_edges_host(const ComSceneDesc* desc_h, float* edges_out64, in
   return COM_OK;
 }
 
+int com_scene_detector_edges_host(const ComSceneDesc* desc_h, float* edges_out32, int32_t* n_edges_out) {
+  if (!desc_h || !edges_out32 || !n_edges_out) {
+    com::set_error("com_scene_detector_edges_host: null argument");
+    return COM_E_BADARG;
+  }
+  com::HostScene hs;
+  int rc = com::build_host_scene(*desc_h, hs);
+  if (rc) return rc;
+  std::memcpy(edges_out32, hs.dev.det_edge, sizeof(hs.dev.det_edge));
+  *n_edges_out = hs.dev.n_det_edge;
+  return COM_OK;
+}
+
 int com_scene_filter_info(const ComScene* scene, int32_t* slit_filter, int32_t* filter_disabled, double* slit_period_mm,
                           double* eps_mm) {
   if (!scene) return COM_E_BADARG;

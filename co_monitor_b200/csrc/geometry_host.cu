@@ -411,6 +411,11 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
         dv.slit_edge[side][k] = make_float4((float)ap.edge[k][0], (float)ap.edge[k][1], (float)(ap.edge[k][2] + eps),
                                             (float)(ap.edge[k][2] - safe));
     }
+    dv.n_det_edge = (okd && det.n_edges <= 8) ? det.n_edges : 0;
+    for (int k = 0; k < dv.n_det_edge; ++k) {  // x = xc + hw Xs / W, y = yc + hh Ys / W
+      const double A = det.edge[k][0] * hw, B = det.edge[k][1] * hh, Cc = det.edge[k][0] * xc + det.edge[k][1] * yc + det.edge[k][2];
+      dv.det_edge[k] = make_float4((float)A, (float)B, (float)(Cc + eps), (float)(Cc - safe));
+    }
     dv.n_port_edge = (okq && port.n_edges <= 16) ? port.n_edges : 0;
     for (int k = 0; k < dv.n_port_edge; ++k)
       dv.port_edge[k] = make_float4((float)port.edge[k][0], (float)port.edge[k][1], (float)(port.edge[k][2] + eps),

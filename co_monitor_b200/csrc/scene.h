@@ -80,6 +80,11 @@ struct DeviceScene {
   // inner rectangle port_inner, which vouches for fewer rays.
   float4 port_edge[16];
   int n_port_edge;
+  // edges of the detector polygon in the SCALED frame of det_forms: (A, B, C + eps, C - certain_mm) with
+  // A Xs + B Ys + C W >= 0 (times the sign of W) inside.  A skewed detector section loses a tenth of its area to the inner
+  // rectangle det_inner (channel O); the edges lose nothing.  n_det_edge = 0: det_inner is used.
+  float4 det_edge[8];
+  int n_det_edge;
   const float4* port_forms;      // [Cp][3]: X', Y', W on the port plane
   // reflectivity profile at every value the rounded angle can take: refl_table[m] = refl_max * exp(-(aoi - aoi0)^2 /
   // (2 sigma^2)) with aoi = (180 - m / 100) / 2, m = rint(deg * 100) in 0..18000 (simulation.py:520-531, 564-577)

@@ -140,9 +140,18 @@ __device__ __forceinline__ bool certain_everywhere(const DeviceScene& sc, const 
   const float xs = form(__ldg(&sc.det_forms[cj]), p), ys = form(__ldg(&sc.det_forms[Cp + cj]), p);
   const float wd = form(__ldg(&sc.det_forms[2 * Cp + cj]), p);
   const float sd = wd < 0.f ? -1.f : 1.f;
-  if (!(fabsf(wd) > 1e-3f && ratio_inside(sd, xs, wd, sc.det_inner.xlo, sc.det_inner.xhi) &&
-        ratio_inside(sd, ys, wd, sc.det_inner.ylo, sc.det_inner.yhi)))
+  if (!(fabsf(wd) > 1e-3f)) return false;
+  if (sc.n_det_edge > 0) {
+    float md = 0.f;
+    for (int q = 0; q < sc.n_det_edge; ++q) {
+      const float4 ed = sc.det_edge[q];
+      md = fminf(md, sd * fmaf(ed.x, xs, fmaf(ed.y, ys, ed.w * wd)));
+    }
+    if (md < 0.f) return false;
+  } else if (!(ratio_inside(sd, xs, wd, sc.det_inner.xlo, sc.det_inner.xhi) &&
+               ratio_inside(sd, ys, wd, sc.det_inner.ylo, sc.det_inner.yhi))) {
     return false;
+  }
   const float4* pf = sc.port_forms + 3 * cj;
   const float Xq = form(__ldg(pf), p), Yq = form(__ldg(pf + 1), p), Wq = form(__ldg(pf + 2), p);
   const float sp = Wq < 0.f ? -1.f : 1.f;
@@ -697,8 +706,15 @@ __global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(co
       // certain part of the detector interval
       // (inner bounds start unbounded: only thresholds that really clip are moved inwards by 1e-3 voxel below)
       float li = -1e9f, hi_i = 1e9f;
-      clip_ratio(li, hi_i, s, xs0, dxs, w0, dws, sc.det_inner.xlo, sc.det_inner.xhi);
-      clip_ratio(li, hi_i, s, ys0, dys, w0, dws, sc.det_inner.ylo, sc.det_inner.yhi);
+      if (sc.n_det_edge > 0) {  // the detector polygon edge by edge, inner offsets
+        for (int q = 0; q < sc.n_det_edge; ++q) {
+          const float4 ed = sc.det_edge[q];
+          clip_halfline(li, hi_i, s * fmaf(ed.x, xs0, fmaf(ed.y, ys0, ed.w * w0)), s * fmaf(ed.x, dxs, fmaf(ed.y, dys, ed.w * dws)));
+        }
+      } else {
+        clip_ratio(li, hi_i, s, xs0, dxs, w0, dws, sc.det_inner.xlo, sc.det_inner.xhi);
+        clip_ratio(li, hi_i, s, ys0, dys, w0, dws, sc.det_inner.ylo, sc.det_inner.yhi);
+      }
       if (!(sc.det_inner.xlo <= sc.det_inner.xhi)) li = 1.f, hi_i = 0.f;
 
       // ---- collimator: which slits can the detector interval reach ----
@@ -1492,8 +1508,9 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
                                         kExpandThreads - 1) / kExpandThreads;
     expand_kernel<<<(unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>(batches, (unsigned long long)sms * 8)),
                     kExpandThreads, 0, stream>>>(P);
-  } else if (lattice_kernel)
+  } else if (lattice_kernel) {
     filter_kernel_lattice<<<grid, threads, 0, stream>>>(P);
+  }
   else
     filter_kernel<<<grid, threads, 0, stream>>>(P);
   COM_CUDA(cudaGetLastError());

@@ -167,8 +167,12 @@ class ChannelScene:
         n_pe = C.c_int32()
         _lib.check(self._lib.com_scene_port_edges_host(C.byref(self.desc), C.c_void_p(pedges.ctypes.data), C.byref(n_pe)),
                    "com_scene_port_edges_host")
+        dedges = np.zeros((8, 4), np.float32)
+        n_de = C.c_int32()
+        _lib.check(self._lib.com_scene_detector_edges_host(C.byref(self.desc), C.c_void_p(dedges.ctypes.data), C.byref(n_de)),
+                   "com_scene_detector_edges_host")
         return dict(det_forms=det, slit_forms=slit, rect_crys=rects[:4], rect_plasma=rects[4:], period=period.value,
-                    port_edges=pedges[: n_pe.value],
+                    port_edges=pedges[: n_pe.value], det_edges=dedges[: n_de.value],
                     det_inner=r12[:4], port_outer=r12[4:8], port_inner=r12[8:], interval_filter=bool(ivl.value), port_forms=port,
                     slit_edges=[edges[0, :n_edges[0]], edges[1, :n_edges[1]]], certain_off=bool(coff.value),
                     inner_crys=cert[:4], inner_plasma=cert[4:8], certain_mm=float(cert[8]),

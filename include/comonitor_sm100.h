@@ -192,6 +192,9 @@ int com_scene_interval_tables_host(const ComSceneDesc* desc_h, float* rects12, i
 /* The port polygon as the filters' certain test uses it: edges_out64 [16][4] = (a, b, c + eps, c - certain_mm) per edge
  * with a x + b y + c >= 0 inside (aperture frame, mm), *n_edges_out how many are used (0: the inner rectangle is used). */
 int com_scene_port_edges_host(const ComSceneDesc* desc_h, float* edges_out64, int32_t* n_edges_out);
+/* The detector polygon likewise, in the SCALED frame of the detector forms (|Xs|, |Ys| <= |W| is the grown bounding
+ * rectangle): edges_out32 [8][4] = (A, B, C + eps, C - certain_mm) with A Xs + B Ys + C W >= 0 (times sign W) inside. */
+int com_scene_detector_edges_host(const ComSceneDesc* desc_h, float* edges_out32, int32_t* n_edges_out);
 
 /* what the FP32 filter was built with (any output pointer may be NULL; no counterpart in the reference, whose slits
  * are tested one by one, simulation.py:344-369): whether the collimator was found periodic
