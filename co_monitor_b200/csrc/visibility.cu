@@ -1109,7 +1109,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
       ++n_pass;
       atomicAdd(&P.w_out[vloc], w);
       if (P.nrays_out) {
-        if (atomicAdd(&P.nrays_out[vloc], 1u) == 0u) ++n_vis;
+        atomicAdd(&P.nrays_out[vloc], 1u);  // result unused: a reduction, nobody waits for the round trip to L2
       }
       if (P.hist_out) {
         const int bin = P.reff_bin[P.vox_begin + vloc];
@@ -1214,7 +1214,7 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     ++n_pass;
     atomicAdd(&P.w_out[vloc], w);
     if (P.nrays_out) {
-      if (atomicAdd(&P.nrays_out[vloc], 1u) == 0u) ++n_vis;
+      atomicAdd(&P.nrays_out[vloc], 1u);  // result unused: a reduction, nobody waits for the round trip to L2
     }
     if (P.hist_out) {
       const int bin = P.reff_bin[P.vox_begin + vloc];
@@ -1246,6 +1246,28 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[1]);
     if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[2]);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Visible voxels of a launch = voxels with a ray count > 0, counted once both fp64 kernels are done (4 B per voxel read;
+// the kernels above add to the counts without waiting for the old value).
+__global__ void __launch_bounds__(256) count_visible_kernel(const unsigned int* __restrict__ nrays, long long n, ComStats* stats) {
+  unsigned int c = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four independent coalesced loads in flight
+    const unsigned int a = __ldcs(nrays + i), b = __ldcs(nrays + i + stride), d = __ldcs(nrays + i + 2 * stride),
+                       e = __ldcs(nrays + i + 3 * stride);
+    c += (a != 0u) + (b != 0u) + (d != 0u) + (e != 0u);
+  }
+  for (; i < n; i += stride) c += __ldcs(nrays + i) != 0u;
+  for (int off = 16; off; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+  __shared__ unsigned int s_c;
+  if (threadIdx.x == 0) s_c = 0u;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_c) atomicAdd((unsigned long long*)&stats->visible_voxels, (unsigned long long)s_c);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1538,6 +1560,9 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
     }
     if (g_timing_on) cudaEventRecord(g_ev[2], stream);
     exact_kernel<<<blocks, kExactThreads, smem, stream>>>(P);
+    if (nrays_out)
+      count_visible_kernel<<<(unsigned int)std::max<long long>(1, std::min<long long>((n_vox + 1023) / 1024, (long long)sms * 8)),
+                             256, 0, stream>>>(nrays_out, n_vox, stats_out);
   }
   COM_CUDA(cudaGetLastError());
   if (g_timing_on) {
