@@ -53,7 +53,8 @@ struct K1Params {
   uint2* cand;       // (voxel_local, crystal) pairs
   unsigned long long cand_capacity;
   unsigned long long* counters;  // [0] slots used at the front (certain), [1] next work item, [2] slots used at the back,
-                                 // [5] interval records reserved, [6] rays in all interval records
+                                 // [5] interval records reserved, [6] rays in all interval records, [7] certain rays the
+                                 // weight-only kernel took straight from the records
   double* w_out;
   unsigned int* nrays_out;
   ComRayRecord* rays_out;
@@ -65,6 +66,9 @@ struct K1Params {
   unsigned long long magic_nz, magic_nx, magic_cpb;  // weight kernel: multipliers replacing divisions by nz, nx, cols per block
   uint4* recs;            // column-interval kernel: one 16-byte record per interval (layout at the kernel's emit)
   unsigned long long rec_capacity;
+  int records_to_weight;  // 1: the weight-only kernel reads the certain parts straight from the records (expand_kernel then
+                          // lists the uncertain rays only, counters[0] stays 0 and counters[7] counts the certain rays)
+  double dz_d[3];         // position step between z-consecutive voxels, fp64
   int front_weight_only;  // 1: the front region of the list was produced by the column-interval kernel and is handled by
                           // weight_kernel (the exact kernel then takes the back region only)
   int accumulate_stats;  // 1: add this launch's counters to *stats instead of overwriting them (whole-volume runs)
@@ -602,7 +606,7 @@ __device__ __forceinline__ float dz_dot(const float4 g, const float* dz) {
   return fmaf(g.x, dz[0], fmaf(g.y, dz[1], g.z * dz[2]));
 }
 
-__global__ void __launch_bounds__(kLatticeWarps * 32) interval_kernel_lattice(const __grid_constant__ K1Params P) {
+__global__ void __launch_bounds__(kLatticeWarps * 32, 3) interval_kernel_lattice(const __grid_constant__ K1Params P) {
   __shared__ float4 s_base[kLatticeWarps][kColsPerItem];  // column base positions (recentred FP32, w = 1)
   __shared__ uint4 s_out[kLatticeWarps][64];             // interval records waiting for a 32-wide flush
 
@@ -860,8 +864,9 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
     if (threadIdx.x == 0) s_c[0] = 0u, s_u[0] = 0u;
     __syncthreads();
     const unsigned int Tc = s_c[kExpandThreads], Tu = s_u[kExpandThreads];
+    const bool list_certain = P.records_to_weight == 0;
     if (threadIdx.x == 0) {
-      s_pos[0] = Tc ? atomicAdd(&P.counters[0], (unsigned long long)Tc) : 0ull;
+      s_pos[0] = (Tc && list_certain) ? atomicAdd(&P.counters[0], (unsigned long long)Tc) : 0ull;
       s_pos[1] = Tu ? atomicAdd(&P.counters[2], (unsigned long long)Tu) : 0ull;
     }
     __syncthreads();
@@ -874,7 +879,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
       }
       return lo;
     };
-    for (unsigned int r = threadIdx.x; r < Tc; r += kExpandThreads) {
+    for (unsigned int r = threadIdx.x; list_certain && r < Tc; r += kExpandThreads) {
       const int q = owner(s_c, r);
       const uint4 e = s_rec[q];
       const unsigned long long pos = pc + r;
@@ -970,8 +975,9 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   const unsigned long long n = overflow ? 0ull : total;
   const unsigned long long i_first = P.front_weight_only ? n_front : 0ull;  // weight_kernel owns the front region
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const unsigned long long written = total;
-    const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total);
+    const unsigned long long direct = P.records_to_weight ? P.counters[7] : 0ull;  // certain rays that never were listed
+    const unsigned long long written = total + direct;
+    const unsigned long long certain = (sc.filter_disabled || P.tile_voxels != 0) ? 0ull : min(P.counters[0], total) + direct;
     const unsigned long long tests = (unsigned long long)P.n_vox * (unsigned long long)sc.n_crystal;
     if (P.accumulate_stats) {  // launches of one stream run one after the other: plain read-modify-write
       P.stats->candidates += written, P.stats->certain_candidates += certain, P.stats->tests += tests;
@@ -1164,6 +1170,26 @@ __device__ __forceinline__ unsigned int fast_div(unsigned int n, unsigned long l
   return d == 1u ? n : (unsigned int)__umul64hi((unsigned long long)n, m);
 }
 
+// distance^2, rounded angle (as m = rint(100 deg)) and weight of one ray from d = c - p and the crystal normal
+__device__ __forceinline__ double certain_ray_weight(const DeviceScene& sc, const double* __restrict__ table, const D3 d,
+                                                     const D3 nrm, double& dd, double& m, unsigned int& n_round) {
+  dd = dot(d, d);
+  const double dn = dot(d, nrm);
+  const double cosang = 2.0 * (dn * dn) / dd - 1.0;
+  const double deg100 = acos(cosang) * (180.0 / 3.141592653589793) * 100.0;
+  m = rint(deg100);
+  if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
+  const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * dd);
+  double prof;
+  if (m >= 0.0 && m <= 18000.0) {
+    prof = table[(int)m];
+  } else {  // NaN angle (cosine rounded beyond 1): what the formula gives
+    const double aoi = (180.0 - m / 100.0) / 2.0, da = aoi - sc.aoi0;
+    prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
+  }
+  return fraction * prof;
+}
+
 __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_constant__ K1Params P) {
   const DeviceScene& sc = P.sc;
   const ComLattice& L = P.vox.lat;
@@ -1197,20 +1223,8 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     // decides).  The rounded angle can differ from the reference's only when deg * 100 is within rounding distance of a
     // half-integer; rays within 1e-9 of one are counted.
     const D3 d = c - p;
-    const double dd = dot(d, d), dn = dot(d, nrm);
-    const double cosang = 2.0 * (dn * dn) / dd - 1.0;
-    const double deg100 = acos(cosang) * (180.0 / 3.141592653589793) * 100.0;
-    const double m = rint(deg100);
-    if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
-    const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * dd);
-    double prof;
-    if (m >= 0.0 && m <= 18000.0) {
-      prof = table[(int)m];
-    } else {  // NaN angle (cosine rounded beyond 1): what the formula gives
-      const double aoi = (180.0 - m / 100.0) / 2.0, da = aoi - sc.aoi0;
-      prof = sc.refl_max * exp(-(da * da) / (2.0 * (sc.refl_sigma * sc.refl_sigma)));
-    }
-    const double w = fraction * prof;
+    double dd, m;
+    const double w = certain_ray_weight(sc, table, d, nrm, dd, m, n_round);
     ++n_pass;
     atomicAdd(&P.w_out[vloc], w);
     if (P.nrays_out) {
@@ -1245,6 +1259,115 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
     if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[1]);
     if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1w on the interval records themselves: no per-ray list is written or read for the certain rays.  A block takes 256
+// records; the thread that loaded record q prepares what its rays share - d0 = c - p of the first certain voxel (the
+// lattice formula once per record) and the crystal normal - in shared memory; ray r of the block finds its record by
+// a binary search in the scanned lengths and is d0 - j dz, j voxels further along the column.
+__global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __grid_constant__ K1Params P) {
+  __shared__ unsigned int s_c[kWeightThreads + 1];
+  __shared__ unsigned int s_warp[kWeightThreads / 32];
+  __shared__ unsigned int s_v[kWeightThreads], s_ci[kWeightThreads];
+  __shared__ double s_d0[kWeightThreads][3], s_n[kWeightThreads][3];
+  __shared__ unsigned int s_acc[2];
+  const DeviceScene& sc = P.sc;
+  const ComLattice& L = P.vox.lat;
+  const unsigned long long reserved = P.counters[5];
+  if (reserved > P.rec_capacity) return;  // record overflow: expand_kernel reports it, nothing may be accumulated
+  const double* __restrict__ table = sc.refl_table;
+  const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx, cpb = L.shard_cols_per_block > 0 ? (unsigned int)L.shard_cols_per_block : 1u;
+  const bool sharded = L.shard_count > 1 && L.shard_cols_per_block > 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const D3 dz = {P.dz_d[0], P.dz_d[1], P.dz_d[2]};
+  unsigned int n_pass = 0, n_round = 0;
+  if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+  for (unsigned long long first = (unsigned long long)blockIdx.x * kWeightThreads; first < reserved;
+       first += (unsigned long long)gridDim.x * kWeightThreads) {
+    const unsigned long long i = first + threadIdx.x;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (i < reserved) rec = P.recs[i];
+    const unsigned int c_len = rec.w;
+    unsigned int ic = c_len;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int a = __shfl_up_sync(0xffffffffu, ic, off);
+      if (lane >= off) ic += a;
+    }
+    if (lane == 31) s_warp[warp] = ic;
+    if (c_len) {  // what the rays of this record share
+      const unsigned int vloc = rec.x + (rec.z >> 16);
+      const int ci = (int)(rec.y & kCandCrystalMask);
+      const unsigned int f = (unsigned int)P.vox_begin + vloc;
+      unsigned int col = fast_div(f, P.magic_nz, nz);
+      const unsigned int iz = f - col * nz;
+      if (sharded) {
+        const unsigned int lb = fast_div(col, P.magic_cpb, cpb);
+        col = (lb * (unsigned int)L.shard_count + (unsigned int)L.shard_index) * cpb + (col - lb * cpb);
+      }
+      const unsigned int iy = fast_div(col, P.magic_nx, nx), ix = col - iy * nx;
+      const D3 p = lattice_point(L, ix, iy, iz);
+      const D3 c = ld3(sc.crystal_xyz + 3 * ci), nrm = ld3(sc.crystal_normal + 3 * ci);
+      s_d0[threadIdx.x][0] = c.x - p.x, s_d0[threadIdx.x][1] = c.y - p.y, s_d0[threadIdx.x][2] = c.z - p.z;
+      s_n[threadIdx.x][0] = nrm.x, s_n[threadIdx.x][1] = nrm.y, s_n[threadIdx.x][2] = nrm.z;
+      s_v[threadIdx.x] = vloc, s_ci[threadIdx.x] = (unsigned int)ci;
+    }
+    __syncthreads();
+    unsigned int bc = 0;
+    for (int q = 0; q < warp; ++q) bc += s_warp[q];
+    s_c[threadIdx.x + 1] = bc + ic;
+    if (threadIdx.x == 0) s_c[0] = 0u;
+    __syncthreads();
+    const unsigned int Tc = s_c[kWeightThreads];
+    for (unsigned int r = threadIdx.x; r < Tc; r += kWeightThreads) {
+      int lo = 0, hi = kWeightThreads - 1;  // largest q with s_c[q] <= r
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_c[mid] <= r) lo = mid; else hi = mid - 1;
+      }
+      const int q = lo;
+      const unsigned int j = r - s_c[q];
+      const unsigned int vloc = s_v[q] + j;
+      const double jf = (double)j;
+      // d = c - (p + j dz): one rounding per component on top of the record's own d0
+      const D3 d = {fma(-jf, dz.x, s_d0[q][0]), fma(-jf, dz.y, s_d0[q][1]), fma(-jf, dz.z, s_d0[q][2])};
+      const D3 nrm = {s_n[q][0], s_n[q][1], s_n[q][2]};
+      double dd, m;
+      const double w = certain_ray_weight(sc, table, d, nrm, dd, m, n_round);
+      ++n_pass;
+      atomicAdd(&P.w_out[vloc], w);
+      if (P.nrays_out) atomicAdd(&P.nrays_out[vloc], 1u);
+      if (P.hist_out) {
+        const int bin = P.reff_bin[P.vox_begin + vloc];
+        if (bin < P.n_bins) atomicAdd(&P.hist_out[bin], w);
+      }
+      if (P.rays_out) {
+        const unsigned long long pos = atomicAdd(P.rays_count, 1ull);
+        if ((long long)pos < P.rays_capacity)
+          P.rays_out[pos] = ComRayRecord{(P.vox_begin + (long long)vloc) * (long long)sc.n_crystal + (long long)s_ci[q], sqrt(dd),
+                                         (180.0 - m / 100.0) / 2.0, w};
+      }
+    }
+    __syncthreads();  // the shared tables are rewritten by the next batch
+  }
+  for (int off = 16; off; off >>= 1) {
+    n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);
+    n_round += __shfl_down_sync(0xffffffffu, n_round, off);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    if (n_pass) atomicAdd(&s_acc[0], n_pass);
+    if (n_round) atomicAdd(&s_acc[1], n_round);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_acc[0]) {
+      atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
+      atomicAdd(&P.counters[7], (unsigned long long)s_acc[0]);
+    }
+    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[1]);
   }
 }
 
@@ -1523,6 +1646,14 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
     timing_collect();
     cudaEventRecord(g_ev[0], stream);
   }
+  P.records_to_weight = (interval_kernel && P.front_weight_only) ? 1 : 0;
+  if (lattice_h)
+    for (int i = 0; i < 3; ++i) P.dz_d[i] = lattice_h->step[2] * lattice_h->rotation[6 + i];
+  if (P.front_weight_only) {
+    auto magic = [](long long d) { return d >= 2 ? ~0ull / (unsigned long long)d + 1ull : 0ull; };
+    P.magic_nz = magic(lattice_h->nz), P.magic_nx = magic(lattice_h->nx);
+    P.magic_cpb = magic(std::max<long long>(1, lattice_h->shard_cols_per_block));
+  }
   if (interval_kernel) {
     interval_kernel_lattice<<<grid, threads, 0, stream>>>(P);
     // interval records -> per-ray list (grid-stride over batches of 256 records; the count is only known on the device)
@@ -1547,10 +1678,14 @@ int visibility_launch_packed(const ComScene* scene, const ComLattice* lattice_h,
     const unsigned long long slots = std::min<unsigned long long>(P.cand_capacity, (unsigned long long)n_vox * P.sc.n_crystal);
     const unsigned int blocks = (unsigned int)std::max<unsigned long long>(
         1, std::min<unsigned long long>((slots + kExactThreads - 1) / kExactThreads, (unsigned long long)sms * occ_x * 4ull));
-    if (P.front_weight_only) {
-      auto magic = [](long long d) { return d >= 2 ? ~0ull / (unsigned long long)d + 1ull : 0ull; };
-      P.magic_nz = magic(lattice_h->nz), P.magic_nx = magic(lattice_h->nx);
-      P.magic_cpb = magic(std::max<long long>(1, lattice_h->shard_cols_per_block));
+    if (P.records_to_weight) {
+      int occ_w = 0;
+      COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, weight_kernel_records, kWeightThreads, 0));
+      if (occ_w < 1) occ_w = 1;
+      const unsigned long long batches = (std::min<unsigned long long>(P.rec_capacity, slots) + kWeightThreads - 1) / kWeightThreads;
+      weight_kernel_records<<<(unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>(batches, (unsigned long long)sms * occ_w * 2ull)),
+                              kWeightThreads, 0, stream>>>(P);
+    } else if (P.front_weight_only) {
       int occ_w = 0;
       COM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, weight_kernel, kWeightThreads, 0));
       if (occ_w < 1) occ_w = 1;
