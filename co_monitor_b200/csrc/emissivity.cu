@@ -363,15 +363,18 @@ __global__ void __launch_bounds__(kK2Threads) weight_histogram_kernel(const K2Pa
 // (every passing ray adds a strictly positive weight), which is the set the reference takes the maximum over.
 constexpr int kMmBins = 4096;
 
-__device__ __forceinline__ void bin_one(double* s_h, unsigned int b, double w) {
+__device__ __forceinline__ void bin_one(double* s_h, unsigned int b, double w, unsigned int& n_nonzero) {
+  n_nonzero += w != 0.0;
   if (w != 0.0 && b != 0xFFFFu) atomicAdd(&s_h[min(b, (unsigned int)(kMmBins - 1))], w);
 }
 
 __global__ void __launch_bounds__(kK2Threads) weight_histogram_mm_kernel(const uint16_t* __restrict__ reff_mm,
                                                                        const double* __restrict__ w, long long n_max,
                                                                        const unsigned long long* n_device,
-                                                                       double* __restrict__ hist_mm) {
+                                                                       double* __restrict__ hist_mm,
+                                                                       unsigned long long* nonzero_out) {
   __shared__ double s_h[kMmBins];
+  unsigned int nzc = 0;  // voxels with a non-zero weight seen by this thread (= visible voxels, see above)
   for (int k = threadIdx.x; k < kMmBins; k += kK2Threads) s_h[k] = 0.0;
   __syncthreads();
   const long long n = n_device ? (long long)min((unsigned long long)n_max, *n_device) : n_max;
@@ -391,20 +394,24 @@ __global__ void __launch_bounds__(kK2Threads) weight_histogram_mm_kernel(const u
       rb = __ldcs(r4 + j);
       b0 = __ldcs(w2 + 4 * j), b1 = __ldcs(w2 + 4 * j + 1), b2 = __ldcs(w2 + 4 * j + 2), b3 = __ldcs(w2 + 4 * j + 3);
     }
-    bin_one(s_h, ra.x & 0xFFFFu, a0.x), bin_one(s_h, ra.x >> 16, a0.y);
-    bin_one(s_h, ra.y & 0xFFFFu, a1.x), bin_one(s_h, ra.y >> 16, a1.y);
-    bin_one(s_h, ra.z & 0xFFFFu, a2.x), bin_one(s_h, ra.z >> 16, a2.y);
-    bin_one(s_h, ra.w & 0xFFFFu, a3.x), bin_one(s_h, ra.w >> 16, a3.y);
-    bin_one(s_h, rb.x & 0xFFFFu, b0.x), bin_one(s_h, rb.x >> 16, b0.y);
-    bin_one(s_h, rb.y & 0xFFFFu, b1.x), bin_one(s_h, rb.y >> 16, b1.y);
-    bin_one(s_h, rb.z & 0xFFFFu, b2.x), bin_one(s_h, rb.z >> 16, b2.y);
-    bin_one(s_h, rb.w & 0xFFFFu, b3.x), bin_one(s_h, rb.w >> 16, b3.y);
+    bin_one(s_h, ra.x & 0xFFFFu, a0.x, nzc), bin_one(s_h, ra.x >> 16, a0.y, nzc);
+    bin_one(s_h, ra.y & 0xFFFFu, a1.x, nzc), bin_one(s_h, ra.y >> 16, a1.y, nzc);
+    bin_one(s_h, ra.z & 0xFFFFu, a2.x, nzc), bin_one(s_h, ra.z >> 16, a2.y, nzc);
+    bin_one(s_h, ra.w & 0xFFFFu, a3.x, nzc), bin_one(s_h, ra.w >> 16, a3.y, nzc);
+    bin_one(s_h, rb.x & 0xFFFFu, b0.x, nzc), bin_one(s_h, rb.x >> 16, b0.y, nzc);
+    bin_one(s_h, rb.y & 0xFFFFu, b1.x, nzc), bin_one(s_h, rb.y >> 16, b1.y, nzc);
+    bin_one(s_h, rb.z & 0xFFFFu, b2.x, nzc), bin_one(s_h, rb.z >> 16, b2.y, nzc);
+    bin_one(s_h, rb.w & 0xFFFFu, b3.x, nzc), bin_one(s_h, rb.w >> 16, b3.y, nzc);
   }
   if (blockIdx.x == 0)  // the < 8 voxels left over
-    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += kK2Threads) bin_one(s_h, reff_mm[i], w[i]);
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += kK2Threads) bin_one(s_h, reff_mm[i], w[i], nzc);
   __syncthreads();
   for (int k = threadIdx.x; k < kMmBins; k += kK2Threads)
     if (s_h[k] != 0.0) atomicAdd(&hist_mm[k], s_h[k]);
+  if (nonzero_out) {
+    for (int off = 16; off; off >>= 1) nzc += __shfl_down_sync(0xffffffffu, nzc, off);
+    if ((threadIdx.x & 31) == 0 && nzc) atomicAdd(nonzero_out, (unsigned long long)nzc);
+  }
 }
 
 // Boundary cut and millimetre bin -> profile row on the small histogram (one block).
@@ -614,6 +621,24 @@ bool non_decreasing(const double* a, int n, int stride = 1) {
 }
 }  // namespace
 
+// com_weight_histogram_mm, also adding the number of voxels with a non-zero weight to *nonzero_out (device; null: not counted)
+namespace com {
+int weight_histogram_mm_count(const uint16_t* reff_mm, const double* w, long long n, const unsigned long long* n_device,
+                              double* hist_mm, unsigned long long* nonzero_out, cudaStream_t stream);
+}
+int com::weight_histogram_mm_count(const uint16_t* reff_mm, const double* w, long long n, const unsigned long long* n_device,
+                                   double* hist_mm, unsigned long long* nonzero_out, cudaStream_t stream) {
+  if (!reff_mm || !w || !hist_mm || n < 0 || (reinterpret_cast<uintptr_t>(reff_mm) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
+    com::set_error("com_weight_histogram_mm: null or not 16-byte aligned arguments");
+    return COM_E_BADARG;
+  }
+  if (n == 0) return COM_OK;
+  const int blocks = (int)std::min<long long>((n / 8 + com::kK2Threads - 1) / com::kK2Threads + 1, 148 * 6);
+  com::weight_histogram_mm_kernel<<<blocks, com::kK2Threads, 0, stream>>>(reff_mm, w, n, n_device, hist_mm, nonzero_out);
+  COM_CUDA(cudaGetLastError());
+  return COM_OK;
+}
+
 extern "C" {
 
 // Validates the description and lays all tables out in one fp64 blob; `dev` gets pointers relative to a null base
@@ -790,7 +815,7 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
     COM_CUDA(cudaMemsetAsync(hist_mm, 0, sizeof(double) * com::kMmBins, s));
     const int blocks = (int)std::min<long long>((n / 8 + com::kK2Threads - 1) / com::kK2Threads + 1, 148 * 6);
     com::weight_histogram_mm_kernel<<<blocks, com::kK2Threads, 0, s>>>(
-        reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm);
+        reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm, nullptr);
     com::histogram_rows_kernel<<<1, com::kK2Threads, 0, s>>>(P, hist_mm);
     COM_CUDA(cudaGetLastError());
   } else if (n > 0) {
@@ -808,17 +833,10 @@ int com_weight_histogram(const double* profile, int32_t K, int32_t profile_sorte
 
 int com_weight_histogram_mm(const uint16_t* reff_mm, const double* w, int64_t n, const uint64_t* n_device,
                             double* hist_mm, com_stream_t stream) {
-  if (!reff_mm || !w || !hist_mm || n < 0 || (reinterpret_cast<uintptr_t>(reff_mm) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
-    com::set_error("com_weight_histogram_mm: null or not 16-byte aligned arguments");
-    return COM_E_BADARG;
-  }
-  if (n == 0) return COM_OK;
-  const int blocks = (int)std::min<long long>((n / 8 + com::kK2Threads - 1) / com::kK2Threads + 1, 148 * 6);
-  com::weight_histogram_mm_kernel<<<blocks, com::kK2Threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm);
-  COM_CUDA(cudaGetLastError());
-  return COM_OK;
+  return com::weight_histogram_mm_count(reff_mm, w, n, reinterpret_cast<const unsigned long long*>(n_device), hist_mm, nullptr,
+                                        static_cast<cudaStream_t>(stream));
 }
+
 
 int com_histogram_rows(const double* profile, int32_t K, int32_t profile_sorted, double profile_reff_max,
                        const double* hist_mm, const double* mapped_reff_max, double* hist_rows_out,

@@ -362,12 +362,17 @@ int build_host_scene(const ComSceneDesc& d, HostScene& hs) {
     okc_slits = okc && okp;
   }
 
-  hs.refl_table.resize(18001);
+  hs.refl_table.resize(18001 + 18002);
   for (int m = 0; m <= 18000; ++m) {  // the expressions of the fp64 kernel, operation by operation
     const double aoi = (180.0 - (double)m / 100.0) / 2.0;
     const double da = aoi - dv.aoi0;
     hs.refl_table[m] = dv.refl_max * std::exp(-(da * da) / (2.0 * (dv.refl_sigma * dv.refl_sigma)));
   }
+  // ... followed by the cosines of the rounding boundaries: entry 18001 + j = cos((j - 0.5) / 100 degrees), j = 0..18001;
+  // rint(100 deg) = m  <=>  cos_bound[m + 1] < cos <= cos_bound[m]  (the cosine decreases with the angle)
+  for (int j = 0; j <= 18001; ++j)
+    hs.refl_table[18001 + j] = std::cos(((double)j - 0.5) * (3.141592653589793 / 18000.0));
+  hs.refl_table[18001] = 2.0, hs.refl_table[18001 + 18001] = -2.0;  // the angle lies in [0, 180] degrees: no boundary beyond
   const int Cp = dv.n_crystal_padded;
   hs.det_forms.assign((size_t)4 * 3 * Cp, 0.f);
   hs.slit_forms.assign((size_t)4 * 6 * Cp, 0.f);

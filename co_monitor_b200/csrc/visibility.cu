@@ -1176,9 +1176,32 @@ __device__ __forceinline__ double certain_ray_weight(const DeviceScene& sc, cons
   dd = dot(d, d);
   const double dn = dot(d, nrm);
   const double cosang = 2.0 * (dn * dn) / dd - 1.0;
-  const double deg100 = acos(cosang) * (180.0 / 3.141592653589793) * 100.0;
-  m = rint(deg100);
-  if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
+  // m = rint(100 deg(acos(cos))) without the fp64 arc cosine: an FP32 estimate (good to a few 1e-3 of a unit), then the
+  // decision in fp64 against the cosines of the two rounding boundaries, cos_bound[m + 1] < cos <= cos_bound[m].  Equal to
+  // rounding the fp64 angle except within ~1e-12 of a boundary; rays within 1e-9 of one are counted, as before
+  // (a boundary distance of 1e-9 units is at most 1e-9 * pi / 18000 in the cosine).
+  const double* __restrict__ cos_bound = table + 18001;
+  bool bracketed = false;
+  if (cosang >= -1.0 && cosang <= 1.0) {
+    int mi = __float2int_rn(acosf((float)cosang) * 5729.5779513082f);
+    mi = min(max(mi, 0), 18000);
+    double hi = cos_bound[mi], lo = cos_bound[mi + 1];
+#pragma unroll 1
+    for (int it = 0; it < 4 && !(lo < cosang && cosang <= hi); ++it) {
+      mi = cosang > hi ? max(mi - 1, 0) : min(mi + 1, 18000);
+      hi = cos_bound[mi], lo = cos_bound[mi + 1];
+    }
+    if (lo < cosang && cosang <= hi) {
+      bracketed = true;
+      m = (double)mi;
+      if (fmin(hi - cosang, cosang - lo) < 1e-9 * (3.141592653589793 / 18000.0)) ++n_round;
+    }
+  }
+  if (!bracketed) {  // cosine rounded beyond +-1, or an angle at the ends of the table: the formula itself
+    const double deg100 = acos(cosang) * (180.0 / 3.141592653589793) * 100.0;
+    m = rint(deg100);
+    if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
+  }
   const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * dd);
   double prof;
   if (m >= 0.0 && m <= 18000.0) {

@@ -22,6 +22,8 @@ int visibility_launch(const ComScene*, const ComLattice*, const double*, long lo
 size_t visibility_workspace_bytes(const DeviceScene&, long long, double);
 long long lattice_local_voxels(const ComLattice&);
 void visibility_accumulate_stats(bool on);
+int weight_histogram_mm_count(const uint16_t*, const double*, long long, const unsigned long long*, double*,
+                              unsigned long long*, cudaStream_t);
 }  // namespace com
 
 #define COM_CUDA(x)                                                            \
@@ -41,7 +43,6 @@ struct ComVolume {
   int device = 0;
   uint16_t* d_reff_mm = nullptr;  // (n)
   double* d_w = nullptr;          // (chunk)
-  uint32_t* d_nrays = nullptr;    // (chunk)
   void* d_ws = nullptr;           // candidate list of one launch, grown on demand
   size_t ws_bytes = 0;
   double* d_src = nullptr;        // Reff source grid
@@ -97,7 +98,6 @@ int com_volume_create(const ComLattice* lattice_h, int64_t chunk_voxels, double 
   cudaError_t e = cudaGetDevice(&v->device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&v->d_reff_mm), align_up(sizeof(uint16_t) * (size_t)n, 256));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&v->d_w), sizeof(double) * (size_t)chunk);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&v->d_nrays), sizeof(uint32_t) * (size_t)chunk);
   if (e != cudaSuccess) {
     com::set_error("com_volume_create: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -112,7 +112,6 @@ int com_volume_destroy(ComVolume* v) {
   if (!v) return COM_OK;
   if (v->d_reff_mm) cudaFree(v->d_reff_mm);
   if (v->d_w) cudaFree(v->d_w);
-  if (v->d_nrays) cudaFree(v->d_nrays);
   if (v->d_ws) cudaFree(v->d_ws);
   if (v->d_src) cudaFree(v->d_src);
   delete v;
@@ -198,10 +197,14 @@ int com_volume_histograms(ComVolume* v, int32_t n_channels, const ComScene* cons
   for (int c = 0; c < n_channels && rc == COM_OK; ++c) {
     for (long long lo = 0; lo < v->n && rc == COM_OK; lo += v->chunk) {
       const long long hi = std::min(v->n, lo + v->chunk);
-      rc = com::visibility_launch(scenes[c], &v->lat, nullptr, lo, hi, v->d_w, v->d_nrays, nullptr, 0, nullptr, nullptr,
+      // No per-voxel ray counts here: a voxel is visible iff its weight is non-zero (every passing ray adds a strictly
+      // positive weight - the set the Stage-2 histogram uses anyway), so the 10 B/voxel pass counts the visible voxels
+      // and Stage 1 issues one atomic per ray instead of two.
+      rc = com::visibility_launch(scenes[c], &v->lat, nullptr, lo, hi, v->d_w, nullptr, nullptr, 0, nullptr, nullptr,
                                   nullptr, 0, &stats[c], v->d_ws, v->ws_bytes, s);
       if (rc == COM_OK)
-        rc = com_weight_histogram_mm(v->d_reff_mm + lo, v->d_w, hi - lo, nullptr, hist_mm + (size_t)c * COM_MM_BINS, stream);
+        rc = com::weight_histogram_mm_count(v->d_reff_mm + lo, v->d_w, hi - lo, nullptr, hist_mm + (size_t)c * COM_MM_BINS,
+                                            reinterpret_cast<unsigned long long*>(&stats[c].visible_voxels), s);
     }
   }
   com::visibility_accumulate_stats(false);
