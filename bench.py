@@ -8,8 +8,10 @@ x 600 crystal points x 10 slits for all four channels B/C/N/O = 2.35e12 voxel-de
 STRONG scaling: the z-columns of the lattice are dealt block-cyclically over the N ranks.  A step is the whole path:
 
     Stage 1 (visibility + weight) of the rank's shard, launch by launch, each launch folded into the channel's
-    Reff-millimetre histogram  ->  ONE all-reduce(SUM) of the packed [4 x 4096 bins | counters] buffer (NCCL)
-    ->  Stage 2 (EXCIT + RECOM emissivity -> flux) from the global histograms, one launch
+    Reff-millimetre histogram  ->  the single exchange of the packed [4 x 4096 bins | counters] buffers, fused into
+    Stage 2: after one device-side barrier the Stage-2 launch itself reads the ranks' buffers over NVLink (symmetric
+    memory), sums them and evaluates EXCIT + RECOM emissivity -> flux (NCCL all-reduce + Stage 2 when symmetric memory
+    cannot be set up, and as the timed comparison)
 
 One JSON line (rank 0):
   value            tests/s with every ray's detector test evaluated individually (COM_FILTER_NO_RUN_CULL; SURVEY.md 8(d)
@@ -20,8 +22,10 @@ One JSON line (rank 0):
                    histograms + counters down; exchange; com_histograms_flux_host: profile + histograms up, flux down)
   small_grid       configs[1] (10 mm lattice, the golden-parity workload), device step and host-buffer calls
   grid_1mm         configs[2] lattice (1 mm) rate;  sweep_1000  configs[3]: 1000 profile slices from cached weights
-  roofline         dominant kernel (K1a FP32 filter) against the issue peak, instruction counts and DRAM bytes MEASURED in
-                   this run by an `ncu --metrics` pass over one channel (counters only - never times)
+  roofline         dominant kernel of the headline step (K1a FP32 every-ray filter) against the issue peak, instruction counts
+                   and DRAM bytes MEASURED in this run by an `ncu --metrics` pass over one channel (counters only - never
+                   times); roofline_production: the same for the shipped step's interval / weight-only / exact kernels
+  explicit_voxels  Stage 1 on explicit (P,3) fp64 voxels with the packed float4 copy the filter streams by cp.async.bulk
   roofline_stage2  the Stage-2 voxel pass (10 B/voxel) on this run's real weights against the measured HBM peak
   cpu_baseline     the NumPy/Qhull oracle on a bounded sample of the same lattice on this box's host cores
 """
@@ -695,7 +699,9 @@ def run_ours(args):
                     + ", com_histograms_flux_host (profile + global histograms up, fused Stage 2, flux down); scene and table "
                       "handles are created once (com_scene_create / com_tables_create) and reused",
         },
-        "gpu_launches": int(steps * (n_ch * pipe.volume.n_launches * 3 + 1)),
+        # headline step: per channel and launch the every-ray filter, the weight-only kernel, the exact kernel and the
+        # histogram pass, then one Stage-2 launch (the shipped step has interval + expand kernels instead of the filter)
+        "gpu_launches": int(steps * (n_ch * pipe.volume.n_launches * 4 + 1)),
         "wall_s_timed_region": wall_nc,
         "clocks": clocks,
         "roofline": roofline,

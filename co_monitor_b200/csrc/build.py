@@ -38,12 +38,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *srcs]
+    tmp = LIB + f".tmp{os.getpid()}"  # linked beside the target, then renamed over it: a process that has the old
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *srcs]  # library mapped keeps its (unlinked) file intact
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+    os.replace(tmp, LIB)
     with open(os.path.join(HERE, "ptxas_info.txt"), "w") as fh:
         fh.write(proc.stderr)
     return LIB

@@ -982,11 +982,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     if (P.accumulate_stats) {  // launches of one stream run one after the other: plain read-modify-write
       P.stats->candidates += written, P.stats->certain_candidates += certain, P.stats->tests += tests;
       P.stats->candidate_capacity = max((unsigned long long)P.stats->candidate_capacity, P.cand_capacity);
-      P.stats->overflow |= overflow ? 1 : 0;
+      if (overflow) atomicOr((unsigned long long*)&P.stats->overflow, 1ull);
     } else {
       P.stats->candidates = written, P.stats->certain_candidates = certain, P.stats->tests = tests;
       P.stats->candidate_capacity = P.cand_capacity;
-      P.stats->overflow = overflow ? 1 : 0;
+      if (overflow) atomicOr((unsigned long long*)&P.stats->overflow, 1ull);  // stats were zeroed before the launch
     }
   }
   if (i_first + (unsigned long long)blockIdx.x * kExactThreads >= n) return;
@@ -1018,6 +1018,10 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
     const uint2 e = i < n_front ? P.cand[i] : P.cand[P.cand_capacity - 1ull - (i - n_front)];
     const long long vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask), slit_hint = (int)(e.y >> 28);
+    if (vloc >= P.n_vox || ci >= sc.n_crystal) {  // never true for a list the filters wrote: a guard, not a code path
+      atomicOr((unsigned long long*)&P.stats->overflow, 2ull);  // (no compute-sanitizer on this pool; tests require 0)
+      continue;
+    }
     const bool certain = (e.y & kCandCertain) != 0u;  // K1a found the ray >= certain_mm inside one slit on both sides
     // ... and inside port and detector: nothing is left to test (the detector image still needs the detector hit)
     const bool certain_all = (e.y & kCandCertainAll) != 0u && sc.pix_out == nullptr;
@@ -1227,6 +1231,10 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
     const uint2 e = P.cand[i];
     const unsigned int vloc = e.x;
     const int ci = (int)(e.y & kCandCrystalMask);
+    if ((long long)vloc >= P.n_vox || ci >= sc.n_crystal) {  // guard (see exact_kernel)
+      atomicOr((unsigned long long*)&P.stats->overflow, 2ull);
+      continue;
+    }
     // voxel position (lattice.cuh: lattice_point), the index arithmetic by multiplication
     const unsigned int f = (unsigned int)P.vox_begin + vloc;
     unsigned int col = fast_div(f, P.magic_nz, nz);
@@ -1353,6 +1361,10 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __
       const int q = lo;
       const unsigned int j = r - s_c[q];
       const unsigned int vloc = s_v[q] + j;
+      if ((long long)vloc >= P.n_vox || (int)s_ci[q] >= sc.n_crystal) {  // guard (see exact_kernel)
+        atomicOr((unsigned long long*)&P.stats->overflow, 2ull);
+        continue;
+      }
       const double jf = (double)j;
       // d = c - (p + j dz): one rounding per component on top of the record's own d0
       const D3 d = {fma(-jf, dz.x, s_d0[q][0]), fma(-jf, dz.y, s_d0[q][1]), fma(-jf, dz.z, s_d0[q][2])};

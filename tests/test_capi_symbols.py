@@ -136,4 +136,4 @@ def test_driver_build_entry_point():
     own checks."""
     import __graft_entry__ as entry
 
-    entry.build()
+    entry.build(force=False)  # the driver's own call compiles from source (force defaults to True without a GPU)
