@@ -573,7 +573,7 @@ def run_ours(args):
                                          "executed_lane_instr_per_candidate", pc.get("candidates")),
         "expand_kernel_lane_instr_per_candidate": ((cnt_prod or {}).get("kernels", {}).get("expand_kernel", {}).get(
             "smsp__thread_inst_executed.sum", 0.0) / pc["candidates"]) if pc.get("candidates") else None,
-        "weight_kernel": kernel_record(cnt_prod, "weight_kernel", kt_prod_c["weight_ms"], "executed_lane_instr_per_ray",
+        "weight_kernel": kernel_record(cnt_prod, "weight_kernel_records", kt_prod_c["weight_ms"], "executed_lane_instr_per_ray",
                                        pc.get("certain_candidates")),
         "exact_kernel": kernel_record(cnt_prod, "exact_kernel", kt_prod_c["exact_ms"], "executed_lane_instr_per_candidate",
                                       (pc.get("candidates") or 0) - (pc.get("certain_candidates") or 0) or None),
