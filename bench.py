@@ -321,7 +321,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+
+        # a rank that dies must not leave the others waiting for ten minutes of box time
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=300))
     lib = _lib.load()
     warmup = max(args.warmup, 3)
     steps = args.steps
@@ -748,7 +751,7 @@ def subrecords(args, lib, device, tables, profile, flush):
     # ---- configs[1]: the golden-parity workload (10 mm lattice, 270 000 voxels x 4 channels) ----
     lat10 = quiet(CuboidMesh, 10).lattice
     sc10 = [quiet(make_channel, el, SLITS, H, L, lattice=lat10) for el in ELEMENTS]
-    p10 = VolumePipeline(lat10, sc10, tables, profile, 2.0, chunk=lat10.n_points, device=device)
+    p10 = VolumePipeline(lat10, sc10, tables, profile, 2.0, chunk=lat10.n_points, device=device, exchange="none")
     p10.volume.set_reff_resampled(src)
     ms10 = time_steps(p10.step, 20)
     st10 = p10.global_stats()
@@ -811,7 +814,7 @@ def subrecords(args, lib, device, tables, profile, flush):
     n_slices = 1000
     profs = np.stack([TwoGaussSumProfile(NE_SWEEP, list(TE_SWEEP_LO + (TE_SWEEP_HI - TE_SWEEP_LO) * (s / (n_slices - 1)))).profiles_df[
         ["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy() for s in range(n_slices)])
-    p10 = VolumePipeline(lat10, sc10, tables, profs, 2.0, chunk=lat10.n_points, device=device)
+    p10 = VolumePipeline(lat10, sc10, tables, profs, 2.0, chunk=lat10.n_points, device=device, exchange="none")
     p10.volume.set_reff_resampled(src)
     p10.stage1()
     ms_sw = time_steps(p10.stage2, 10)
@@ -839,7 +842,7 @@ def subrecords(args, lib, device, tables, profile, flush):
     if args.spacing != 1.0:
         lat1 = quiet(CuboidMesh, 1).lattice
         sc1 = [quiet(make_channel, el, SLITS, H, L, lattice=lat1) for el in ELEMENTS]
-        p1 = VolumePipeline(lat1, sc1, tables, profile, 2.0, chunk=args.chunk, device=device)
+        p1 = VolumePipeline(lat1, sc1, tables, profile, 2.0, chunk=args.chunk, device=device, exchange="none")
         p1.volume.set_reff_resampled(src)
         ms1 = time_steps(p1.step, n_rep)
         st1 = p1.global_stats()

@@ -245,7 +245,9 @@ class VolumePipeline:
                 collective call, bit-identical results on every rank.  Two buffers alternate between steps so that one
                 barrier per step is enough (a rank can only be one step ahead of a peer that is still reading);
     ``"auto"``  ``"peer"`` when symmetric memory can be set up, else ``"nccl"`` (``exchange_mode`` /
-                ``exchange_note`` say which and why)."""
+                ``exchange_note`` say which and why);
+    ``"none"``  this pipeline holds a whole (unsharded) lattice and exchanges nothing even though a process group exists
+                (a rank-local side computation inside a multi-rank job)."""
 
     def __init__(self, lattice, scenes, tables, profile: np.ndarray, concentration_percent: float = 2.0, chunk: int = 1 << 26,
                  candidate_fraction: float = 0.0, device=None, group=None, exchange: str = "nccl"):
@@ -263,7 +265,9 @@ class VolumePipeline:
             prof = prof[None]
         self.meta = _profile_meta(prof)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if exchange not in ("nccl", "peer", "auto", "none"):
+            raise ValueError("exchange must be 'nccl', 'peer', 'auto' or 'none'")
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() and exchange != "none" else 1
         n_packed = n_ch * (_lib.COM_MM_BINS + _lib.N_STATS)
         self.exchange_mode, self.exchange_note, self._symm, self._peer_ptrs, self._slot = "none", "one rank", None, None, 0
         if self.world > 1:
