@@ -1179,7 +1179,8 @@ __device__ __forceinline__ double certain_ray_weight(const DeviceScene& sc, cons
                                                      const D3 nrm, double& dd, double& m, unsigned int& n_round) {
   dd = dot(d, d);
   const double dn = dot(d, nrm);
-  const double cosang = 2.0 * (dn * dn) / dd - 1.0;
+  const double rdd = 1.0 / dd;  // one reciprocal serves the cosine and the solid angle (each within an ulp or two of the
+  const double cosang = 2.0 * (dn * dn) * rdd - 1.0;  // quotient the exact kernel forms)
   // m = rint(100 deg(acos(cos))) without the fp64 arc cosine: an FP32 estimate (good to a few 1e-3 of a unit), then the
   // decision in fp64 against the cosines of the two rounding boundaries, cos_bound[m + 1] < cos <= cos_bound[m].  Equal to
   // rounding the fp64 angle except within ~1e-12 of a boundary; rays within 1e-9 of one are counted, as before
@@ -1206,7 +1207,7 @@ __device__ __forceinline__ double certain_ray_weight(const DeviceScene& sc, cons
     m = rint(deg100);
     if (fabs(fabs(deg100 - m) - 0.5) < 1e-9) ++n_round;
   }
-  const double fraction = sc.area_pt / (4.0 * 3.141592653589793 * dd);
+  const double fraction = (sc.area_pt / (4.0 * 3.141592653589793)) * rdd;
   double prof;
   if (m >= 0.0 && m <= 18000.0) {
     prof = table[(int)m];
@@ -1294,13 +1295,12 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1w on the interval records themselves: no per-ray list is written or read for the certain rays.  A block takes 256
-// records; the thread that loaded record q prepares what its rays share - d0 = c - p of the first certain voxel (the
-// lattice formula once per record) and the crystal normal - in shared memory; ray r of the block finds its record by
-// a binary search in the scanned lengths and is d0 - j dz, j voxels further along the column.
+// K1w on the interval records themselves: no per-ray list is written or read for the certain rays.  A WARP takes 32
+// consecutive records; the lane that loaded record q prepares what its rays share - d0 = c - p of the first certain
+// voxel (the lattice formula once per record) and the crystal normal - in the warp's slice of shared memory; ray r of
+// the warp finds its record by a 5-step binary search over the lanes' scanned lengths (shuffles) and is d0 - j dz,
+// j voxels further along the column.  Warp-synchronous: no block barrier in the loop.
 __global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __grid_constant__ K1Params P) {
-  __shared__ unsigned int s_c[kWeightThreads + 1];
-  __shared__ unsigned int s_warp[kWeightThreads / 32];
   __shared__ unsigned int s_v[kWeightThreads], s_ci[kWeightThreads];
   __shared__ double s_d0[kWeightThreads][3], s_n[kWeightThreads][3];
   __shared__ unsigned int s_acc[2];
@@ -1311,23 +1311,26 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __
   const double* __restrict__ table = sc.refl_table;
   const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx, cpb = L.shard_cols_per_block > 0 ? (unsigned int)L.shard_cols_per_block : 1u;
   const bool sharded = L.shard_count > 1 && L.shard_cols_per_block > 0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wbase = (int)threadIdx.x - lane;  // wbase: first shared-memory slot of this warp
   const D3 dz = {P.dz_d[0], P.dz_d[1], P.dz_d[2]};
   unsigned int n_pass = 0, n_round = 0;
   if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
-  for (unsigned long long first = (unsigned long long)blockIdx.x * kWeightThreads; first < reserved;
-       first += (unsigned long long)gridDim.x * kWeightThreads) {
-    const unsigned long long i = first + threadIdx.x;
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * (kWeightThreads / 32);
+  for (unsigned long long first = ((unsigned long long)blockIdx.x * (kWeightThreads / 32) + (threadIdx.x >> 5)) * 32ull;
+       first < reserved; first += n_warps * 32ull) {
+    const unsigned long long i = first + lane;
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (i < reserved) rec = P.recs[i];
     const unsigned int c_len = rec.w;
-    unsigned int ic = c_len;
+    unsigned int ic = c_len;  // inclusive scan over the warp's 32 records
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned int a = __shfl_up_sync(0xffffffffu, ic, off);
       if (lane >= off) ic += a;
     }
-    if (lane == 31) s_warp[warp] = ic;
+    const unsigned int ex = ic - c_len;  // first ray of this lane's record
+    const unsigned int Tw = __shfl_sync(0xffffffffu, ic, 31);
+    __syncwarp();  // the previous batch's rays are done with the shared slots
     if (c_len) {  // what the rays of this record share
       const unsigned int vloc = rec.x + (rec.z >> 16);
       const int ci = (int)(rec.y & kCandCrystalMask);
@@ -1345,21 +1348,20 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __
       s_n[threadIdx.x][0] = nrm.x, s_n[threadIdx.x][1] = nrm.y, s_n[threadIdx.x][2] = nrm.z;
       s_v[threadIdx.x] = vloc, s_ci[threadIdx.x] = (unsigned int)ci;
     }
-    __syncthreads();
-    unsigned int bc = 0;
-    for (int q = 0; q < warp; ++q) bc += s_warp[q];
-    s_c[threadIdx.x + 1] = bc + ic;
-    if (threadIdx.x == 0) s_c[0] = 0u;
-    __syncthreads();
-    const unsigned int Tc = s_c[kWeightThreads];
-    for (unsigned int r = threadIdx.x; r < Tc; r += kWeightThreads) {
-      int lo = 0, hi = kWeightThreads - 1;  // largest q with s_c[q] <= r
-      while (lo < hi) {
+    __syncwarp();
+    for (unsigned int r0 = 0; r0 < Tw; r0 += 32u) {  // warp-uniform trip count: the shuffles need every lane
+      const unsigned int r = r0 + (unsigned int)lane;
+      int lo = 0, hi = 31;  // largest q with ex[q] <= r
+#pragma unroll
+      for (int step = 0; step < 5; ++step) {
         const int mid = (lo + hi + 1) >> 1;
-        if (s_c[mid] <= r) lo = mid; else hi = mid - 1;
+        const unsigned int e = __shfl_sync(0xffffffffu, ex, mid);
+        if (e <= r) lo = mid; else hi = mid - 1;
       }
-      const int q = lo;
-      const unsigned int j = r - s_c[q];
+      const unsigned int ex_lo = __shfl_sync(0xffffffffu, ex, lo);  // before any lane leaves: every lane is a source
+      if (r >= Tw) continue;
+      const int q = wbase + lo;
+      const unsigned int j = r - ex_lo;
       const unsigned int vloc = s_v[q] + j;
       if ((long long)vloc >= P.n_vox || (int)s_ci[q] >= sc.n_crystal) {  // guard (see exact_kernel)
         atomicOr((unsigned long long*)&P.stats->overflow, 2ull);
@@ -1385,7 +1387,6 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel_records(const __
                                          (180.0 - m / 100.0) / 2.0, w};
       }
     }
-    __syncthreads();  // the shared tables are rewritten by the next batch
   }
   for (int off = 16; off; off >>= 1) {
     n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);

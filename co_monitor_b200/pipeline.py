@@ -133,3 +133,14 @@ class ChannelPipeline:
         self.launch_geometry()
         self.launch_emissivity()
         return self.flux
+
+    def check(self) -> dict:
+        """Statistics of the last Stage-1 launch (one host synchronisation).  Raises ``ComonitorError(COM_E_OVERFLOW)`` when
+        the candidate list overflowed: the launch then accumulated nothing (the exact kernel skips an overflowed list), so
+        weights, histogram and flux of that launch are zeros, not partial sums - call this once after warm-up, or size the
+        plan with ``candidate_fraction`` from a measured count."""
+        st = self.plan.stats()
+        if st["overflow"]:
+            raise _lib.ComonitorError(_lib.COM_E_OVERFLOW, "ChannelPipeline",
+                                      f"candidate list overflow: {st['candidates']} candidates > capacity {st['candidate_capacity']}")
+        return st

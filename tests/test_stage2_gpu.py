@@ -179,6 +179,7 @@ def test_device_pipeline_matches_reference_flux(gold, reff10):
             pipe = ChannelPipeline(scene, tables, lattice, reff, 0, lattice.n_points, 2.0, stage2=mode)
             pipe.set_profile(prof)
             flux = pipe.launch().cpu().numpy()
+            assert not pipe.check()["overflow"]
             np.testing.assert_allclose(flux, gold[f"main_{el}_flux"], rtol=1e-11)
             if mode == "histogram":
                 assert float(pipe.boundary.item()) == float(gold[f"main_{el}_reff_boundary"][0])
