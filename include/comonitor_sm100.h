@@ -231,11 +231,13 @@ typedef struct ComStats {
   uint64_t candidates;      /* rays the FP32 filter sent to the fp64 stage                           */
   uint64_t passing_rays;    /* rays that pass every aperture in fp64                                 */
   uint64_t near_edge_rays;  /* fp64-decided rays within near_edge_mm of an aperture edge they were tested on */
-  uint64_t visible_voxels;  /* voxels with >= 1 passing ray                                          */
+  uint64_t visible_voxels;  /* voxels with >= 1 passing ray (counted from nrays_out: 0 when that is NULL;
+                               com_volume_histograms counts voxels with a non-zero weight instead)   */
   uint64_t candidate_capacity; /* capacity the launch ran with                                       */
-  uint64_t overflow;        /* != 0: candidates > capacity, results incomplete (COM_E_OVERFLOW)      */
-  uint64_t certain_candidates; /* candidates the FP32 filter vouched for (well inside every aperture it tested):
-                                  the fp64 stage skips those tests for them (lattice kernel only)            */
+  uint64_t overflow;        /* bit 0: candidates > capacity - the launch accumulated NOTHING (COM_E_OVERFLOW);
+                               bit 1: an index guard of the fp64 kernels fired (never expected)      */
+  uint64_t certain_candidates; /* candidates the FP32 filter vouched for (>= certain_mm inside every aperture):
+                                  only their weight is computed in fp64 (lattice kernels only)               */
   uint64_t near_band_rays;  /* like near_edge_rays at the wider near_band_mm (default 1e-4 mm)                */
   uint64_t shield_blocked_rays;   /* rays through every reference aperture but stopped by an ECRH shield (extension) */
   uint64_t segment_rejected_rays; /* rays the infinite-line test accepts but COM_PHYS_SEGMENT_CHECK rejects (extension) */
@@ -252,8 +254,9 @@ typedef struct ComRayRecord {
   double weight;     /* contribution to total_intensity_fraction */
 } ComRayRecord;
 
-/* Bytes of scratch needed by com_visibility_weights for n voxels against this scene (the candidate list: rays the FP32
- * filter could not reject; the reference materialises all P x C rays instead, simulation.py:316-321).
+/* Bytes of scratch needed by com_visibility_weights for n voxels against this scene: 256 B of counters, the candidate
+ * list (rays the FP32 filter could not reject, 8 B each; the reference materialises all P x C rays instead,
+ * simulation.py:316-321) and the column-interval filter's records (16 B each, as many slots as the candidate list).
  * candidate_fraction <= 0 selects the default (2 % of the rays, at least 1 Mi entries). */
 size_t com_visibility_workspace_bytes(const ComScene* scene, int64_t n_voxels, double candidate_fraction);
 
