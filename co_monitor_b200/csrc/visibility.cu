@@ -1,20 +1,26 @@
 // Stage 1 on sm_100a: visibility + geometric weight of every (voxel, crystal point) ray.
 //
-//   K1a  filter_kernel_lattice / filter_kernel   FP32, all P*C rays.  One warp = 32 crystal points, each lane holding
-//        the three linear forms (Xs, Ys, W) of its point's mirrored detector: a ray can only reach the detector when
-//        max(|Xs|, |Ys|) <= |W| (stage A; band eps folded into the forms).  The lattice kernel walks z-runs of the
-//        implicit lattice with forward differences (3 FADD per ray) and skips whole runs from the linearity of the
-//        forms; the explicit-voxel kernel evaluates the forms on tiles of voxels staged in shared memory.  Survivors
-//        are compacted through a per-warp shared-memory queue (ballot + popc) and, 32 at a time, tested against the
-//        periodic collimator on both sides (stage B: bounding rectangles grown by eps, so the filter can only
-//        over-accept).  What is left goes to a global candidate list, flagged "certain" when it lies well inside one
-//        slit on both sides.
-//   K1b  exact_kernel   fp64, candidates only (~0.5 % of the rays).  Restates the reference arithmetic ray by ray
-//        (simulation.py:143-173, 273-325, 344-428, 483-536, 564-577): plane hits, polygon tests for port, slit (skipped
-//        for "certain" candidates) and detector, distance, AOI with round(deg, 2), weight; accumulates per voxel.
+// FP32 front ends (find the candidate rays; can only over-accept - bounding shapes grown by eps = 5e-3 mm):
+//   interval_kernel_lattice   the shipped filter for implicit lattices.  Along a z-column every aperture test is a linear
+//                             inequality in the voxel index, so the passing voxels of a (column, crystal point) pair are a
+//                             few intervals; one 16-byte record per interval leaves the kernel, with the part of it that
+//                             is >= certain_mm inside every polygon (slit, detector and port edges) marked "certain".
+//   expand_kernel             interval records -> per-ray list of the uncertain rays (block scan + binary search).
+//   filter_kernel_lattice     every ray's detector test evaluated: forward differences along z-runs (3 FADD per ray), with
+//                             or without the run-level cull; survivors compacted through a per-warp shared-memory queue
+//                             and tested against the periodic collimator (stage B); certain rays classified on the
+//                             compacted survivors.  `value` of bench.py, and geometries the interval form does not cover.
+//   filter_kernel             explicit voxels: 512-voxel tiles in shared memory, moved there by cp.async.bulk from the
+//                             packed float4 copy (voxel_pack_kernel) or converted from the fp64 rows.
+// fp64 back ends (simulation.py:143-173, 273-325, 344-428, 483-536, 564-577):
+//   weight_kernel_records     certain rays straight from the interval records: distance, angle, weight only.
+//   weight_kernel             the same from the per-ray list (front region) of filter_kernel_lattice.
+//   exact_kernel              every other candidate: the reference arithmetic ray by ray - plane hits, polygon tests for
+//                             port, slit and detector, distance, AOI with round(deg, 2), weight; optional extensions.
+//   count_visible_kernel      visible voxels = voxels with a ray count > 0.
 //
-// The visibility mask is therefore decided in fp64 for every ray the reference could accept; the FP32 pass only
-// discards rays that miss an aperture by more than eps, and only vouches for rays that clear the slit edges by 2e-2 mm.
+// The visibility mask is therefore decided in fp64 for every ray within eps of any aperture edge; the FP32 pass only
+// discards rays that miss an aperture by more than eps, and only vouches for rays that clear every edge by certain_mm.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -624,7 +630,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32, 3) interval_kernel_lattice
   // a per-ray emit loop runs with a handful of lanes): .x launch-local index of the interval's first voxel, .y crystal
   // index | slit hint << 28, .z length | (offset of the certain part) << 16, .w length of the certain part (0: none).
   // expand_kernel turns the records into the per-ray list the fp64 kernels read, with every lane busy.
-  unsigned long long n_rays = 0, n_certain = 0;  // per lane, for the statistics
+  unsigned long long n_rays = 0;  // per lane: rays in the records it emitted (sizes the workspace after an overflow)
   auto flush = [&](int count) {
     __syncwarp();
     const uint4 mine = outq[min(lane, 63)];
@@ -649,7 +655,7 @@ __global__ void __launch_bounds__(kLatticeWarps * 32, 3) interval_kernel_lattice
                          c_len = cert ? (unsigned int)(ci_hi - ci_lo + 1) : 0u;
       outq[on + __popc(bal & lt_mask)] = make_uint4(v0 + (unsigned int)a, (unsigned int)ci | ((unsigned int)slit << 28),
                                                     len | (c_off << 16), c_len);
-      n_rays += len, n_certain += c_len;
+      n_rays += len;
     }
     on += __popc(bal);
     if (on >= 32) flush(32);
@@ -813,7 +819,6 @@ __global__ void __launch_bounds__(kLatticeWarps * 32, 3) interval_kernel_lattice
     }
   }
   if (on > 0) flush(on);
-  (void)n_certain;
   n_rays = __reduce_add_sync(0xffffffffu, (unsigned int)min(n_rays, 0xFFFFFFFFull >> 5));  // per lane < 2^27 in any launch
   if (lane == 0 && n_rays) atomicAdd(&P.counters[6], n_rays);
 }
@@ -1008,7 +1013,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   __syncthreads();
 
   const int S = sc.n_slits;
-  unsigned int n_pass = 0, n_edge = 0, n_band = 0, n_vis = 0, n_shield = 0, n_seg = 0, n_round = 0;
+  unsigned int n_pass = 0, n_edge = 0, n_band = 0, n_shield = 0, n_seg = 0, n_round = 0;
   const double kNear = sc.near_edge_mm, kBand = sc.near_band_mm;
   const bool seg_check = (sc.physics_flags & COM_PHYS_SEGMENT_CHECK) != 0;
   // FP32 edge distances decide beyond this; twice the near-edge radii so that the near-edge counts stay exact
@@ -1139,11 +1144,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   }
 
   // block-level stats
-  constexpr int kStats = 7;
+  constexpr int kStats = 6;  // visible voxels are counted by count_visible_kernel afterwards
   __shared__ unsigned int s_acc[kStats];
   if (threadIdx.x < kStats) s_acc[threadIdx.x] = 0;
   __syncthreads();
-  unsigned int mine[kStats] = {n_pass, n_edge, n_vis, n_band, n_shield, n_seg, n_round};
+  unsigned int mine[kStats] = {n_pass, n_edge, n_band, n_shield, n_seg, n_round};
 #pragma unroll
   for (int q = 0; q < kStats; ++q) {
     unsigned int v = mine[q];
@@ -1153,7 +1158,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(const __grid_const
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long* out[kStats] = {(unsigned long long*)&P.stats->passing_rays, (unsigned long long*)&P.stats->near_edge_rays,
-                                       (unsigned long long*)&P.stats->visible_voxels, (unsigned long long*)&P.stats->near_band_rays,
+                                       (unsigned long long*)&P.stats->near_band_rays,
                                        (unsigned long long*)&P.stats->shield_blocked_rays,
                                        (unsigned long long*)&P.stats->segment_rejected_rays,
                                        (unsigned long long*)&P.stats->near_rounding_rays};
@@ -1223,7 +1228,7 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
   const ComLattice& L = P.vox.lat;
   const unsigned long long total = P.counters[0] + P.counters[2];
   const unsigned long long n = total > P.cand_capacity ? 0ull : P.counters[0];  // overflow: the exact kernel reports it
-  unsigned int n_pass = 0, n_vis = 0, n_round = 0;
+  unsigned int n_pass = 0, n_round = 0;
   const double* __restrict__ table = sc.refl_table;
   const unsigned int nz = (unsigned int)L.nz, nx = (unsigned int)L.nx, cpb = L.shard_cols_per_block > 0 ? (unsigned int)L.shard_cols_per_block : 1u;
   const bool sharded = L.shard_count > 1 && L.shard_cols_per_block > 0;
@@ -1273,24 +1278,21 @@ __global__ void __launch_bounds__(kWeightThreads) weight_kernel(const __grid_con
                                        (180.0 - m / 100.0) / 2.0, w};
     }
   }
-  __shared__ unsigned int s_acc[3];
-  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
+  __shared__ unsigned int s_acc[2];
+  if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
   __syncthreads();
   for (int off = 16; off; off >>= 1) {
     n_pass += __shfl_down_sync(0xffffffffu, n_pass, off);
-    n_vis += __shfl_down_sync(0xffffffffu, n_vis, off);
     n_round += __shfl_down_sync(0xffffffffu, n_round, off);
   }
   if ((threadIdx.x & 31) == 0) {
     if (n_pass) atomicAdd(&s_acc[0], n_pass);
-    if (n_vis) atomicAdd(&s_acc[1], n_vis);
-    if (n_round) atomicAdd(&s_acc[2], n_round);
+    if (n_round) atomicAdd(&s_acc[1], n_round);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {  // (visible voxels are counted by count_visible_kernel afterwards)
     if (s_acc[0]) atomicAdd((unsigned long long*)&P.stats->passing_rays, (unsigned long long)s_acc[0]);
-    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->visible_voxels, (unsigned long long)s_acc[1]);
-    if (s_acc[2]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[2]);
+    if (s_acc[1]) atomicAdd((unsigned long long*)&P.stats->near_rounding_rays, (unsigned long long)s_acc[1]);
   }
 }
 
