@@ -230,6 +230,19 @@ def flux_from_histograms_host(tables, profiles: np.ndarray, hist: np.ndarray, co
     return flux, boundary
 
 
+def exchange_world(exchange: str, group=None) -> int:
+    """Number of ranks a ``VolumePipeline`` built with *exchange* exchanges with: the process group's size, or 1 when no
+    group exists or the pipeline is a rank-local side computation (``exchange="none"``) - such a pipeline must never issue
+    a collective: the other ranks are not there to answer it."""
+    import torch.distributed as dist
+
+    if exchange not in ("nccl", "peer", "auto", "none"):
+        raise ValueError("exchange must be 'nccl', 'peer', 'auto' or 'none'")
+    if exchange == "none" or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
 class VolumePipeline:
     """Stage 1 -> exchange -> Stage 2 of one rank's shard, device-resident and free of host synchronisation.
 
@@ -265,9 +278,7 @@ class VolumePipeline:
             prof = prof[None]
         self.meta = _profile_meta(prof)
         self.group = group
-        if exchange not in ("nccl", "peer", "auto", "none"):
-            raise ValueError("exchange must be 'nccl', 'peer', 'auto' or 'none'")
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() and exchange != "none" else 1
+        self.world = exchange_world(exchange, group)
         n_packed = n_ch * (_lib.COM_MM_BINS + _lib.N_STATS)
         self.exchange_mode, self.exchange_note, self._symm, self._peer_ptrs, self._slot = "none", "one rank", None, None, 0
         if self.world > 1:

@@ -54,6 +54,41 @@ def _worker(rank, world, port, lo, hi, out_dir):
     dist.destroy_process_group()
 
 
+def _world_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from co_monitor_b200.volume import exchange_world
+
+    assert exchange_world("nccl") == 1 and exchange_world("auto") == 1  # no process group yet
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = [exchange_world(m) for m in ("nccl", "peer", "auto", "none")]
+    with open(os.path.join(out_dir, f"world{rank}.txt"), "w") as fh:
+        fh.write(" ".join(map(str, got)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_local_pipelines_exchange_nothing(tmp_path):
+    """bench.py's rank-0-only sub-records build whole-lattice pipelines inside a multi-rank job: with exchange="none" they
+    see a world of one and issue no collective (a one-sided all-reduce there once cost ten minutes of box time)."""
+    import torch.multiprocessing as mp
+
+    from co_monitor_b200.volume import exchange_world
+
+    port = _free_port()
+    mp.start_processes(_world_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    for r in range(2):
+        assert open(tmp_path / f"world{r}.txt").read().split() == ["2", "2", "2", "1"]
+    with pytest.raises(ValueError):
+        exchange_world("ring")
+    # and bench.py asks for exactly that in every sub-record
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    body = src[src.index("def subrecords("):src.index("def explicit_voxels_record(")]
+    assert body.count("VolumePipeline(") == body.count('exchange="none"') >= 3
+
+
 def test_two_rank_reduce_equals_unsharded(tmp_path):
     import torch.multiprocessing as mp
 
