@@ -132,7 +132,7 @@ def column_intervals(t, p0, dz, nz, n_slits, C):
     return out
 
 
-@pytest.mark.parametrize("el,spacing", [("C", 10), ("N", 10), ("C", 1), ("O", 0.65)])
+@pytest.mark.parametrize("el,spacing", [("C", 10), ("N", 10), ("O", 10), ("B", 10), ("C", 1), ("N", 1), ("O", 0.65), ("B", 0.65)])
 def test_intervals_cover_the_oracle_and_certain_rays_pass(el, spacing):
     with contextlib.redirect_stdout(io.StringIO()):
         mesh = CuboidMesh(spacing)
