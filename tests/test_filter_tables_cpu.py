@@ -47,6 +47,25 @@ def certain(t, p, n_slits):
     return inner & ~(np.minimum(np.abs(Wc), np.abs(Wp)) < 1e-3)
 
 
+def certain_everywhere(t, p):
+    """Float32 restatement of visibility.cu::certain_everywhere (what the per-ray kernel adds, in its flush, for rays that are
+    certain on the collimator): inside every detector edge (scaled frame of the detector forms) and every port edge, inner
+    offsets.  Such rays skip every fp64 aperture test: only their weight is computed."""
+    F = np.float32
+    xs, ys, wd = (forms(t["det_forms"][i], p) for i in range(3))
+    sd = np.where(wd < 0, F(-1), F(1))
+    ok = np.abs(wd) > F(1e-3)
+    for ea, eb, _, ei in t["det_edges"]:
+        ok &= sd * (F(ea) * xs + (F(eb) * ys + F(ei) * wd)).astype(F) >= 0
+    pf = t["port_forms"]
+    Xq, Yq, Wq = (forms(pf[:, i], p) for i in range(3))
+    sp = np.where(Wq < 0, F(-1), F(1))
+    ok &= np.abs(Wq) - F(1e-3) >= 0
+    for ea, eb, _, ei in t["port_edges"]:
+        ok &= sp * (F(ea) * Xq + (F(eb) * Yq + F(ei) * Wq)).astype(F) >= 0
+    return ok
+
+
 def stage_b(t, p, n_slits):
     s = t["slit_forms"]
     Xc, Yc, Wc, Xp, Yp = (forms(s[:, i], p) for i in range(5))
@@ -89,6 +108,12 @@ def test_filter_never_rejects_a_ray_the_oracle_accepts(el, spacing, h, l, lo):
     through, port, det = oracle.transmission(osc, *ref.geometry, parts=True)
     assert not (cert & ~through).any(), "a ray flagged certain fails the collimator in the oracle"
     assert cert.sum() > 0.5 * (a & b).sum()
+    # ... and those that are also inside the detector's and the port's inner edges skip EVERY fp64 aperture test (they go to
+    # the weight-only kernel): the oracle must accept each of them outright, and they should be the bulk of the accepted rays
+    assert len(t["det_edges"]) >= 4 and len(t["port_edges"]) == 14
+    cert_all = cert & certain_everywhere(t, p)[:C].T
+    assert not (cert_all & ~ref.mask).any(), "a ray flagged certain-everywhere is rejected by the oracle"
+    assert cert_all.sum() > 0.5 * ref.mask.sum(), (cert_all.sum(), ref.mask.sum())
     # the filter is also selective: few rays beyond the accepted ones survive both stages
     survivors = (a & b).sum()
     assert ref.mask.sum() <= survivors <= 1.3 * ref.mask.sum() + 50
