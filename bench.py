@@ -700,6 +700,7 @@ def run_ours(args):
             "certain_candidates_weight_only": {el: stats[i]["certain_candidates"] for i, el in enumerate(ELEMENTS)},
             "near_edge_rays_1e-9mm": {el: stats[i]["near_edge_rays"] for i, el in enumerate(ELEMENTS)},
             "near_edge_rays_1e-4mm": {el: stats[i]["near_band_rays"] for i, el in enumerate(ELEMENTS)},
+            "near_rounding_rays_1e-9": {el: stats[i]["near_rounding_rays"] for i, el in enumerate(ELEMENTS)},
             "flux_excit_recom_total": {el: [float(x) for x in flux_prod[i]] for i, el in enumerate(ELEMENTS)},
             "total_emissivity": {el: f"{flux_prod[i, 2]:.2e}" for i, el in enumerate(ELEMENTS)},
             "reff_boundary_m": {el: float(boundary[i]) for i, el in enumerate(ELEMENTS)},

@@ -243,3 +243,54 @@ def test_handle_variants_of_the_host_calls(setup, reff10):
     rc = lib.com_visible_weights_host_scene(sc.handle, C.byref(ls), None, lo, hi, C.c_void_p(idx.ctypes.data),
                                             C.c_void_p(w.ctypes.data), 16, C.byref(cnt), C.byref(st))
     assert rc == _lib.COM_E_OVERFLOW and (idx[16:] == -7).all() and np.array_equal(idx[:16], a[0][:16])
+
+
+def test_full_size_volume_three_filters_agree():
+    """BASELINE configs[4] at its full size (0.65 mm lattice, 9.8e8 voxels x 600 crystal points, channel C): the shipped
+    column-interval path, the per-ray path with its run-level cull and the every-ray path decide 5.9e11 rays alike - equal
+    passing-ray and visible-voxel counts, Reff-millimetre histograms equal to rounding - and the flux is the same from any
+    of them.  Size-independent properties stand in for the oracle, which cannot run 5.9e11 rays; slabs of this lattice are
+    compared with the oracle ray by ray in tests/test_fine_lattice_parity_gpu.py."""
+    import torch
+
+    from co_monitor_b200.emissivity.engine import cached_line_tables
+    from co_monitor_b200.emissivity.kinetic_profiles import TwoGaussSumProfile
+    from co_monitor_b200.geometry.engine import make_channel
+    from co_monitor_b200.geometry.mesh_calculation import CuboidMesh
+    from co_monitor_b200.geometry.reff import source_volume
+    from co_monitor_b200.pipeline import LYMAN_ALPHA
+    from co_monitor_b200.volume import VolumePipeline
+
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~45 GB of device memory")
+    with contextlib.redirect_stdout(io.StringIO()):
+        lat = CuboidMesh(0.65).lattice
+    assert lat.n_points == 2076 * 1230 * 384
+    tables = [cached_line_tables("C", *LYMAN_ALPHA["C"], ("EXCIT", "RECOM"), None)]
+    prof = np.ascontiguousarray(TwoGaussSumProfile(NE_MAIN, TE_MAIN).profiles_df[["Reff [m]", "T_e [eV]", "n_e [m-3]"]].to_numpy())
+    results = {}
+    pipe = None
+    for name, kw in (("interval", {}), ("per_ray_cull", {"intervals": False}), ("every_ray", {"intervals": False, "run_cull": False})):
+        with contextlib.redirect_stdout(io.StringIO()):
+            scene = make_channel("C", 10, 30, 20, lattice=lat, **kw)
+        if pipe is None:
+            pipe = VolumePipeline(lat, [scene], tables, prof, 2.0)
+            pipe.volume.set_reff_resampled(source_volume(15))
+        pipe.scenes = [scene]
+        flux = pipe.step().cpu().numpy()[0, 0]
+        st = pipe.global_stats()[0]
+        assert not st["overflow"] and st["tests"] == lat.n_points * 600
+        results[name] = (st, pipe.global_hist.clone(), flux)
+        scene.close()
+    pipe.close()
+    st0, h0, f0 = results["interval"]
+    assert st0["passing_rays"] == 2341144738 and st0["visible_voxels"] == 106866897  # the counts of every run so far
+    # rays whose angle lies within 1e-9 (units of 0.01 degree) of a rounding boundary - the only ones whose rounded angle
+    # could differ from the reference's: 2.3e9 rays x 2e-9 = about five are expected, and found
+    assert st0["near_rounding_rays"] < 50
+    for name in ("per_ray_cull", "every_ray"):
+        st, h, f = results[name]
+        assert st["passing_rays"] == st0["passing_rays"] and st["visible_voxels"] == st0["visible_voxels"]
+        assert st["candidates"] >= st["passing_rays"]
+        torch.testing.assert_close(h, h0, rtol=1e-11, atol=0)
+        np.testing.assert_allclose(f, f0, rtol=1e-12)
